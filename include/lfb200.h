@@ -1,0 +1,137 @@
+/* lfb200.h — C ABI of the B200-native LatentFusion reconstruct->render hot path.
+ *
+ * The reference (NVlabs/latentfusion) is pure Python/PyTorch and has no FFI of its own
+ * (SURVEY.md §8b); the boundary a maintainer binds is therefore the set of ATen ops its hot path
+ * dispatches to.  Each entry point below names the reference call site it replaces
+ * (paths relative to /root/reference/latentfusion/).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no torch types; every pointer is a DEVICE pointer unless it
+ *     says "host"; the caller owns every buffer (the library never allocates or frees, never keeps
+ *     a pointer past the call, never synchronises) so every call is CUDA-graph capturable.
+ *   - `stream` is a cudaStream_t passed as void*.
+ *   - feature maps are dense channels-last fp32: 3-D [N][D][H][W][C], 2-D [N][H][W][C].
+ *   - return value: 0 ok; <0 invalid argument (lf_last_error() has the text); >0 a cudaError_t.
+ *   - thread safety: no global mutable state besides the thread-local last-error string.
+ */
+#ifndef LFB200_H
+#define LFB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LF_OK 0
+#define LF_EINVAL (-1)
+#define LF_EUNSUPPORTED (-2)
+
+/* Per-camera constant block consumed by the resamplers (floats). */
+#define LF_CAM_STRIDE 40
+/* object->camera layout (geometry.py:469-531, :669-685):
+ *   [0..11]  cam_to_obj rows 0..2 (3x4, row major)      geometry.py:211-213
+ *   [12..15] viewport x0, y0, width, height             geometry.py:169-175
+ *   [16..19] u0, v0, fu, fv                             geometry.py:183-197
+ *   [20] znear  [21] z_span  [22] 2/cube_size           geometry.py:249-251, :491, :684
+ * camera->object layout (geometry.py:599-654):
+ *   [0..11]  obj_to_cam rows 0..2                       geometry.py:207-209
+ *   [12..15] viewport x0, y0, width, height
+ *   [16..27] intrinsic 3x4                              geometry.py:636
+ *   [28] znear  [29] zfar  [30] cube_size */
+/* Gradient block produced by lf_resample_o2c_bwd_cam: [0..15] = d/d(cam[0..15]), [16] = d/d(znear). */
+#define LF_CAMGRAD_STRIDE 20
+
+const char* lf_version(void);
+const char* lf_last_error(void);
+/* Number of SMs of the current device (used by callers to size workspaces). */
+int lf_sm_count(void);
+
+/* ---- K1: ObjectToCameraTransform.forward  (modules/geometry.py:669-690; F.grid_sample :17) ----
+ * vol  [B][S][S][S][C]   one latent cube per object (NOT replicated per camera; models.py:493-494)
+ * cam  [N][LF_CAM_STRIDE]; camera n samples object n / (N/B)
+ * out  [N][S][S][S][C] */
+int lf_resample_o2c_fwd(const float* vol, const float* cam, float* out,
+                        int B, int N, int C, int S, void* stream);
+/* backward w.r.t. the camera block (the pose loop's gradient; replaces grid_sampler_3d_backward's
+ * grad_grid + the autograd of geometry.py:469-531,:669-685).
+ * grad_cam [N][LF_CAMGRAD_STRIDE]; workspace: lf_resample_o2c_bwd_cam_ws(N,S) floats. */
+int64_t lf_resample_o2c_bwd_cam_ws(int N, int S);
+int lf_resample_o2c_bwd_cam(const float* grad_out, const float* vol, const float* cam,
+                            float* grad_cam, float* workspace,
+                            int B, int N, int C, int S, void* stream);
+/* backward w.r.t. the volume (training). grad_vol [B][S^3][C] must be zeroed by the caller. */
+int lf_resample_o2c_bwd_vol(const float* grad_out, const float* cam, float* grad_vol,
+                            int B, int N, int C, int S, void* stream);
+
+/* ---- K2: CameraToObjectTransform.forward  (modules/geometry.py:625-657) ----
+ * vol [V][S][S][S][C] camera-frustum volumes, out [V][S][S][S][C] object cubes. */
+int lf_resample_c2o_fwd(const float* vol, const float* cam, float* out,
+                        int V, int C, int S, void* stream);
+int lf_resample_c2o_bwd_vol(const float* grad_out, const float* cam, float* grad_vol,
+                            int V, int C, int S, void* stream);
+
+/* ---- K3/K5/K6: Equalized conv + fused epilogue  (modules/equalized.py:57-64, blocks.py:152-164,
+ *      modules/__init__.py:14-15, geometry.py:704-749) ----
+ * One implicit-GEMM entry point covers every convolution on the path:
+ *   ndim=3, k=3|1 : EqualizedConv3d          (camera/object blocks, GRU gates, OutputBlock3d)
+ *   ndim=2, k=3|1 : EqualizedConv2d          (UNet2d blocks, InputBlock, heads, 2D->3D lift)
+ *   ndim=1        : "depth-collapse" GEMM of FactorProjection3d2d: x [N][S][H][W][C] -> y [N][H][W][Cout],
+ *                   S taps along depth (geometry.py:744-749); w packed [S][Cin][Cout]
+ *   ndim=-1       : "depth-expand" GEMM of FactorProjection2d3d: x [N][H][W][Cin] -> y [N][S][H][W][Cout],
+ *                   one 1x1 GEMM per depth slice (geometry.py:724-728); w packed [S][Cin][Cout], bias [S][Cout];
+ *                   PixelNorm then runs over the whole (S x Cout) group of a pixel, as the reference
+ *                   normalises before its view(); rnorm is [N*H*W].
+ * x   [N][(D)][H][W][Cin]; w packed [taps][Cin][Cout] (host repack of [Cout][Cin][k..]); bias [Cout]
+ * y = conv(x,w)*scale + bias ; act: 0 none, 1 LeakyReLU(slope) ; norm: 0 none, 1 PixelNorm over Cout
+ * y   [N][(D)][H][W][Cout]; rnorm (nullable) [positions] = sqrt(mean_c(a^2)+1e-8) saved for backward. */
+typedef struct {
+    int ndim;          /* 2 or 3: regular conv; 1: depth-collapse; -1: depth-expand (see above) */
+    int n, d, h, w;    /* input extent (d = 1 for 2-D) */
+    int cin, cout;
+    int k;             /* kernel size (1 or 3; for ndim==1: number of depth taps = d) */
+    float scale;       /* He constant sqrt(2/fan_in) */
+    int act;           /* 0 none, 1 leaky relu */
+    float slope;
+    int norm;          /* 0 none, 1 pixel norm */
+    int precision;     /* 0 = fp32 CUDA-core path (exact), 1 = tcgen05 bf16x3 split, 2 = tcgen05 bf16 */
+} lf_conv_desc;
+
+int lf_conv_fwd(const lf_conv_desc* desc, const float* x, const float* w, const float* bias,
+                float* y, float* rnorm, void* stream);
+/* du = d(loss)/d(pre-activation conv output incl. scale&bias) from gy, y (post-norm output), rnorm.
+ * PixelNorm + LeakyReLU backward fused.  Elements are y[(o*gd + t)*inner + p][c]; one norm group =
+ * all (t, c) of a fixed (o, p): gd = 1 for ordinary convs (outer = positions, inner = 1); for the
+ * depth-expand lift outer = N, gd = S, inner = H*W. */
+int lf_actnorm_bwd(const float* gy, const float* y, const float* rnorm, float* du,
+                   int64_t outer, int gd, int64_t inner, int c, int act, float slope, int norm, void* stream);
+/* dx = conv_transpose(du * scale, w): call lf_conv_fwd with the flipped/transposed packed weights
+ * (host repack) and act=norm=0.  Weight / bias gradients (training): */
+int lf_conv_bwd_weight(const lf_conv_desc* desc, const float* x, const float* du,
+                       float* grad_w_packed /* [taps][Cin][Cout], zeroed by caller */,
+                       float* grad_bias /* [Cout], zeroed by caller */, void* stream);
+
+/* ---- Interpolate (modules/__init__.py:18-33): mode 0 nearest, 1 (bi/tri)linear align_corners=False;
+ *      factor 2 (up) or -2 (down by 2).  x [N][(D)][H][W][C]. */
+int lf_interp_fwd(const float* x, float* y, int ndim, int n, int d, int h, int w, int c,
+                  int mode, int factor, void* stream);
+int lf_interp_bwd(const float* gy, float* gx, int ndim, int n, int d, int h, int w, int c,
+                  int mode, int factor, void* stream);
+
+/* ---- K4: view-axis fusion (recon/fusion.py:45-57; functional.py:47-49) ----
+ * z [B][V][P][C] -> out [B][P][C]; kind 0 max, 1 mean, 2 abs_max, 3 median (lower median, as torch). */
+int lf_fuse_pool_fwd(const float* z, float* out, int B, int V, int64_t P, int C, int kind, void* stream);
+int lf_fuse_pool_bwd(const float* gout, const float* z, float* gz, int B, int V, int64_t P, int C,
+                     int kind, void* stream);
+/* ConvGRUCell gate math (modules/gru.py:36-43), conv outputs already computed:
+ *   stage 1: update = sigmoid(u_pre), reset = sigmoid(r_pre), hr = h * reset
+ *   stage 2: h_new = h*(1-update) + o*update */
+int lf_gru_gates1(const float* u_pre, const float* r_pre, const float* h, float* update, float* hr,
+                  int64_t numel, void* stream);
+int lf_gru_gates2(const float* h, const float* update, const float* o, float* h_new,
+                  int64_t numel, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LFB200_H */

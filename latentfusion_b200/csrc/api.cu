@@ -1,0 +1,53 @@
+// C-ABI glue: version / error reporting / precision dispatch for lf_conv_fwd.
+#include "common.cuh"
+
+#include <string.h>
+
+namespace lf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static thread_local int cached_dev = -1, cached = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached = n;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+int conv_fp32_launch(const lf_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
+                     float* rnorm, cudaStream_t st);
+int conv_tc_supported(const lf_conv_desc* d);
+int conv_tc_launch(const lf_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
+                   float* rnorm, cudaStream_t st);
+
+}  // namespace lf
+
+extern "C" const char* lf_version(void) { return "lfb200 0.1.0 (sm_100a)"; }
+extern "C" const char* lf_last_error(void) { return lf::g_err; }
+extern "C" int lf_sm_count(void) { return lf::sm_count(); }
+
+extern "C" int lf_conv_fwd(const lf_conv_desc* desc, const float* x, const float* w, const float* bias,
+                           float* y, float* rnorm, void* stream) {
+    if (desc == nullptr) { lf::set_error("conv: null descriptor"); return LF_EINVAL; }
+    if (desc->precision != 0) {
+        if (!lf::conv_tc_supported(desc)) {
+            lf::set_error("conv: tcgen05 path does not support this shape (ndim=%d k=%d cin=%d cout=%d)",
+                          desc->ndim, desc->k, desc->cin, desc->cout);
+            return LF_EUNSUPPORTED;
+        }
+        return lf::conv_tc_launch(desc, x, w, bias, y, rnorm, (cudaStream_t)stream);
+    }
+    return lf::conv_fp32_launch(desc, x, w, bias, y, rnorm, (cudaStream_t)stream);
+}

@@ -1,0 +1,53 @@
+// Shared helpers for the lfb200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/lfb200.h"
+
+namespace lf {
+
+void set_error(const char* fmt, ...);
+
+#define LF_CHECK_ARG(cond, ...)                      \
+    do {                                             \
+        if (!(cond)) {                               \
+            lf::set_error(__VA_ARGS__);              \
+            return LF_EINVAL;                        \
+        }                                            \
+    } while (0)
+
+#define LF_RETURN_LAUNCH()                                            \
+    do {                                                              \
+        cudaError_t e__ = cudaGetLastError();                         \
+        if (e__ != cudaSuccess) {                                     \
+            lf::set_error("CUDA error: %s", cudaGetErrorString(e__)); \
+            return (int)e__;                                          \
+        }                                                             \
+        return LF_OK;                                                 \
+    } while (0)
+
+int sm_count();
+
+// torch.linspace(a, b, n)[i] exactly as ATen evaluates it (symmetric two-sided formula).
+__device__ __forceinline__ float linspace_at(float a, float b, int n, int i) {
+    float step = (b - a) / (float)(n - 1);
+    return (i < n / 2) ? (a + step * (float)i) : (b - step * (float)(n - 1 - i));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// streaming (write-once) 128-bit store: keep the producer's output from evicting the L2-resident cube
+__device__ __forceinline__ void st4_stream(float* p, float4 v) {
+    __stcs(reinterpret_cast<float4*>(p), v);
+}
+
+}  // namespace lf

@@ -1,0 +1,235 @@
+// Memory-bound helpers of the path: Interpolate (x2 / x0.5, nearest or linear), view-axis pooling
+// fusers, ConvGRU gate math.  All channels-last fp32; one thread per (position, 4 channels) where C%4==0.
+#include "common.cuh"
+
+namespace lf {
+
+// ---------------------------------------------------------------------------------------------
+// Interpolate (modules/__init__.py:18-33 -> F.interpolate(scale_factor, mode, align_corners=False)).
+//   nearest: src = floor(dst / scale)         linear: src = (dst + .5)/scale - .5, clamped at 0
+// Each output (or, in backward, each gradient) element is a tensor-product of <= 2 taps per axis.
+// ---------------------------------------------------------------------------------------------
+struct Tap { int i0, i1; float w0, w1; };
+
+__device__ __forceinline__ Tap axis_tap(int o, int in_size, int mode, int factor) {
+    Tap t;
+    if (factor == 1) { t.i0 = t.i1 = o; t.w0 = 1.f; t.w1 = 0.f; return t; }
+    if (mode == 0) {
+        t.i0 = factor > 0 ? o / 2 : min(o * 2, in_size - 1);
+        t.i1 = t.i0; t.w0 = 1.f; t.w1 = 0.f;
+        return t;
+    }
+    const float inv_scale = factor > 0 ? 0.5f : 2.f;
+    float src = ((float)o + 0.5f) * inv_scale - 0.5f;
+    if (src < 0.f) src = 0.f;
+    t.i0 = (int)src;
+    t.i1 = t.i0 + (t.i0 < in_size - 1 ? 1 : 0);
+    t.w1 = src - (float)t.i0;
+    t.w0 = 1.f - t.w1;
+    return t;
+}
+
+struct InterpGeom {
+    int n, d, h, w, c;          // input extent
+    int od, oh, ow;             // output extent
+    int fd, fh, fw;             // per-axis factor: 1 (untouched), 2, -2
+    int mode;
+};
+
+template <bool BWD>
+__global__ void interp_kernel(const InterpGeom g, const float* __restrict__ src, float* __restrict__ dst) {
+    // forward: src = x, dst = y (gather).  backward: src = gy, dst = gx (scatter with atomics; gx zeroed).
+    const int64_t total = (int64_t)g.n * g.od * g.oh * g.ow * g.c;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = e;
+        const int c = (int)(r % g.c); r /= g.c;
+        const int ox = (int)(r % g.ow); r /= g.ow;
+        const int oy = (int)(r % g.oh); r /= g.oh;
+        const int oz = (int)(r % g.od); r /= g.od;
+        const int n = (int)r;
+        const Tap tz = axis_tap(oz, g.d, g.mode, g.fd);
+        const Tap ty = axis_tap(oy, g.h, g.mode, g.fh);
+        const Tap tx = axis_tap(ox, g.w, g.mode, g.fw);
+        const int64_t base = (int64_t)n * g.d;
+        float accv = 0.f;
+        const float gyv = BWD ? src[e] : 0.f;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const float wz = a ? tz.w1 : tz.w0; const int iz = a ? tz.i1 : tz.i0;
+            if (wz == 0.f) continue;
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const float wy = b ? ty.w1 : ty.w0; const int iy = b ? ty.i1 : ty.i0;
+                if (wy == 0.f) continue;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const float wx = q ? tx.w1 : tx.w0; const int ix = q ? tx.i1 : tx.i0;
+                    if (wx == 0.f) continue;
+                    const int64_t idx = (((base + iz) * g.h + iy) * g.w + ix) * g.c + c;
+                    if (BWD) atomicAdd(dst + idx, gyv * (wz * wy * wx));
+                    else accv += (wz * wy * wx) * src[idx];
+                }
+            }
+        }
+        if (!BWD) dst[e] = accv;
+    }
+}
+
+static int interp_geom(InterpGeom& g, int ndim, int n, int d, int h, int w, int c, int mode, int factor) {
+    LF_CHECK_ARG(ndim == 2 || ndim == 3, "interp: ndim must be 2 or 3");
+    LF_CHECK_ARG(factor == 2 || factor == -2, "interp: factor must be 2 or -2");
+    LF_CHECK_ARG(mode == 0 || mode == 1, "interp: mode must be 0 (nearest) or 1 (linear)");
+    LF_CHECK_ARG(n > 0 && d > 0 && h > 0 && w > 0 && c > 0, "interp: bad extents");
+    g.n = n; g.d = d; g.h = h; g.w = w; g.c = c; g.mode = mode;
+    g.fd = ndim == 3 ? factor : 1; g.fh = factor; g.fw = factor;
+    auto osz = [&](int s, int f) { return f == 1 ? s : (f > 0 ? s * 2 : s / 2); };
+    g.od = osz(d, g.fd); g.oh = osz(h, g.fh); g.ow = osz(w, g.fw);
+    LF_CHECK_ARG(g.od > 0 && g.oh > 0 && g.ow > 0, "interp: output would be empty");
+    return LF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// view-axis pooling (recon/fusion.py:45-57): z[B][V][P][C] -> out[B][P][C]
+// ---------------------------------------------------------------------------------------------
+__global__ void fuse_pool_fwd_kernel(const float* __restrict__ z, float* __restrict__ out, int B, int V, int64_t PC, int kind) {
+    const int64_t total = (int64_t)B * PC;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = e / PC, r = e - b * PC;
+        const float* zp = z + b * V * PC + r;
+        float res;
+        if (kind == 0) {            // max
+            res = zp[0];
+            for (int v = 1; v < V; ++v) res = fmaxf(res, zp[(int64_t)v * PC]);
+        } else if (kind == 1) {     // mean
+            float s = 0.f;
+            for (int v = 0; v < V; ++v) s += zp[(int64_t)v * PC];
+            res = s / (float)V;
+        } else if (kind == 2) {     // abs_max (functional.py:47-49): first index of the max |.|
+            res = zp[0]; float best = fabsf(res);
+            for (int v = 1; v < V; ++v) { const float t = zp[(int64_t)v * PC]; if (fabsf(t) > best) { best = fabsf(t); res = t; } }
+        } else {                    // median: torch returns the LOWER median -> rank (V-1)/2
+            const int want = (V - 1) / 2;
+            res = zp[0];
+            for (int v = 0; v < V; ++v) {
+                const float t = zp[(int64_t)v * PC];
+                int less = 0, eq = 0;
+                for (int u = 0; u < V; ++u) { const float s2 = zp[(int64_t)u * PC]; less += s2 < t; eq += s2 == t; }
+                if (less <= want && want < less + eq) { res = t; break; }
+            }
+        }
+        out[e] = res;
+    }
+}
+
+__global__ void fuse_pool_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ z, float* __restrict__ gz,
+                                     int B, int V, int64_t PC, int kind) {
+    const int64_t total = (int64_t)B * PC;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = e / PC, r = e - b * PC;
+        const float* zp = z + b * V * PC + r;
+        float* gp = gz + b * V * PC + r;
+        const float g = gout[e];
+        if (kind == 1) {
+            for (int v = 0; v < V; ++v) gp[(int64_t)v * PC] = g / (float)V;
+            continue;
+        }
+        int sel = 0;
+        if (kind == 0) {
+            float best = zp[0];
+            for (int v = 1; v < V; ++v) { const float t = zp[(int64_t)v * PC]; if (t > best) { best = t; sel = v; } }
+        } else if (kind == 2) {
+            float best = fabsf(zp[0]);
+            for (int v = 1; v < V; ++v) { const float t = fabsf(zp[(int64_t)v * PC]); if (t > best) { best = t; sel = v; } }
+        } else {
+            const int want = (V - 1) / 2;
+            for (int v = 0; v < V; ++v) {
+                const float t = zp[(int64_t)v * PC];
+                int less = 0, eq = 0;
+                for (int u = 0; u < V; ++u) { const float s2 = zp[(int64_t)u * PC]; less += s2 < t; eq += s2 == t; }
+                if (less <= want && want < less + eq) { sel = v; break; }
+            }
+        }
+        for (int v = 0; v < V; ++v) gp[(int64_t)v * PC] = (v == sel) ? g : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ConvGRUCell gate math (modules/gru.py:36-43)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void gru_gates1_kernel(const float* __restrict__ u_pre, const float* __restrict__ r_pre,
+                                  const float* __restrict__ h, float* __restrict__ update, float* __restrict__ hr, int64_t n) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        update[e] = sigmoidf_(u_pre[e]);
+        hr[e] = h[e] * sigmoidf_(r_pre[e]);
+    }
+}
+
+__global__ void gru_gates2_kernel(const float* __restrict__ h, const float* __restrict__ update,
+                                  const float* __restrict__ o, float* __restrict__ h_new, int64_t n) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const float u = update[e];
+        h_new[e] = h[e] * (1.f - u) + o[e] * u;
+    }
+}
+
+static unsigned ew_grid(int64_t total) {
+    int64_t b = (total + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 32;
+    return (unsigned)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
+}  // namespace lf
+
+using namespace lf;
+
+extern "C" int lf_interp_fwd(const float* x, float* y, int ndim, int n, int d, int h, int w, int c,
+                             int mode, int factor, void* stream) {
+    InterpGeom g;
+    if (int e = interp_geom(g, ndim, n, d, h, w, c, mode, factor)) return e;
+    LF_CHECK_ARG(x && y, "interp: null pointer");
+    const int64_t total = (int64_t)g.n * g.od * g.oh * g.ow * g.c;
+    interp_kernel<false><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(g, x, y);
+    LF_RETURN_LAUNCH();
+}
+
+extern "C" int lf_interp_bwd(const float* gy, float* gx, int ndim, int n, int d, int h, int w, int c,
+                             int mode, int factor, void* stream) {
+    InterpGeom g;
+    if (int e = interp_geom(g, ndim, n, d, h, w, c, mode, factor)) return e;
+    LF_CHECK_ARG(gy && gx, "interp: null pointer");
+    const int64_t total = (int64_t)g.n * g.od * g.oh * g.ow * g.c;
+    cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)g.n * g.d * g.h * g.w * g.c, (cudaStream_t)stream);
+    interp_kernel<true><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(g, gy, gx);
+    LF_RETURN_LAUNCH();
+}
+
+extern "C" int lf_fuse_pool_fwd(const float* z, float* out, int B, int V, int64_t P, int C, int kind, void* stream) {
+    LF_CHECK_ARG(z && out, "fuse_pool: null pointer");
+    LF_CHECK_ARG(B > 0 && V > 0 && P > 0 && C > 0 && kind >= 0 && kind <= 3, "fuse_pool: bad arguments");
+    fuse_pool_fwd_kernel<<<ew_grid((int64_t)B * P * C), 256, 0, (cudaStream_t)stream>>>(z, out, B, V, P * C, kind);
+    LF_RETURN_LAUNCH();
+}
+
+extern "C" int lf_fuse_pool_bwd(const float* gout, const float* z, float* gz, int B, int V, int64_t P, int C,
+                                int kind, void* stream) {
+    LF_CHECK_ARG(gout && z && gz, "fuse_pool: null pointer");
+    LF_CHECK_ARG(B > 0 && V > 0 && P > 0 && C > 0 && kind >= 0 && kind <= 3, "fuse_pool: bad arguments");
+    fuse_pool_bwd_kernel<<<ew_grid((int64_t)B * P * C), 256, 0, (cudaStream_t)stream>>>(gout, z, gz, B, V, P * C, kind);
+    LF_RETURN_LAUNCH();
+}
+
+extern "C" int lf_gru_gates1(const float* u_pre, const float* r_pre, const float* h, float* update, float* hr,
+                             int64_t numel, void* stream) {
+    LF_CHECK_ARG(u_pre && r_pre && h && update && hr && numel > 0, "gru_gates1: bad arguments");
+    gru_gates1_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(u_pre, r_pre, h, update, hr, numel);
+    LF_RETURN_LAUNCH();
+}
+
+extern "C" int lf_gru_gates2(const float* h, const float* update, const float* o, float* h_new,
+                             int64_t numel, void* stream) {
+    LF_CHECK_ARG(h && update && o && h_new && numel > 0, "gru_gates2: bad arguments");
+    gru_gates2_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(h, update, o, h_new, numel);
+    LF_RETURN_LAUNCH();
+}

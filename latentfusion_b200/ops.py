@@ -1,0 +1,424 @@
+"""torch.autograd bindings of the lfb200 C ABI.
+
+Every function here enqueues hand-written sm_100a kernels from ``liblfb200.so`` on the current CUDA
+stream; none has a PyTorch/CPU fallback (CPU tensors raise).  Feature maps keep the reference's
+logical shapes (``[N,C,D,H,W]`` / ``[N,C,H,W]``) but live in channels-last memory, which is what the
+kernels index (``[N][D][H][W][C]``).
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib as L
+
+PRECISION_FP32 = 0      # exact fp32 FFMA path
+PRECISION_BF16X3 = 1    # tcgen05, bf16 hi/lo split (3 MMAs), ~2^-16 relative
+PRECISION_BF16 = 2      # tcgen05, plain bf16 operands, fp32 accumulate
+
+_default_precision = PRECISION_FP32
+
+
+def set_default_precision(p):
+    global _default_precision
+    _default_precision = int(p)
+
+
+def get_default_precision():
+    return _default_precision
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("latentfusion_b200: tensors must live on a CUDA device "
+                               "(the hot path is sm_100a CUDA only; there is no CPU fallback)")
+
+
+def _mf(ndim):
+    return torch.channels_last_3d if ndim == 5 else torch.channels_last
+
+
+def to_cl(x):
+    """Dense fp32 channels-last view/copy of a [N,C,(D),H,W] tensor (no-op when already so)."""
+    if x.dtype != torch.float32:
+        x = x.float()
+    return x.contiguous(memory_format=_mf(x.dim()))
+
+
+def empty_cl(shape, device):
+    return torch.empty(shape, device=device, dtype=torch.float32, memory_format=_mf(len(shape)))
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 / K2: voxel resamplers
+# ------------------------------------------------------------------------------------------------
+class _ResampleO2C(torch.autograd.Function):
+    """ObjectToCameraTransform (reference modules/geometry.py:669-690)."""
+
+    @staticmethod
+    def forward(ctx, vol, cam):
+        _need_cuda(vol, cam)
+        vol = to_cl(vol)
+        cam = cam.detach().float().contiguous()
+        B, C, S = vol.shape[0], vol.shape[1], vol.shape[-1]
+        N = cam.shape[0]
+        if vol.shape[2:] != (S, S, S):
+            raise ValueError(f"object volume must be a cube, got {tuple(vol.shape)}")
+        if cam.shape[1] != L.CAM_STRIDE:
+            raise ValueError("camera block must be [N, LF_CAM_STRIDE]")
+        out = empty_cl((N, C, S, S, S), vol.device)
+        L.check(L.lib().lf_resample_o2c_fwd(_p(vol), _p(cam), _p(out), B, N, C, S, _stream()), 'lf_resample_o2c_fwd')
+        ctx.save_for_backward(vol, cam)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        vol, cam = ctx.saved_tensors
+        gout = to_cl(gout)
+        B, C, S = vol.shape[0], vol.shape[1], vol.shape[-1]
+        N = cam.shape[0]
+        gvol = gcam = None
+        if ctx.needs_input_grad[0]:
+            gvol = torch.zeros_like(vol)
+            L.check(L.lib().lf_resample_o2c_bwd_vol(_p(gout), _p(cam), _p(gvol), B, N, C, S, _stream()),
+                    'lf_resample_o2c_bwd_vol')
+        if ctx.needs_input_grad[1]:
+            ws = torch.empty(L.lib().lf_resample_o2c_bwd_cam_ws(N, S), device=vol.device, dtype=torch.float32)
+            g = torch.empty(N, L.CAMGRAD_STRIDE, device=vol.device, dtype=torch.float32)
+            L.check(L.lib().lf_resample_o2c_bwd_cam(_p(gout), _p(vol), _p(cam), _p(g), _p(ws), B, N, C, S, _stream()),
+                    'lf_resample_o2c_bwd_cam')
+            gcam = torch.zeros(N, L.CAM_STRIDE, device=vol.device, dtype=torch.float32)
+            gcam[:, :16] = g[:, :16]
+            gcam[:, 20] = g[:, 16]
+        return gvol, gcam
+
+
+class _ResampleC2O(torch.autograd.Function):
+    """CameraToObjectTransform (reference modules/geometry.py:625-657).  As in the reference the
+    camera is not differentiated on this direction (its grid is built with an in-place divide)."""
+
+    @staticmethod
+    def forward(ctx, vol, cam):
+        _need_cuda(vol, cam)
+        vol = to_cl(vol)
+        cam = cam.detach().float().contiguous()
+        V, C, S = vol.shape[0], vol.shape[1], vol.shape[-1]
+        if vol.shape[2:] != (S, S, S):
+            raise ValueError(f"camera volume must be a cube, got {tuple(vol.shape)}")
+        if cam.shape != (V, L.CAM_STRIDE):
+            raise ValueError(f"batch dimension of volume ({V}) and camera ({cam.shape[0]}) must match")
+        out = empty_cl((V, C, S, S, S), vol.device)
+        L.check(L.lib().lf_resample_c2o_fwd(_p(vol), _p(cam), _p(out), V, C, S, _stream()), 'lf_resample_c2o_fwd')
+        ctx.save_for_backward(cam)
+        ctx.shape = (V, C, S)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (cam,) = ctx.saved_tensors
+        V, C, S = ctx.shape
+        gvol = None
+        if ctx.needs_input_grad[0]:
+            gout = to_cl(gout)
+            gvol = torch.zeros((V, C, S, S, S), device=gout.device, dtype=torch.float32).contiguous(
+                memory_format=torch.channels_last_3d)
+            L.check(L.lib().lf_resample_c2o_bwd_vol(_p(gout), _p(cam), _p(gvol), V, C, S, _stream()),
+                    'lf_resample_c2o_bwd_vol')
+        return gvol, None
+
+
+def resample_o2c(vol, cam_block):
+    return _ResampleO2C.apply(vol, cam_block)
+
+
+def resample_c2o(vol, cam_block):
+    return _ResampleC2O.apply(vol, cam_block)
+
+
+# ------------------------------------------------------------------------------------------------
+# K3/K5/K6: equalised convolution with fused scale/bias/LeakyReLU/PixelNorm
+# ------------------------------------------------------------------------------------------------
+KIND_CONV, KIND_COLLAPSE, KIND_EXPAND = 0, 1, 2
+
+
+def _pack_weight(weight, kind, depth):
+    """[Cout,Cin,k..] (reference layout) -> packed [taps][Cin][Cout] and its bwd-data twin."""
+    if kind == KIND_CONV:
+        nd = weight.dim() - 2
+        sp = tuple(range(2, 2 + nd))
+        taps = int(math.prod(weight.shape[2:]))
+        fwd = weight.permute(*sp, 1, 0).reshape(taps, weight.shape[1], weight.shape[0])
+        bwd = weight.flip(sp).permute(*sp, 0, 1).reshape(taps, weight.shape[0], weight.shape[1])
+    elif kind == KIND_COLLAPSE:       # weight [Cout, C*S, 1, 1], channel index c*S + d
+        cout = weight.shape[0]
+        w3 = weight.reshape(cout, -1, depth)                 # [co][c][d]
+        fwd = w3.permute(2, 1, 0)                            # [d][c][co]
+        bwd = w3.permute(2, 0, 1)                            # [d][co][c]   (an expand)
+    else:                             # weight [C*S, Cin, 1, 1], output index c*S + d
+        cin = weight.shape[1]
+        w3 = weight.reshape(-1, depth, cin)                  # [c][d][ci]
+        fwd = w3.permute(1, 2, 0)                            # [d][ci][c]
+        bwd = w3.permute(1, 0, 2)                            # [d][c][ci]   (a collapse)
+    return fwd.contiguous().float(), bwd.contiguous().float()
+
+
+def _unpack_weight_grad(gw, weight_shape, kind, depth):
+    """inverse of the forward packing for a gradient [taps][Cin][Cout]."""
+    if kind == KIND_CONV:
+        cout, cin = weight_shape[:2]
+        ks = tuple(weight_shape[2:])
+        nd = len(ks)
+        g = gw.reshape(*ks, cin, cout)
+        return g.permute(nd + 1, nd, *range(nd)).contiguous()
+    if kind == KIND_COLLAPSE:
+        cout = weight_shape[0]
+        return gw.permute(2, 1, 0).reshape(cout, -1, 1, 1).contiguous()       # [co][c][d]
+    cin = weight_shape[1]
+    return gw.permute(2, 0, 1).reshape(-1, cin, 1, 1).contiguous()            # [c][d][ci]
+
+
+def _desc(kind, nd, n, d, h, w, cin, cout, k, scale, act, slope, norm, precision):
+    ndim = {KIND_CONV: nd, KIND_COLLAPSE: 1, KIND_EXPAND: -1}[kind]
+    return L.ConvDesc(ndim, n, d, h, w, cin, cout, k, scale, int(act), slope, int(norm), int(precision))
+
+
+class _EqConv(torch.autograd.Function):
+    """y = PixelNorm(LeakyReLU(conv(x, W) * he + b)) in one kernel.
+    Reference: modules/equalized.py:57-64 + blocks.py:152-158 + modules/__init__.py:14-15."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, kind, depth, act, slope, norm, precision):
+        _need_cuda(x, weight, bias)
+        x = to_cl(x)
+        dev = x.device
+        if kind == KIND_CONV:
+            nd = x.dim() - 2
+            n, cin = x.shape[0], x.shape[1]
+            d = x.shape[2] if nd == 3 else 1
+            h, w = x.shape[-2], x.shape[-1]
+            cout, k = weight.shape[0], weight.shape[-1]
+            if weight.shape[1] != cin:
+                raise ValueError(f"conv: input has {cin} channels, weight expects {weight.shape[1]}")
+            out_shape = (n, cout, d, h, w) if nd == 3 else (n, cout, h, w)
+            gcin, gcout, positions = cin, cout, n * d * h * w
+        elif kind == KIND_COLLAPSE:
+            nd = 3
+            n, cin, d, h, w = x.shape
+            if d != depth or weight.shape[1] != cin * d:
+                raise ValueError("collapse: weight does not match [C*S] input channels")
+            cout, k = weight.shape[0], d
+            out_shape = (n, cout, h, w)
+            gcin, gcout, positions = cin, cout, n * h * w
+        else:
+            nd = 2
+            n, cin, h, w = x.shape
+            d = depth
+            cout_total = weight.shape[0]
+            if cout_total % d != 0 or weight.shape[1] != cin:
+                raise ValueError("expand: weight does not match")
+            cout, k = cout_total // d, 1
+            out_shape = (n, cout, d, h, w)
+            gcin, gcout, positions = cin, cout, n * h * w
+        fan_in = int(math.prod(weight.shape[1:]))
+        scale = math.sqrt(2.0 / fan_in)
+        wf, wb = _pack_weight(weight.detach(), kind, depth)
+        if bias is None:
+            bpk = None
+        elif kind == KIND_EXPAND:
+            bpk = bias.detach().float().reshape(cout, d).t().contiguous()
+        else:
+            bpk = bias.detach().float().contiguous()
+        y = empty_cl(out_shape, dev)
+        rnorm = torch.empty(positions, device=dev, dtype=torch.float32) if norm else None
+        desc = _desc(kind, nd, n, d, h, w, gcin, gcout, k, scale, act, slope, norm, precision)
+        L.check(L.lib().lf_conv_fwd(ctypes.byref(desc), _p(x), _p(wf), _p(bpk), _p(y), _p(rnorm), _stream()),
+                'lf_conv_fwd')
+        ctx.save_for_backward(x, y, rnorm, wb)
+        ctx.cfg = (kind, depth, act, slope, norm, precision, nd, n, d, h, w, gcin, gcout, k, scale,
+                   tuple(weight.shape), bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, y, rnorm, wb = ctx.saved_tensors
+        (kind, depth, act, slope, norm, precision, nd, n, d, h, w, cin, cout, k, scale, wshape, has_bias) = ctx.cfg
+        gy = to_cl(gy)
+        lib = L.lib()
+        if act or norm:
+            du = torch.empty_like(gy)
+            if kind == KIND_EXPAND:
+                outer, gd, inner = n, d, h * w
+            elif kind == KIND_COLLAPSE:
+                outer, gd, inner = n * h * w, 1, 1
+            else:
+                outer, gd, inner = n * d * h * w, 1, 1
+            L.check(lib.lf_actnorm_bwd(_p(gy), _p(y), _p(rnorm), _p(du), outer, gd, inner, cout,
+                                       int(act), slope, int(norm), _stream()), 'lf_actnorm_bwd')
+        else:
+            du = gy
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            # bwd-data = the same implicit GEMM with flipped/transposed weights, no epilogue
+            bkind = {KIND_CONV: KIND_CONV, KIND_COLLAPSE: KIND_EXPAND, KIND_EXPAND: KIND_COLLAPSE}[kind]
+            bnd = {KIND_CONV: nd, KIND_COLLAPSE: 2, KIND_EXPAND: 3}[kind]
+            bdesc = _desc(bkind, bnd, n, d, h, w, cout, cin, k, scale, 0, 0.0, 0, precision)
+            L.check(lib.lf_conv_fwd(ctypes.byref(bdesc), _p(du), _p(wb), None, _p(gx), None, _stream()),
+                    'lf_conv_fwd(bwd-data)')
+        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+            taps = wb.shape[0]
+            gwp = torch.zeros(taps, cin, cout, device=x.device, dtype=torch.float32)
+            gbp = torch.zeros(d if kind == KIND_EXPAND else 1, cout, device=x.device, dtype=torch.float32)
+            wdesc = _desc(kind, nd, n, d, h, w, cin, cout, k, scale, 0, 0.0, 0, 0)
+            L.check(lib.lf_conv_bwd_weight(ctypes.byref(wdesc), _p(x), _p(du), _p(gwp), _p(gbp), _stream()),
+                    'lf_conv_bwd_weight')
+            if ctx.needs_input_grad[1]:
+                gw = _unpack_weight_grad(gwp, wshape, kind, depth)
+            if has_bias and ctx.needs_input_grad[2]:
+                gb = gbp.t().reshape(-1) if kind == KIND_EXPAND else gbp.reshape(-1)
+        return gx, gw, gb, None, None, None, None, None, None
+
+
+def eq_conv(x, weight, bias, act=False, slope=0.2, norm=False, kind=KIND_CONV, depth=0, precision=None):
+    if precision is None:
+        precision = _default_precision
+    return _EqConv.apply(x, weight, bias, kind, depth, bool(act), float(slope), bool(norm), int(precision))
+
+
+# ------------------------------------------------------------------------------------------------
+# Interpolate
+# ------------------------------------------------------------------------------------------------
+class _Interp(torch.autograd.Function):
+    """modules/__init__.py:18-33 (F.interpolate, scale 2 or 0.5, nearest / (bi|tri)linear)."""
+
+    @staticmethod
+    def forward(ctx, x, mode, factor):
+        _need_cuda(x)
+        x = to_cl(x)
+        nd = x.dim() - 2
+        n, c = x.shape[:2]
+        d = x.shape[2] if nd == 3 else 1
+        h, w = x.shape[-2:]
+        f = (lambda s: s * 2) if factor > 0 else (lambda s: s // 2)
+        out_shape = (n, c, f(d), f(h), f(w)) if nd == 3 else (n, c, f(h), f(w))
+        y = empty_cl(out_shape, x.device)
+        L.check(L.lib().lf_interp_fwd(_p(x), _p(y), nd, n, d, h, w, c, mode, factor, _stream()), 'lf_interp_fwd')
+        ctx.cfg = (nd, n, d, h, w, c, mode, factor, tuple(x.shape))
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        nd, n, d, h, w, c, mode, factor, xshape = ctx.cfg
+        gy = to_cl(gy)
+        gx = empty_cl(xshape, gy.device)
+        L.check(L.lib().lf_interp_bwd(_p(gy), _p(gx), nd, n, d, h, w, c, mode, factor, _stream()), 'lf_interp_bwd')
+        return gx, None, None
+
+
+def interpolate(x, scale_factor, mode):
+    if scale_factor == 2.0:
+        factor = 2
+    elif scale_factor == 0.5:
+        factor = -2
+    else:
+        raise ValueError(f"interpolate: scale_factor {scale_factor} unsupported (2.0 or 0.5)")
+    if mode == 'nearest':
+        m = 0
+    elif mode in ('bilinear', 'trilinear', 'linear'):
+        m = 1
+    else:
+        raise ValueError(f"interpolate: mode {mode!r} unsupported")
+    return _Interp.apply(x, m, factor)
+
+
+# ------------------------------------------------------------------------------------------------
+# K4: view-axis pooling + GRU gates
+# ------------------------------------------------------------------------------------------------
+POOL_KINDS = {'max': 0, 'mean': 1, 'abs_max': 2, 'median': 3}
+
+
+class _FusePool(torch.autograd.Function):
+    """recon/fusion.py:45-57 over dim 1 of [B,V,C,D,H,W]."""
+
+    @staticmethod
+    def forward(ctx, z, kind):
+        _need_cuda(z)
+        B, V = z.shape[:2]
+        zf = to_cl(z.reshape(B * V, *z.shape[2:]))
+        C = z.shape[2]
+        P = int(math.prod(z.shape[3:]))
+        out = empty_cl((B, *z.shape[2:]), z.device)
+        L.check(L.lib().lf_fuse_pool_fwd(_p(zf), _p(out), B, V, P, C, kind, _stream()), 'lf_fuse_pool_fwd')
+        ctx.save_for_backward(zf)
+        ctx.cfg = (B, V, P, C, kind, tuple(z.shape))
+        return out.unsqueeze(1)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (zf,) = ctx.saved_tensors
+        B, V, P, C, kind, zshape = ctx.cfg
+        g = to_cl(gout.reshape(B, *zshape[2:]))
+        gz = torch.empty_like(zf)
+        L.check(L.lib().lf_fuse_pool_bwd(_p(g), _p(zf), _p(gz), B, V, P, C, kind, _stream()), 'lf_fuse_pool_bwd')
+        return gz.view(zshape), None
+
+
+def fuse_pool(z, pool_type):
+    if pool_type not in POOL_KINDS:
+        raise ValueError(f"Unknown pool_type value {pool_type}")
+    return _FusePool.apply(z, POOL_KINDS[pool_type])
+
+
+class _GruGates1(torch.autograd.Function):
+    """update = sigmoid(u_pre); hr = h * sigmoid(r_pre)   (modules/gru.py:38-40)."""
+
+    @staticmethod
+    def forward(ctx, u_pre, r_pre, h):
+        _need_cuda(u_pre, r_pre, h)
+        u_pre, r_pre, h = to_cl(u_pre), to_cl(r_pre), to_cl(h)
+        update, hr = torch.empty_like(u_pre), torch.empty_like(h)
+        L.check(L.lib().lf_gru_gates1(_p(u_pre), _p(r_pre), _p(h), _p(update), _p(hr), u_pre.numel(), _stream()),
+                'lf_gru_gates1')
+        ctx.save_for_backward(update, r_pre, h)
+        return update, hr
+
+    @staticmethod
+    def backward(ctx, g_update, g_hr):
+        update, r_pre, h = ctx.saved_tensors
+        r = torch.sigmoid(r_pre)
+        return g_update * update * (1 - update), g_hr * h * r * (1 - r), g_hr * r
+
+
+class _GruGates2(torch.autograd.Function):
+    """h_new = h*(1-update) + o*update   (modules/gru.py:41)."""
+
+    @staticmethod
+    def forward(ctx, h, update, o):
+        _need_cuda(h, update, o)
+        h, update, o = to_cl(h), to_cl(update), to_cl(o)
+        out = torch.empty_like(h)
+        L.check(L.lib().lf_gru_gates2(_p(h), _p(update), _p(o), _p(out), h.numel(), _stream()), 'lf_gru_gates2')
+        ctx.save_for_backward(h, update, o)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h, update, o = ctx.saved_tensors
+        return g * (1 - update), g * (o - h), g * update
+
+
+def gru_gates1(u_pre, r_pre, h):
+    return _GruGates1.apply(u_pre, r_pre, h)
+
+
+def gru_gates2(h, update, o):
+    return _GruGates2.apply(h, update, o)

@@ -1,0 +1,357 @@
+"""Pose estimators driving the render path.  API mirror of reference
+``latentfusion/pose/estimation.py`` (load_from_config :29-59, default_pose_loss :70-118,
+PoseEstimator :129-216, CrossEntropyPoseEstimator :298-497, GradientPoseEstimator :500-713); the
+TOML configs under the reference's ``configs/`` load unchanged.
+
+The host loops stay Python, like the reference.  Per iteration the heavy work is
+``model.render_latent_object`` (fused sm_100a kernels) and its backward to the 10 camera floats.
+"""
+import copy
+import math
+from collections import defaultdict
+from pathlib import Path
+
+import numpy as np
+import torch
+from torch import optim
+from torch.nn import functional as F
+
+from .. import three, utils
+from ..modules.geometry import Camera
+from ..observation import Observation  # noqa: F401  (re-exported for API parity)
+from . import initialization
+from . import utils as pu
+
+DEFAULT_TRANSLATION_STD = 0.01
+DEFAULT_QUATERION_STD = 10.0 / 180.0 * math.pi
+
+
+def load_from_config(config, model, **kwargs):
+    if isinstance(config, (Path, str)):
+        import toml
+        config = toml.load(config)
+    params = dict(config['args'])
+    params.update(kwargs)
+    kind = config['type']
+    if kind == 'cross_entropy':
+        return CrossEntropyPoseEstimator(model=model, **params, loss_weights=config['loss_weights'])
+    if kind == 'gradient':
+        schedules = {k: load_schedules_from_config(v) for k, v in config.get('loss_schedules', {}).items()}
+        return GradientPoseEstimator(model=model, **params, loss_weights=config['loss_weights'],
+                                     loss_schedules=schedules)
+    if kind == 'metropolis':
+        raise NotImplementedError("the Metropolis estimator is not part of the accelerated path")
+    raise ValueError(f"Unknown estimator type {kind}")
+
+
+def load_schedules_from_config(config):
+    config = dict(config)
+    kind = config.pop('type')
+    if kind == 'exponential':
+        return utils.ExponentialScheduler(**config)
+    if kind == 'linear':
+        return utils.LinearScheduler(**config)
+    raise ValueError(f"Unknown schedule type {kind}")
+
+
+def cosine_distance(x1, x2, dim=1, eps=1e-8):
+    return 1.0 - torch.cosine_similarity(x1, x2, 0 if x1.dim() == 1 else dim, eps)
+
+
+def default_pose_loss(target, z_pred_depth, z_pred_mask_logits, z_pred_camera, z_pred_latent=None,
+                      z_target_latent=None):
+    """Fitness of a batch of rendered hypotheses against one target observation: every term is a
+    per-hypothesis scalar.  Crops are pasted back into the full frame (nearest for depth, bilinear
+    for mask logits) before comparing."""
+    pred_depth, _ = z_pred_camera.uncrop(z_pred_depth, scale_mode='nearest')
+    pred_mask_logits, _ = z_pred_camera.uncrop(z_pred_mask_logits, scale_mode='bilinear')
+    pred_mask = torch.sigmoid(pred_mask_logits)
+    pred_depth = pred_depth * pred_mask
+    invalid = (target.depth == 0) & (target.mask > 0.1)        # mask says object, sensor saw nothing
+    target = target.prepare()
+
+    losses = {}
+    depth_l1 = pu.zero_invalid_pixels(
+        F.l1_loss(pred_depth, target.depth.expand_as(pred_depth), reduction='none'), invalid)
+    losses['ov_depth'] = pu.reduce_loss_mask(depth_l1, pred_mask * target.mask)
+    losses['depth'] = depth_l1.mean(dim=(1, 2, 3))
+    losses['iou'] = pu.iou_loss(pred_mask, pu.zero_invalid_pixels(target.mask, invalid))
+    losses['mask'] = F.binary_cross_entropy_with_logits(
+        pred_mask_logits, target.mask.expand_as(pred_mask), reduction='none').mean(dim=(1, 2, 3))
+    if z_pred_latent is not None and z_target_latent is not None:
+        a = z_pred_latent.reshape(z_pred_latent.shape[0], -1)
+        b = z_target_latent.reshape(z_target_latent.shape[0], -1)
+        losses['latent'] = cosine_distance(a, b.expand_as(a))
+    return losses
+
+
+def weigh_losses(loss_dict, weight_dict):
+    return {k: weight_dict.get(k, 0.0) * v for k, v in loss_dict.items()}
+
+
+class PoseEstimator:
+
+    def __init__(self, *, model, ranking_size, loss_weights, loss_func=None, return_camera_history=False,
+                 verbose=False):
+        self.model = model
+        self.ranking_size = ranking_size
+        self.loss_func = default_pose_loss if loss_func is None else loss_func
+        self.loss_weights = defaultdict(float)
+        self.loss_weights.update(loss_weights)
+        self.return_camera_history = return_camera_history
+        self.verbose = verbose
+
+    @property
+    def device(self):
+        return self.model.device
+
+    @classmethod
+    def initial_pose(cls, target_obs):
+        return initialization.estimate_initial_pose(target_obs.depth, target_obs.mask,
+                                                    target_obs.camera.intrinsic, target_obs.camera.width,
+                                                    target_obs.camera.height)
+
+    def estimate(self, z_obj, target_obs, **kwargs):
+        if len(target_obs) > 1:
+            raise ValueError("The pose can only be estiamted for one observation at a time.")
+        return self._estimate(z_obj, target_obs, **kwargs)
+
+    def _estimate(self, z_obj, target_obs, **kwargs):
+        raise NotImplementedError()
+
+    def _track_best_items(self, ranking, step, items, loss):
+        """Merge this step's (item, loss) pairs into the running top-`ranking_size` list; returns how
+        much the best loss improved."""
+        loss = loss.detach().cpu()
+        prev_best = ranking[0][1] if ranking else float('inf')
+        ranking.extend((item, err.item(), step) for item, err in zip(items, loss))
+        ranking.sort(key=lambda r: r[1])
+        del ranking[self.ranking_size:]
+        best = ranking[0][1]
+        return prev_best - best if best < prev_best else 0.0
+
+    def _render_observation(self, z_obj, camera, **kwargs):
+        z_camera = camera.zoom(None, self.model.input_size, self.model.camera_dist)
+        with torch.set_grad_enabled(kwargs.get('grad_enabled', False)):
+            pred, z_latent = self.model.render_latent_object(z_obj, z_camera.to(self.device), return_latent=True)
+            z_mask = pred['mask'].squeeze(0)
+            z_mask_logits = pred['mask_logits'].squeeze(0)
+            z_depth = camera.denormalize_depth(pred['depth'].squeeze(0)) * z_mask
+        return z_depth, z_mask_logits, z_latent, z_camera
+
+
+class CrossEntropyPoseEstimator(PoseEstimator):
+    """Cross-entropy method over (translation, log-quaternion) with a diagonal GMM proposal
+    (sklearn, host side); rendering the samples is forward-only."""
+
+    def __init__(self, *, num_samples, num_elites, num_iters, num_gmm_components, learning_rate,
+                 sample_flipped=False, init_hemisphere=False, init_upright=False,
+                 translation_std=DEFAULT_TRANSLATION_STD, quaternion_std=DEFAULT_QUATERION_STD, **kwargs):
+        super().__init__(**kwargs)
+        self.num_samples, self.num_elites, self.num_iters = num_samples, num_elites, num_iters
+        self.num_gmm_components, self.learning_rate = num_gmm_components, learning_rate
+        self.sample_flipped, self.init_upright, self.init_hemisphere = sample_flipped, init_upright, init_hemisphere
+        self.translation_std, self.quaternion_std = translation_std, quaternion_std
+        self.elite_sched = utils.ExponentialScheduler(num_samples, num_elites, num_iters)
+
+    def _estimate(self, z_obj, target_obs, **kwargs):
+        if kwargs.get('cameras', None):
+            cameras = kwargs['cameras']
+            camera_init = cameras[0]
+        else:
+            camera_init = self.initial_pose(target_obs)
+            cameras = pu.sample_cameras_with_estimate(n=self.num_gmm_components * self.num_samples,
+                                                      camera_est=camera_init, upright=self.init_upright,
+                                                      hemisphere=self.init_hemisphere)
+        gmm = self._create_gmm(self._camera_to_params(cameras).cpu())
+        target_obs = target_obs.to(self.device)
+        history, ranking, prev_gmm = [], [], None
+        for step in utils.trange(self.num_iters):
+            elites = int(self.elite_sched.get(step))
+            cameras, losses = self._refine_pose(z_obj, target_obs, prev_gmm, gmm, num_elites=elites,
+                                                camera_init=camera_init)
+            prev_gmm = gmm
+            gmm = self._create_gmm(self._camera_to_params(cameras).cpu())
+            if self._track_best_items(ranking, step, cameras, losses) > 0:
+                history.append((losses, Camera.cat([c for c, _, _ in ranking])))
+        best = Camera.cat([c for c, _, _ in ranking])
+        return (best, history) if self.return_camera_history else best
+
+    def _refine_pose(self, z_obj, target_obs, prev_gmm, gmm, num_elites, camera_init):
+        proposal = self._combined_gmm(prev_gmm, gmm, self.learning_rate) if prev_gmm is not None else gmm
+        n = self.num_samples // 4 if self.sample_flipped else self.num_samples
+        cameras = self._params_to_camera(self._sample_poses(proposal, n), camera_init=camera_init,
+                                         device=self.device)
+        if self.sample_flipped:
+            cameras = Camera.cat([cameras] + [pu.flip_camera(cameras, axis=a)
+                                              for a in ((0.0, 0.0, 1.0), (0.0, 1.0, 0.0), (1.0, 0.0, 0.0))])
+        z_target_latent = None
+        if self.loss_weights.get('latent', 0.0) > 0.0:
+            with torch.no_grad():
+                z_target_latent = self.model.compute_latent_code(target_obs, cameras[0])
+        depth, mask_logits, latent, z_camera = self._render_observation(z_obj, cameras)
+        loss_dict = self.loss_func(target_obs, depth, mask_logits, z_camera, z_pred_latent=latent,
+                                   z_target_latent=z_target_latent)
+        loss = sum(weigh_losses(loss_dict, self.loss_weights).values())
+        elite = torch.argsort(loss)[:num_elites]
+        return cameras[elite], loss[elite]
+
+    def _sample_poses(self, gmm, n):
+        params, _ = gmm.sample(n)
+        params = torch.tensor(params, dtype=torch.float32, device=self.device)
+        params[:, :3] += torch.randn_like(params[:, :3]) * self.translation_std
+        params[:, 3:] += torch.randn_like(params[:, 3:]) * self.quaternion_std
+        return params
+
+    def _create_gmm(self, params=None):
+        import sklearn.mixture
+        gmm = sklearn.mixture.GaussianMixture(covariance_type='diag', n_components=self.num_gmm_components,
+                                              reg_covar=1e-5)
+        if params is not None:
+            if torch.is_tensor(params):
+                params = params.detach().cpu().numpy()
+            gmm.fit(np.asarray(params, dtype=np.float64))     # float64: current sklearn rejects degenerate f32 fits
+        return gmm
+
+    def _combined_gmm(self, old_gmm, new_gmm, alpha):
+        if not 0.0 <= alpha <= 1.0:
+            raise ValueError("alpha must be between 0.0 and 1.0")
+        out = self._create_gmm()
+        out.weights_ = np.concatenate([(1.0 - alpha) * old_gmm.weights_, alpha * new_gmm.weights_], axis=0)
+        for name in ('means_', 'covariances_', 'precisions_cholesky_'):
+            setattr(out, name, np.concatenate([getattr(old_gmm, name), getattr(new_gmm, name)], axis=0))
+        return out
+
+    @classmethod
+    def _camera_to_params(cls, camera):
+        return torch.cat([camera.translation, camera.log_quaternion], dim=-1)
+
+    @classmethod
+    def _params_to_camera(cls, params, camera_init, device='cpu'):
+        if params.dim() == 1:
+            params = params.unsqueeze(0)
+        return Camera(intrinsic=camera_init.intrinsic.expand(params.shape[0], -1, -1).to(device), extrinsic=None,
+                      translation=params[:, :3].to(device), log_quaternion=params[:, 3:].to(device),
+                      width=camera_init.width, height=camera_init.height, z_span=camera_init.z_span).to(device)
+
+
+class GradientPoseEstimator(PoseEstimator):
+    """First-order refinement of N pose hypotheses: each hypothesis has its own optimiser and
+    ReduceLROnPlateau schedule over (log-quaternion, translation, viewport)."""
+
+    def __init__(self, *, learning_rate, num_samples, num_iters, converge_threshold, converge_patience,
+                 lr_reduce_patience=25, lr_reduce_threshold=1e-5, lr_reduce_factor=0.5, track_stats=False,
+                 loss_schedules=None, optimizer='adamw', **kwargs):
+        super().__init__(**kwargs)
+        self.learning_rate, self.num_samples, self.num_iters = learning_rate, num_samples, num_iters
+        self.optimizer = optimizer
+        self.lr_reduce_patience, self.lr_reduce_threshold = lr_reduce_patience, lr_reduce_threshold
+        self.lr_reduce_factor = lr_reduce_factor
+        self.converge_threshold, self.converge_patience = converge_threshold, converge_patience
+        self.loss_schedules = dict(loss_schedules or {})
+        self.track_stats = track_stats
+
+    def _estimate(self, z_obj, target_obs, **kwargs):
+        if 'camera' in kwargs:
+            camera = kwargs['camera']
+        else:
+            camera = pu.sample_cameras_with_estimate(n=self.num_samples, camera_est=self.initial_pose(target_obs))
+        target_obs = target_obs.to(self.device)
+        # the *zoomed* camera (viewport box around the object) is what gets optimised
+        camera = camera.zoom(None, self.model.input_size, self.model.camera_dist).to(self.device)
+        ranking = []
+        stats, history = self._optimize_camera(z_obj, target_obs, camera, iters=self.num_iters, ranking=ranking)
+        best = Camera.cat([c for c, _, _ in ranking])
+        if self.track_stats and self.return_camera_history:
+            return best, stats, history
+        if self.track_stats:
+            return best, stats
+        if self.return_camera_history:
+            return best, history
+        return best
+
+    @classmethod
+    def get_optimizer(cls, name, *args, **kwargs):
+        table = {'adamw': optim.AdamW, 'adam': optim.Adam, 'sgd': optim.SGD, 'adagrad': optim.Adagrad}
+        if name not in table:
+            raise ValueError(f"Unknow optimizer {name!r}")
+        return table[name](*args, **kwargs)
+
+    def _optimize_camera(self, z_obj, target_obs, cameras, iters, ranking):
+        params = [pu.parameterize_camera(c, optimize_viewport=True) for c in cameras]
+        optimizers, schedulers = [], []
+        for cam in params:
+            opt = self.get_optimizer(self.optimizer, [cam.log_quaternion, cam.translation, cam.viewport],
+                                     lr=self.learning_rate)
+            optimizers.append(opt)
+            schedulers.append(optim.lr_scheduler.ReduceLROnPlateau(
+                opt, patience=self.lr_reduce_patience, threshold=self.lr_reduce_threshold,
+                factor=self.lr_reduce_factor))
+        stats, history, converge_count = {}, [], 0
+        for step in utils.trange(iters):
+            for opt in optimizers:
+                opt.zero_grad()
+            cameras = Camera.cat(params)
+            z_target_latent = None
+            if self.loss_weights.get('latent', 0.0) > 0.0:
+                with torch.no_grad():
+                    z_target_latent = self.model.compute_latent_code(target_obs, cameras)
+            z_depth, z_mask, z_mask_logits, z_latent = self._render_observation(z_obj, cameras)
+            weights = copy.copy(self.loss_weights)
+            weights.update({k: s.get(step) for k, s in self.loss_schedules.items()})
+            loss_dict = self.loss_func(target_obs, z_depth, z_mask_logits, cameras, z_pred_latent=z_latent,
+                                       z_target_latent=z_target_latent)
+            optim_loss = sum(weigh_losses(loss_dict, weights).values())
+            optim_loss.mean().backward()
+            rank_loss = sum(weigh_losses(loss_dict, self.loss_weights).values()).detach()
+
+            snapshot = pu.deparameterize_camera(cameras.uncrop()).clone()
+            if self.return_camera_history:
+                history.append((rank_loss.cpu(), snapshot.cpu()))
+            delta = self._track_best_items(ranking, step, items=snapshot.cpu(), loss=rank_loss)
+
+            if self.track_stats:
+                angle = three.quaternion.angular_distance(snapshot.quaternion, target_obs.camera.quaternion).squeeze()
+                trans = torch.norm(snapshot.translation - target_obs.camera.translation, dim=1).squeeze()
+                self._record_stat_dict(stats, {
+                    **{f'{k}_loss': v.detach().cpu() for k, v in loss_dict.items()},
+                    **{f'{k}_weight': v for k, v in weights.items()},
+                    'delta': delta, 'converge_count': converge_count, 'angle_dist': angle.cpu(),
+                    'trans_dist': trans.cpu(), 'optim_loss': optim_loss.detach().cpu(),
+                    'rank_loss': rank_loss.cpu()})
+
+            rank_host = rank_loss.cpu()
+            for i, (opt, sched) in enumerate(zip(optimizers, schedulers)):
+                opt.step()
+                sched.step(rank_host[i])
+
+            if delta < self.converge_threshold:
+                converge_count += 1
+            elif delta > self.converge_threshold:
+                converge_count = 0
+            if converge_count >= self.converge_patience:
+                break
+        return stats, history
+
+    @classmethod
+    def _record_stat(cls, history, key, value):
+        value = value.detach().cpu() if torch.is_tensor(value) else torch.tensor(value)
+        value = value.squeeze().unsqueeze(0)
+        if value.dim() > 2:
+            for i in range(value.shape[-1]):
+                cls._record_stat(history, f'{key}[{i}]', value[..., i])
+        else:
+            history[key] = torch.cat((history[key], value), dim=0) if key in history else value
+
+    @classmethod
+    def _record_stat_dict(cls, history, d):
+        for key, value in d.items():
+            cls._record_stat(history, key, value)
+
+    def _render_observation(self, z_obj, camera, **kwargs):
+        """The optimised camera is already the zoomed one, so render it as is."""
+        pred, z_latent = self.model.render_latent_object(z_obj, camera.to(self.model.device), return_latent=True)
+        z_mask = pred['mask'].squeeze(0)
+        z_mask_logits = pred['mask_logits'].squeeze(0)
+        z_depth = camera.denormalize_depth(pred['depth'].squeeze(0))
+        return z_depth, z_mask, z_mask_logits, z_latent
