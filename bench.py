@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py — pose-refine render iters/sec (16 ref views, 64^3 latent, 128^2 render) on N B200s.
+
+One *step* = one body of GradientPoseEstimator._optimize_camera (reference
+pose/estimation.py:601-677) over 8 pose hypotheses per GPU: camera assembly -> render_latent_object
+forward -> default_pose_loss -> backward to the 10 camera floats -> per-hypothesis Adam + plateau
+scheduler step -> ranking.  Workload = BASELINE.json configs[1]: LF-synth(S=64, C=32), V=16, N=8,
+fp32, synthetic ShapeNet-shaped inputs, random-init weights.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (torchrun for N>1)
+  python bench.py --impl reference [...]                         the reference algorithm's CPU path
+                                                                 (oracle port: plain PyTorch ops on host cores)
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+S, C, V, N_HYP = 64, 32, 16, 8
+METRIC = "pose-refine render iters/sec (16-view, 64^3 latent, 128^2 out)"
+LOSS_WEIGHTS = dict(depth=1.0, ov_depth=0.3, iou=0.0, mask=0.0, latent=0.0)        # configs/adam_quick.toml
+EST_ARGS = dict(optimizer='adam', num_samples=N_HYP, ranking_size=N_HYP, learning_rate=0.01,
+                lr_reduce_patience=10, lr_reduce_threshold=1e-4, converge_threshold=1e-6,
+                converge_patience=10 ** 9)                                          # never stop early in a timed run
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p['hbm_gbs'], bf16_tflops=p['bf16_tflops'], bf16_tflops_sustained=p['bf16_tflops_sustained'],
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampler running during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        clocks = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+        smax = next((float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()), None)
+        return {"sm_mhz": statistics.median(clocks) if clocks else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(clocks)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload construction (identical seeds on both arms)
+# ------------------------------------------------------------------------------------------------
+def synthetic_inputs(seed=0):
+    """Reference views + masks, reference cameras, hypothesis cameras, target observation — all HOST tensors."""
+    from tests import parity_helpers as ph
+    ref_cams, dist = ph.synthetic_cameras(V, S, seed=seed + 1, perturb=False)
+    gt, _ = ph.synthetic_cameras(1, S, seed=seed + 2, perturb=False)
+    torch.manual_seed(seed + 3)
+    color = torch.rand(1, V, 3, 2 * S, 2 * S) * 2 - 1
+    yy, xx = torch.meshgrid(torch.arange(2 * S, dtype=torch.float32), torch.arange(2 * S, dtype=torch.float32), indexing='ij')
+    disc = (((yy - S + 0.5) ** 2 + (xx - S + 0.5) ** 2) <= (0.4 * 2 * S) ** 2).float()
+    mask = disc.view(1, 1, 1, 2 * S, 2 * S).expand(1, V, -1, -1, -1).contiguous()
+    yy, xx = torch.meshgrid(torch.arange(480, dtype=torch.float32), torch.arange(640, dtype=torch.float32), indexing='ij')
+    tmask = (((yy - 251.5) ** 2 + (xx - 315.4) ** 2) <= 45.0 ** 2).float().view(1, 1, 480, 640)
+    tdepth = tmask * dist
+    return dict(ref_cams=ref_cams, gt=gt, dist=dist, color=color, mask=mask, tmask=tmask, tdepth=tdepth)
+
+
+def hypothesis_cameras(gt_full, n, seed):
+    from latentfusion_b200.modules.geometry import Camera
+    from latentfusion_b200.pose import utils as pu
+    torch.manual_seed(seed)
+    return Camera.cat([pu.perturb_camera(gt_full, 0.01, 10.0 / 180.0 * math.pi) for _ in range(n)])
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference algorithm on host cores (oracle port, test infrastructure)
+# ------------------------------------------------------------------------------------------------
+def reference_iteration(O, sds, arch, z_obj, cam_dict, tdepth, tmask, n_hyp):
+    """Forward + backward of one refine iteration for n_hyp hypotheses with plain PyTorch CPU ops —
+    op for op what the reference executes (F.grid_sample, F.conv3d, ... see oracle/lf_oracle.py)."""
+    cam = O.Cam(cam_dict['intrinsic'][:n_hyp], cam_dict['log_quaternion'][:n_hyp].clone().requires_grad_(True),
+                cam_dict['translation'][:n_hyp].clone().requires_grad_(True),
+                cam_dict['viewport'][:n_hyp].clone().requires_grad_(True))
+    # the reference also back-propagates into the (frozen) network weights: keep requires_grad on them
+    total, losses, _, _ = O.refine_iteration(sds['photographer'], arch['photographer'], z_obj, cam, tdepth, tmask,
+                                             LOSS_WEIGHTS)
+    total.mean().backward()
+    return total.detach()
+
+
+def run_reference(args):
+    from oracle import lf_oracle as O
+    from tests import parity_helpers as ph
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    device = torch.device(args.ref_device)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    inp = synthetic_inputs()
+    torch.manual_seed(0)
+    _, _, _, arch, sds = ph.random_lfsynth(S, C, seed=0, device='cpu')
+    for k in sds['photographer']:
+        sds['photographer'][k] = sds['photographer'][k].to(device).requires_grad_(True)
+    torch.manual_seed(5)
+    z_obj = torch.randn(1, C, S, S, S, device=device) * 0.5      # the cube's values do not change the cost
+    hyp = hypothesis_cameras(inp['gt'].uncrop(), N_HYP, seed=7).zoom(None, 2 * S, inp['dist'])
+    cam_dict = {k: v.to(device) for k, v in ph.cam_to_dict(hyp).items()}
+    tdepth, tmask = inp['tdepth'].to(device), inp['tmask'].to(device)
+    n_sample = args.ref_hyp
+    scale = N_HYP / n_sample
+
+    def one():
+        if device.type == 'cuda':
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reference_iteration(_dev(O, device), sds, arch, z_obj, cam_dict, tdepth, tmask, n_sample)
+        if device.type == 'cuda':
+            torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    for _ in range(args.warmup):
+        one()
+    times = [one() for _ in range(args.steps)]
+    sec_per_iter = statistics.mean(times) * scale
+    value = 1.0 / sec_per_iter
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_iter * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"configs[1]: LF-synth(S={S},C={C}), V={V}, N={N_HYP} hypotheses, 128^2 render, fp32",
+                       "device": str(device)},
+            "cpu_baseline": {"value": value, "unit": "iters/s", "cores": cores if device.type == 'cpu' else 0,
+                             "kind": "port",
+                             "sample": f"fwd+bwd of {n_sample} of {N_HYP} hypotheses per step (cost is linear in N: "
+                                       f"time x{scale:g}); plain PyTorch {device.type} ops, all host threads"},
+            "e2e": {"value": value, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def _dev(O, device):
+    """The oracle builds a few constant tensors on the default device; route them for the cuda context run."""
+    if device.type == 'cuda':
+        torch.set_default_device(device)
+    return O
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from tests import parity_helpers as ph
+    from latentfusion_b200 import ops
+    from latentfusion_b200.observation import Observation
+    from latentfusion_b200.pose import estimation
+    from latentfusion_b200.recon.inference import LatentFusionModel
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (our arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    ops.set_default_precision(args.precision)
+
+    inp = synthetic_inputs()
+    sculptor, fuser, photographer, arch, sds = ph.random_lfsynth(S, C, seed=0, device=dev)
+    model = LatentFusionModel(sculptor, fuser, photographer, inp['dist'], dev)
+
+    # ---- reconstruction (once per object, untimed here; reported separately): views shard over ranks,
+    # per-view cubes are all-gathered (NCCL), the GRU recurrence runs replicated.
+    from latentfusion_b200 import dist as lfdist
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); t0.record()
+    with torch.no_grad():
+        z_obj = lfdist.build_latent_object_sharded(model, inp['ref_cams'], inp['color'], inp['mask'], rank, world)
+    t1.record(); torch.cuda.synchronize()
+    recon_ms = t0.elapsed_time(t1)
+
+    # ---- per-rank hypotheses (weak scaling: N_HYP per GPU, independent -> no per-iteration collective)
+    hyp_full = hypothesis_cameras(inp['gt'].uncrop(), N_HYP, seed=7 + rank)
+    gt_full = inp['gt'].uncrop()
+    target_host = Observation(torch.zeros(1, 3, 480, 640).pin_memory(), inp['tdepth'].pin_memory(),
+                              inp['tmask'].pin_memory(), gt_full)
+    target_dev = target_host.to(dev)
+    cfg = {'type': 'gradient', 'args': dict(EST_ARGS, num_iters=args.steps), 'loss_weights': LOSS_WEIGHTS}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        return ms
+
+    # L2 hygiene: the per-step working set (8 cubes x 268 MB activations) is >> 126 MB L2, so every
+    # iteration streams from HBM; no explicit flush is needed (stated in config.l2).
+    # ---------------- device-resident number ("value") ----------------
+    est_w = estimation.load_from_config(cfg, model, num_iters=args.warmup)
+    est_w.estimate(z_obj, target_dev, camera=hyp_full.to(dev))
+    est = estimation.load_from_config(cfg, model, num_iters=args.steps)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ops.KernelTrace.reset(enabled=not args.no_kernel_events)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    est.estimate(z_obj, target_dev, camera=hyp_full.to(dev))
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ops.KernelTrace.launches
+    ktrace = ops.KernelTrace.summary()
+    ops.KernelTrace.reset(False)
+    ms_per_step = ms_total / args.steps
+    value = world * 1000.0 / ms_per_step
+
+    # ---------------- end-to-end through the public API with HOST buffers ----------------
+    est1 = estimation.load_from_config(cfg, model, num_iters=1)
+    hyp_host = hypothesis_cameras(gt_full, N_HYP, seed=7 + rank)
+    for t in (hyp_host.intrinsic, hyp_host.log_quaternion, hyp_host.translation, hyp_host.viewport):
+        t.data = t.data.pin_memory()
+    h2d = sum(t.numel() * 4 for t in (target_host.color, target_host.depth, target_host.mask, hyp_host.intrinsic,
+                                      hyp_host.log_quaternion, hyp_host.translation, hyp_host.viewport))
+    d2h = N_HYP * 4 + N_HYP * (12 + 3 + 3 + 4) * 4       # rank losses + the ranked cameras read back per step
+    for _ in range(max(3, args.warmup)):
+        est1.estimate(z_obj, target_host, camera=hyp_host)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        best = est1.estimate(z_obj, target_host, camera=hyp_host)     # H2D of target+cameras, D2H of ranking inside
+        _ = best.translation.sum().item()
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e_value = world * 1000.0 / e2e_ms
+
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    # ---------------- roofline of the dominant kernel + per-kernel table ----------------
+    peaks = measured_peaks()
+    kernels = {}
+    for name, d in ktrace.items():
+        gbs = d['bytes'] / d['calls'] / (d['ms_avg'] * 1e-3) / 1e9 if d['bytes'] else None
+        tfs = d['flops'] / d['calls'] / (d['ms_avg'] * 1e-3) / 1e12 if d['flops'] else None
+        kernels[name] = {"calls_per_step": d['calls'] / args.steps, "ms_avg": round(d['ms_avg'], 4),
+                         "share_of_step": round(d['ms_total'] / ms_total, 4),
+                         "achieved_GBs": None if gbs is None else round(gbs, 1),
+                         "achieved_TFs": None if tfs is None else round(tfs, 2)}
+    roof = None
+    if ktrace:
+        top = max(ktrace.items(), key=lambda kv: kv[1]['ms_total'])
+        name, d = top
+        conv_like = d['flops'] > 0 and (d['flops'] / max(d['bytes'], 1)) > 50
+        if conv_like:
+            peak = peaks['bf16_tflops_sustained']
+            ach = d['flops'] / d['calls'] / (d['ms_avg'] * 1e-3) / 1e12
+            roof = {"kernel": name, "bound": "tensor", "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s",
+                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": peaks['source'] + ' bf16 sustained'}
+        else:
+            peak = peaks['hbm_gbs']
+            ach = d['bytes'] / d['calls'] / (d['ms_avg'] * 1e-3) / 1e9
+            roof = {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": peaks['source']}
+    res = kernels.get('lf_resample_o2c_fwd')
+    resample_roof = None
+    if res and res['achieved_GBs']:
+        resample_roof = {"kernel": "lf_resample_o2c_fwd", "bound": "hbm", "achieved": res['achieved_GBs'],
+                         "peak": peaks['hbm_gbs'], "unit": "GB/s", "frac": round(res['achieved_GBs'] / peaks['hbm_gbs'], 4),
+                         "algorithmic_bytes": 4 * C * S ** 3 * (1 + N_HYP)}
+
+    # ---------------- CPU baseline (oracle port, bounded sample, rank 0, N=1 only) ----------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(sds, arch, inp)
+
+    line = {"metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if args.precision == 0 else ("bf16x3" if args.precision == 1 else "bf16"),
+            "data": "synthetic",
+            "config": {"workload": f"configs[1]: LF-synth(S={S},C={C}), V={V} ref views, N={N_HYP} hypotheses/GPU, "
+                                   f"128^2 render, fp32 storage; 1 iter = render fwd + pose loss + bwd to cameras + Adam",
+                       "hypotheses_per_gpu": N_HYP, "hypothesis_renders_per_s": value * N_HYP,
+                       "parallelism": f"hypotheses sharded x{world}, z_obj replicated",
+                       "l2": "per-step working set (>2 GB of activations) exceeds the 126 MB L2; no flush needed",
+                       "precision": args.precision, "recon_ms_once_per_object": round(recon_ms, 2)},
+            "e2e": {"value": e2e_value, "unit": "iters/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h,
+                    "note": "each step = estimator.estimate(z_obj, host target obs, host cameras) for 1 iteration"},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_resample": resample_roof,
+            "kernels": kernels, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(sds, arch, inp):
+    from oracle import lf_oracle as O
+    from tests import parity_helpers as ph
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in sds['photographer'].items()}
+    torch.manual_seed(5)
+    z_obj = torch.randn(1, C, S, S, S) * 0.5
+    hyp = hypothesis_cameras(inp['gt'].uncrop(), N_HYP, seed=7).zoom(None, 2 * S, inp['dist'])
+    cam_dict = ph.cam_to_dict(hyp)
+    n_sample = 2
+    reference_iteration(O, {'photographer': sd}, arch, z_obj, cam_dict, inp['tdepth'], inp['tmask'], 1)   # warm-up
+    t0 = time.perf_counter()
+    reps = 2
+    for _ in range(reps):
+        reference_iteration(O, {'photographer': sd}, arch, z_obj, cam_dict, inp['tdepth'], inp['tmask'], n_sample)
+    sec = (time.perf_counter() - t0) / reps * (N_HYP / n_sample)
+    return {"value": 1.0 / sec, "unit": "iters/s", "cores": cores, "kind": "port",
+            "sample": f"{reps} x (fwd+bwd of {n_sample} of {N_HYP} hypotheses), time scaled x{N_HYP // n_sample}; "
+                      f"plain PyTorch CPU ops restating the reference (oracle/lf_oracle.py), {cores} threads"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--precision', type=int, default=int(os.environ.get('LFB200_PRECISION', '0')))
+    ap.add_argument('--ref-device', default='cpu', help='reference arm device (cpu = the baseline; cuda = context)')
+    ap.add_argument('--ref-hyp', type=int, default=2, help='hypotheses per reference step (bounded sample)')
+    ap.add_argument('--no-kernel-events', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

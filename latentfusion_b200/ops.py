@@ -32,6 +32,46 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class KernelTrace:
+    """Optional per-call CUDA-event trace of the library entry points (used by bench.py to measure each
+    kernel's average launch duration live, on the launching stream).  Off by default: zero overhead."""
+    enabled = False
+    records = []          # (name, start_event, end_event, algorithmic_bytes, flops)
+    launches = 0          # kernels launched through the C ABI since reset (always counted)
+
+    @classmethod
+    def reset(cls, enabled=False):
+        cls.enabled, cls.records, cls.launches = enabled, [], 0
+
+    @classmethod
+    def summary(cls):
+        """{name: dict(calls, ms_total, ms_avg, bytes, flops)}; call after a device synchronize."""
+        out = {}
+        for name, e0, e1, nbytes, flops in cls.records:
+            d = out.setdefault(name, dict(calls=0, ms_total=0.0, bytes=0, flops=0))
+            d['calls'] += 1
+            d['ms_total'] += e0.elapsed_time(e1)
+            d['bytes'] += nbytes
+            d['flops'] += flops
+        for d in out.values():
+            d['ms_avg'] = d['ms_total'] / d['calls']
+        return out
+
+
+def _call(name, fn, args, kernels=1, nbytes=0, flops=0):
+    """Invoke one C-ABI entry point, optionally bracketed by CUDA events on the current stream."""
+    KernelTrace.launches += kernels
+    if KernelTrace.enabled:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        status = fn(*args)
+        e1.record()
+        KernelTrace.records.append((name, e0, e1, nbytes, flops))
+    else:
+        status = fn(*args)
+    L.check(status, name)
+
+
 def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -76,7 +116,8 @@ class _ResampleO2C(torch.autograd.Function):
         if cam.shape[1] != L.CAM_STRIDE:
             raise ValueError("camera block must be [N, LF_CAM_STRIDE]")
         out = empty_cl((N, C, S, S, S), vol.device)
-        L.check(L.lib().lf_resample_o2c_fwd(_p(vol), _p(cam), _p(out), B, N, C, S, _stream()), 'lf_resample_o2c_fwd')
+        _call('lf_resample_o2c_fwd', L.lib().lf_resample_o2c_fwd, (_p(vol), _p(cam), _p(out), B, N, C, S, _stream()),
+              nbytes=4 * C * S ** 3 * (B + N))
         ctx.save_for_backward(vol, cam)
         return out
 
@@ -89,13 +130,14 @@ class _ResampleO2C(torch.autograd.Function):
         gvol = gcam = None
         if ctx.needs_input_grad[0]:
             gvol = torch.zeros_like(vol)
-            L.check(L.lib().lf_resample_o2c_bwd_vol(_p(gout), _p(cam), _p(gvol), B, N, C, S, _stream()),
-                    'lf_resample_o2c_bwd_vol')
+            _call('lf_resample_o2c_bwd_vol', L.lib().lf_resample_o2c_bwd_vol,
+                  (_p(gout), _p(cam), _p(gvol), B, N, C, S, _stream()), nbytes=4 * C * S ** 3 * (B + N))
         if ctx.needs_input_grad[1]:
             ws = torch.empty(L.lib().lf_resample_o2c_bwd_cam_ws(N, S), device=vol.device, dtype=torch.float32)
             g = torch.empty(N, L.CAMGRAD_STRIDE, device=vol.device, dtype=torch.float32)
-            L.check(L.lib().lf_resample_o2c_bwd_cam(_p(gout), _p(vol), _p(cam), _p(g), _p(ws), B, N, C, S, _stream()),
-                    'lf_resample_o2c_bwd_cam')
+            _call('lf_resample_o2c_bwd_cam', L.lib().lf_resample_o2c_bwd_cam,
+                  (_p(gout), _p(vol), _p(cam), _p(g), _p(ws), B, N, C, S, _stream()), kernels=2,
+                  nbytes=4 * C * S ** 3 * (B + N))
             gcam = torch.zeros(N, L.CAM_STRIDE, device=vol.device, dtype=torch.float32)
             gcam[:, :16] = g[:, :16]
             gcam[:, 20] = g[:, 16]
@@ -117,7 +159,8 @@ class _ResampleC2O(torch.autograd.Function):
         if cam.shape != (V, L.CAM_STRIDE):
             raise ValueError(f"batch dimension of volume ({V}) and camera ({cam.shape[0]}) must match")
         out = empty_cl((V, C, S, S, S), vol.device)
-        L.check(L.lib().lf_resample_c2o_fwd(_p(vol), _p(cam), _p(out), V, C, S, _stream()), 'lf_resample_c2o_fwd')
+        _call('lf_resample_c2o_fwd', L.lib().lf_resample_c2o_fwd, (_p(vol), _p(cam), _p(out), V, C, S, _stream()),
+              nbytes=4 * C * S ** 3 * 2 * V)
         ctx.save_for_backward(cam)
         ctx.shape = (V, C, S)
         return out
@@ -131,8 +174,8 @@ class _ResampleC2O(torch.autograd.Function):
             gout = to_cl(gout)
             gvol = torch.zeros((V, C, S, S, S), device=gout.device, dtype=torch.float32).contiguous(
                 memory_format=torch.channels_last_3d)
-            L.check(L.lib().lf_resample_c2o_bwd_vol(_p(gout), _p(cam), _p(gvol), V, C, S, _stream()),
-                    'lf_resample_c2o_bwd_vol')
+            _call('lf_resample_c2o_bwd_vol', L.lib().lf_resample_c2o_bwd_vol,
+                  (_p(gout), _p(cam), _p(gvol), V, C, S, _stream()), nbytes=4 * C * S ** 3 * 2 * V)
         return gvol, None
 
 
@@ -191,6 +234,11 @@ def _desc(kind, nd, n, d, h, w, cin, cout, k, scale, act, slope, norm, precision
     return L.ConvDesc(ndim, n, d, h, w, cin, cout, k, scale, int(act), slope, int(norm), int(precision))
 
 
+def _conv_name(kind, nd, k, what):
+    tag = {KIND_CONV: f'conv{nd}d_k{k}', KIND_COLLAPSE: 'collapse', KIND_EXPAND: 'expand'}[kind]
+    return f'lf_conv_{what}[{tag}]'
+
+
 class _EqConv(torch.autograd.Function):
     """y = PixelNorm(LeakyReLU(conv(x, W) * he + b)) in one kernel.
     Reference: modules/equalized.py:57-64 + blocks.py:152-158 + modules/__init__.py:14-15."""
@@ -240,8 +288,11 @@ class _EqConv(torch.autograd.Function):
         y = empty_cl(out_shape, dev)
         rnorm = torch.empty(positions, device=dev, dtype=torch.float32) if norm else None
         desc = _desc(kind, nd, n, d, h, w, gcin, gcout, k, scale, act, slope, norm, precision)
-        L.check(L.lib().lf_conv_fwd(ctypes.byref(desc), _p(x), _p(wf), _p(bpk), _p(y), _p(rnorm), _stream()),
-                'lf_conv_fwd')
+        taps = wf.shape[0]
+        _call(_conv_name(kind, nd, k, 'fwd'), L.lib().lf_conv_fwd,
+              (ctypes.byref(desc), _p(x), _p(wf), _p(bpk), _p(y), _p(rnorm), _stream()),
+              kernels=2 if (norm and (kind == KIND_EXPAND or gcout > 64)) else 1,
+              nbytes=4 * (x.numel() + y.numel()), flops=2 * positions * taps * gcin * gcout)
         ctx.save_for_backward(x, y, rnorm, wb)
         ctx.cfg = (kind, depth, act, slope, norm, precision, nd, n, d, h, w, gcin, gcout, k, scale,
                    tuple(weight.shape), bias is not None)
@@ -261,8 +312,9 @@ class _EqConv(torch.autograd.Function):
                 outer, gd, inner = n * h * w, 1, 1
             else:
                 outer, gd, inner = n * d * h * w, 1, 1
-            L.check(lib.lf_actnorm_bwd(_p(gy), _p(y), _p(rnorm), _p(du), outer, gd, inner, cout,
-                                       int(act), slope, int(norm), _stream()), 'lf_actnorm_bwd')
+            _call('lf_actnorm_bwd', lib.lf_actnorm_bwd, (_p(gy), _p(y), _p(rnorm), _p(du), outer, gd, inner, cout,
+                                                        int(act), slope, int(norm), _stream()),
+                  nbytes=4 * 3 * gy.numel())
         else:
             du = gy
         gx = gw = gb = None
@@ -272,15 +324,17 @@ class _EqConv(torch.autograd.Function):
             bkind = {KIND_CONV: KIND_CONV, KIND_COLLAPSE: KIND_EXPAND, KIND_EXPAND: KIND_COLLAPSE}[kind]
             bnd = {KIND_CONV: nd, KIND_COLLAPSE: 2, KIND_EXPAND: 3}[kind]
             bdesc = _desc(bkind, bnd, n, d, h, w, cout, cin, k, scale, 0, 0.0, 0, precision)
-            L.check(lib.lf_conv_fwd(ctypes.byref(bdesc), _p(du), _p(wb), None, _p(gx), None, _stream()),
-                    'lf_conv_fwd(bwd-data)')
+            _call(_conv_name(kind, nd, k, 'bwd_data'), lib.lf_conv_fwd,
+                  (ctypes.byref(bdesc), _p(du), _p(wb), None, _p(gx), None, _stream()),
+                  nbytes=4 * (du.numel() + gx.numel()),
+                  flops=2 * (n * h * w * (d if kind == KIND_CONV else 1)) * wb.shape[0] * cin * cout)
         if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
             taps = wb.shape[0]
             gwp = torch.zeros(taps, cin, cout, device=x.device, dtype=torch.float32)
             gbp = torch.zeros(d if kind == KIND_EXPAND else 1, cout, device=x.device, dtype=torch.float32)
             wdesc = _desc(kind, nd, n, d, h, w, cin, cout, k, scale, 0, 0.0, 0, 0)
-            L.check(lib.lf_conv_bwd_weight(ctypes.byref(wdesc), _p(x), _p(du), _p(gwp), _p(gbp), _stream()),
-                    'lf_conv_bwd_weight')
+            _call('lf_conv_bwd_weight', lib.lf_conv_bwd_weight,
+                  (ctypes.byref(wdesc), _p(x), _p(du), _p(gwp), _p(gbp), _stream()))
             if ctx.needs_input_grad[1]:
                 gw = _unpack_weight_grad(gwp, wshape, kind, depth)
             if has_bias and ctx.needs_input_grad[2]:
@@ -311,7 +365,8 @@ class _Interp(torch.autograd.Function):
         f = (lambda s: s * 2) if factor > 0 else (lambda s: s // 2)
         out_shape = (n, c, f(d), f(h), f(w)) if nd == 3 else (n, c, f(h), f(w))
         y = empty_cl(out_shape, x.device)
-        L.check(L.lib().lf_interp_fwd(_p(x), _p(y), nd, n, d, h, w, c, mode, factor, _stream()), 'lf_interp_fwd')
+        _call('lf_interp_fwd', L.lib().lf_interp_fwd, (_p(x), _p(y), nd, n, d, h, w, c, mode, factor, _stream()),
+              nbytes=4 * (x.numel() + y.numel()))
         ctx.cfg = (nd, n, d, h, w, c, mode, factor, tuple(x.shape))
         return y
 
@@ -320,7 +375,8 @@ class _Interp(torch.autograd.Function):
         nd, n, d, h, w, c, mode, factor, xshape = ctx.cfg
         gy = to_cl(gy)
         gx = empty_cl(xshape, gy.device)
-        L.check(L.lib().lf_interp_bwd(_p(gy), _p(gx), nd, n, d, h, w, c, mode, factor, _stream()), 'lf_interp_bwd')
+        _call('lf_interp_bwd', L.lib().lf_interp_bwd, (_p(gy), _p(gx), nd, n, d, h, w, c, mode, factor, _stream()),
+              nbytes=4 * (gy.numel() + gx.numel()))
         return gx, None, None
 
 
@@ -357,7 +413,8 @@ class _FusePool(torch.autograd.Function):
         C = z.shape[2]
         P = int(math.prod(z.shape[3:]))
         out = empty_cl((B, *z.shape[2:]), z.device)
-        L.check(L.lib().lf_fuse_pool_fwd(_p(zf), _p(out), B, V, P, C, kind, _stream()), 'lf_fuse_pool_fwd')
+        _call('lf_fuse_pool_fwd', L.lib().lf_fuse_pool_fwd, (_p(zf), _p(out), B, V, P, C, kind, _stream()),
+              nbytes=4 * (zf.numel() + out.numel()))
         ctx.save_for_backward(zf)
         ctx.cfg = (B, V, P, C, kind, tuple(z.shape))
         return out.unsqueeze(1)
@@ -368,7 +425,7 @@ class _FusePool(torch.autograd.Function):
         B, V, P, C, kind, zshape = ctx.cfg
         g = to_cl(gout.reshape(B, *zshape[2:]))
         gz = torch.empty_like(zf)
-        L.check(L.lib().lf_fuse_pool_bwd(_p(g), _p(zf), _p(gz), B, V, P, C, kind, _stream()), 'lf_fuse_pool_bwd')
+        _call('lf_fuse_pool_bwd', L.lib().lf_fuse_pool_bwd, (_p(g), _p(zf), _p(gz), B, V, P, C, kind, _stream()))
         return gz.view(zshape), None
 
 
@@ -386,8 +443,8 @@ class _GruGates1(torch.autograd.Function):
         _need_cuda(u_pre, r_pre, h)
         u_pre, r_pre, h = to_cl(u_pre), to_cl(r_pre), to_cl(h)
         update, hr = torch.empty_like(u_pre), torch.empty_like(h)
-        L.check(L.lib().lf_gru_gates1(_p(u_pre), _p(r_pre), _p(h), _p(update), _p(hr), u_pre.numel(), _stream()),
-                'lf_gru_gates1')
+        _call('lf_gru_gates1', L.lib().lf_gru_gates1,
+              (_p(u_pre), _p(r_pre), _p(h), _p(update), _p(hr), u_pre.numel(), _stream()))
         ctx.save_for_backward(update, r_pre, h)
         return update, hr
 
@@ -406,7 +463,7 @@ class _GruGates2(torch.autograd.Function):
         _need_cuda(h, update, o)
         h, update, o = to_cl(h), to_cl(update), to_cl(o)
         out = torch.empty_like(h)
-        L.check(L.lib().lf_gru_gates2(_p(h), _p(update), _p(o), _p(out), h.numel(), _stream()), 'lf_gru_gates2')
+        _call('lf_gru_gates2', L.lib().lf_gru_gates2, (_p(h), _p(update), _p(o), _p(out), h.numel(), _stream()))
         ctx.save_for_backward(h, update, o)
         return out
 

@@ -306,13 +306,14 @@ class GradientPoseEstimator(PoseEstimator):
             rank_loss = sum(weigh_losses(loss_dict, self.loss_weights).values()).detach()
 
             snapshot = pu.deparameterize_camera(cameras.uncrop()).clone()
+            if self.track_stats:     # before snapshot.cpu(): nn.Module.cpu() moves the camera in place
+                angle = three.quaternion.angular_distance(snapshot.quaternion, target_obs.camera.quaternion).squeeze()
+                trans = torch.norm(snapshot.translation - target_obs.camera.translation, dim=1).squeeze()
             if self.return_camera_history:
                 history.append((rank_loss.cpu(), snapshot.cpu()))
             delta = self._track_best_items(ranking, step, items=snapshot.cpu(), loss=rank_loss)
 
             if self.track_stats:
-                angle = three.quaternion.angular_distance(snapshot.quaternion, target_obs.camera.quaternion).squeeze()
-                trans = torch.norm(snapshot.translation - target_obs.camera.translation, dim=1).squeeze()
                 self._record_stat_dict(stats, {
                     **{f'{k}_loss': v.detach().cpu() for k, v in loss_dict.items()},
                     **{f'{k}_weight': v for k, v in weights.items()},

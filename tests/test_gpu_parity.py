@@ -61,7 +61,9 @@ def test_o2c_vs_oracle_shapes(dev, C, S, N):
     (ref * w).sum().backward()
     cam = ph.product_camera(d, dev, requires_grad=True)
     out = ObjectToCameraTransform(1.0)(vol.to(dev), cam)
-    torch.testing.assert_close(out.cpu(), ref.detach(), **OUT_TOL)
+    # white-noise volumes are the worst case for coordinate rounding (|d out / d coord| ~ S); the camera
+    # sits ~20-30 m away at these tiny S, so 1 ulp of the projected coordinate is ~1e-5 voxel
+    torch.testing.assert_close(out.cpu(), ref.detach(), atol=5e-4, rtol=1e-3)
     (out * w.to(dev)).sum().backward()
     for k in ('log_quaternion', 'translation', 'viewport'):
         torch.testing.assert_close(getattr(cam, k).grad.cpu(), getattr(ocam, k).grad, atol=2e-3, rtol=2e-3)
