@@ -134,26 +134,52 @@ __device__ __forceinline__ CornerOfs corner_offsets(const Samp& s, int S, int C)
 // ------------------------------------------------------------------------------------------
 // forward: one lane-group (LPV lanes) per output voxel
 // ------------------------------------------------------------------------------------------
+// Output voxels are walked brick by brick (BX x BY x BZ voxels per CTA) so that the 8-corner reuse
+// between neighbouring output voxels is served by L1 instead of L2: a b^3 brick touches ~(b+1)^3 input
+// voxels for 8*b^3 corner reads.
+constexpr int BX = 8, BY = 8, BZ = 4;          // 256 voxels per CTA
+
+struct BrickGrid {
+    int nbx, nby, nbz;                          // bricks per axis
+    __host__ __device__ int per_cam() const { return nbx * nby * nbz; }
+};
+
+__host__ __device__ inline BrickGrid brick_grid(int S, int bx, int by, int bz) {
+    BrickGrid g;
+    g.nbx = (S + bx - 1) / bx; g.nby = (S + by - 1) / by; g.nbz = (S + bz - 1) / bz;
+    return g;
+}
+
 template <int MODE, int VEC>
 __global__ void __launch_bounds__(256)
 resample_fwd_kernel(const float* __restrict__ vol, const float* __restrict__ cam, float* __restrict__ out,
                     int views_per_obj, int N, int C, int S, int lpv_log2) {
     const int64_t S3 = (int64_t)S * S * S;
-    const int64_t total = (int64_t)N * S3;
+    const BrickGrid bg = brick_grid(S, BX, BY, BZ);
+    const int n = blockIdx.x / bg.per_cam();
+    int b = blockIdx.x - n * bg.per_cam();
+    const int bi = b % bg.nbx; b /= bg.nbx;
+    const int bj = b % bg.nby; const int bk = b / bg.nby;
     const int lpv = 1 << lpv_log2;
-    const int64_t gthread = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int sub = (int)(gthread & (lpv - 1));
-    const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) >> lpv_log2;
-    for (int64_t v = gthread >> lpv_log2; v < total; v += ngroups) {
-        const int n = (int)(v / S3);
-        const int p = (int)(v - (int64_t)n * S3);
-        const int i = p % S, j = (p / S) % S, k = p / (S * S);
+    const int sub = threadIdx.x & (lpv - 1);
+    const int grp = threadIdx.x >> lpv_log2;
+    const int ngrp = blockDim.x >> lpv_log2;
+
+    __shared__ float cm[LF_CAM_STRIDE];
+    if (threadIdx.x < LF_CAM_STRIDE) cm[threadIdx.x] = cam[(int64_t)n * LF_CAM_STRIDE + threadIdx.x];
+    __syncthreads();
+
+    const float* vb = vol + (int64_t)(MODE == 0 ? n / views_per_obj : n) * S3 * C;
+    for (int lv = grp; lv < BX * BY * BZ; lv += ngrp) {
+        const int i = bi * BX + (lv % BX);
+        const int j = bj * BY + (lv / BX) % BY;
+        const int k = bk * BZ + lv / (BX * BY);
+        if (i >= S || j >= S || k >= S) continue;
         float gx, gy, gz;
-        gen_grid<MODE>(cam + (int64_t)n * LF_CAM_STRIDE, S, i, j, k, gx, gy, gz);
+        gen_grid<MODE>(cm, S, i, j, k, gx, gy, gz);
         const Samp s = make_samp(gx, gy, gz, S);
         const CornerOfs co = corner_offsets(s, S, C);
-        const float* vb = vol + (int64_t)(MODE == 0 ? n / views_per_obj : n) * S3 * C;
-        float* ob = out + v * C;
+        float* ob = out + ((int64_t)n * S3 + ((int64_t)k * S + j) * S + i) * C;
         for (int c = sub * VEC; c < C; c += lpv * VEC) {
             typename Vec<VEC>::T val[8];
 #pragma unroll
@@ -206,7 +232,8 @@ resample_bwd_vol_kernel(const float* __restrict__ gout, const float* __restrict_
 // camera (deterministic, no atomics).
 // ------------------------------------------------------------------------------------------
 constexpr int kCamGradTerms = 17;          // M[12], vp x0,y0,w,h, znear
-constexpr int kBwdCamChunk = 2048;         // voxels per block
+constexpr int CBX = 16, CBY = 16, CBZ = 8;  // bwd_cam brick: 2048 voxels per block
+constexpr int kBwdCamChunk = CBX * CBY * CBZ;
 
 template <int VEC>
 __global__ void __launch_bounds__(256)
@@ -230,13 +257,18 @@ resample_o2c_bwd_cam_kernel(const float* __restrict__ gout, const float* __restr
     for (int t = 0; t < kCamGradTerms; ++t) acc[t] = 0.f;
 
     const float* vb = vol + (int64_t)(n / views_per_obj) * S3 * C;
-    const int p_end = min(S3, (b + 1) * kBwdCamChunk);
-    // warp-uniform trip count (the shuffles below use the full mask); out-of-range groups redo the
-    // last voxel and drop the result
-    for (int p0 = b * kBwdCamChunk; p0 < p_end; p0 += ngrp) {
-        const bool valid = (p0 + grp) < p_end;
-        const int p = valid ? (p0 + grp) : (p_end - 1);
-        const int i = p % S, j = (p / S) % S, k = p / (S * S);
+    const BrickGrid bg = brick_grid(S, CBX, CBY, CBZ);
+    int bb_ = b;
+    const int bi = bb_ % bg.nbx; bb_ /= bg.nbx;
+    const int bj = bb_ % bg.nby; const int bk = bb_ / bg.nby;
+    // warp-uniform trip count (the shuffles below use the full mask); voxels outside the cube are
+    // clamped to a valid one and their result dropped
+    for (int lv0 = 0; lv0 < kBwdCamChunk; lv0 += ngrp) {
+        const int lv = lv0 + grp;
+        int i = bi * CBX + (lv % CBX), j = bj * CBY + (lv / CBX) % CBY, k = bk * CBZ + lv / (CBX * CBY);
+        const bool valid = (lv < kBwdCamChunk) && i < S && j < S && k < S;
+        i = min(i, S - 1); j = min(j, S - 1); k = min(k, S - 1);
+        const int p = (k * S + j) * S + i;
         // --- forward recompute of the grid (same op order as gen_grid<0>) keeping intermediates
         const float tu = linspace_at(0.f, 1.f, S, i);
         const float tv = linspace_at(0.f, 1.f, S, j);
@@ -348,13 +380,14 @@ static int grid_for(int64_t total_groups, int lpv_log2) {
 
 template <int MODE>
 static int launch_fwd(const float* vol, const float* cam, float* out, int vpo, int N, int C, int S, cudaStream_t st) {
-    const int64_t total = (int64_t)N * S * S * S;
+    const int64_t blocks = (int64_t)N * brick_grid(S, BX, BY, BZ).per_cam();
+    LF_CHECK_ARG(blocks < (1ll << 31), "resample: too many bricks");
     if (C % 4 == 0) {
         const int l = lpv_log2_for(C, 4);
-        resample_fwd_kernel<MODE, 4><<<grid_for(total, l), 256, 0, st>>>(vol, cam, out, vpo, N, C, S, l);
+        resample_fwd_kernel<MODE, 4><<<(unsigned)blocks, 256, 0, st>>>(vol, cam, out, vpo, N, C, S, l);
     } else {
         const int l = lpv_log2_for(C, 1);
-        resample_fwd_kernel<MODE, 1><<<grid_for(total, l), 256, 0, st>>>(vol, cam, out, vpo, N, C, S, l);
+        resample_fwd_kernel<MODE, 1><<<(unsigned)blocks, 256, 0, st>>>(vol, cam, out, vpo, N, C, S, l);
     }
     LF_RETURN_LAUNCH();
 }
@@ -396,9 +429,8 @@ extern "C" int lf_resample_o2c_bwd_vol(const float* gout, const float* cam, floa
 }
 
 extern "C" int64_t lf_resample_o2c_bwd_cam_ws(int N, int S) {
-    const int64_t S3 = (int64_t)S * S * S;
-    const int64_t bpc = (S3 + kBwdCamChunk - 1) / kBwdCamChunk;
-    return (int64_t)N * bpc * kCamGradTerms;
+    if (N <= 0 || S <= 0) return 0;
+    return (int64_t)N * brick_grid(S, CBX, CBY, CBZ).per_cam() * kCamGradTerms;
 }
 
 extern "C" int lf_resample_o2c_bwd_cam(const float* gout, const float* vol, const float* cam, float* gcam,
@@ -406,8 +438,7 @@ extern "C" int lf_resample_o2c_bwd_cam(const float* gout, const float* vol, cons
     if (int e = check_common(gout, vol, cam, N, C, S)) return e;
     LF_CHECK_ARG(gcam && ws, "o2c_bwd_cam: null output/workspace");
     LF_CHECK_ARG(B > 0 && N % B == 0, "o2c: N=%d must be a multiple of B=%d", N, B);
-    const int S3 = S * S * S;
-    const int bpc = (S3 + kBwdCamChunk - 1) / kBwdCamChunk;
+    const int bpc = brick_grid(S, CBX, CBY, CBZ).per_cam();
     cudaStream_t st = (cudaStream_t)stream;
     if (C % 4 == 0) {
         const int l = lpv_log2_for(C, 4);

@@ -35,9 +35,13 @@ class LatentFusionModel(object):
         return self.train(False)
 
     def train(self, train):
+        # Inference façade: eval() also freezes the weights.  The reference leaves requires_grad=True, so
+        # every pose-refinement backward also computes (and discards) all conv weight gradients
+        # (SURVEY.md §3.1); nothing ever reads them.  train(True) re-enables them.
         for m in (self.sculptor, self.photographer, self.fuser, self.generator):
             if m is not None:
                 m.train(train)
+                m.requires_grad_(bool(train))
         return self
 
     def zoom_observation(self, observation):

@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Per-kernel micro-benchmark at BASELINE config-2 extents (dev tool; numbers quoted in profiles/ come
+from bench.py's live trace, this is for iterating on one kernel and for ncu captures).
+
+  python tools/kbench.py [--only resample|conv|all] [--iters 20] [--precision 0|1|2]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from latentfusion_b200 import ops  # noqa: E402
+from latentfusion_b200.modules.geometry import ObjectToCameraTransform  # noqa: E402
+from tests import parity_helpers as ph  # noqa: E402
+
+
+def timeit(fn, iters, flush):
+    ms = []
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    for _ in range(iters):
+        flush.fill_(1.0)          # evict L2 (buffer > 126 MB)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    ms.sort()
+    return ms[len(ms) // 2], ms[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--only', default='all')
+    ap.add_argument('--iters', type=int, default=20)
+    ap.add_argument('--precision', type=int, default=0)
+    ap.add_argument('-S', type=int, default=64)
+    ap.add_argument('-C', type=int, default=32)
+    ap.add_argument('-N', type=int, default=8)
+    a = ap.parse_args()
+    S, C, N = a.S, a.C, a.N
+    dev = torch.device('cuda:0')
+    flush = torch.empty(64 * 1024 * 1024, device=dev)     # 256 MB
+    peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}
+    out = {}
+    cams, _ = ph.synthetic_cameras(N, S, seed=9)
+    cam = cams.to(dev)
+    torch.manual_seed(0)
+    vol = ops.to_cl(torch.randn(1, C, S, S, S, device=dev))
+    if a.only in ('all', 'resample'):
+        T = ObjectToCameraTransform(1.0)
+        blk = cam.o2c_block(1.0)
+        nbytes = 4 * C * S ** 3 * (1 + N)
+        med, best = timeit(lambda: ops.resample_o2c(vol, blk), a.iters, flush)
+        out['o2c_fwd'] = dict(ms=med, best_ms=best, GBs=nbytes / med / 1e6, frac=nbytes / med / 1e6 / peaks['hbm_gbs'])
+        w = ops.to_cl(torch.randn(N, C, S, S, S, device=dev))
+        blk_g = blk.clone().requires_grad_(True)
+
+        def bwd():
+            o = ops.resample_o2c(vol, blk_g)
+            o.backward(w)
+        med2, best2 = timeit(bwd, a.iters, flush)
+        out['o2c_fwd+bwd_cam'] = dict(ms=med2, bwd_only_ms=med2 - med, GBs_bwd=nbytes / (med2 - med) / 1e6)
+    if a.only in ('all', 'conv'):
+        x = ops.to_cl(torch.randn(N, C, S, S, S, device=dev))
+        wgt = torch.randn(C, C, 3, 3, 3, device=dev)
+        b = torch.randn(C, device=dev)
+        flops = 2 * N * S ** 3 * 27 * C * C
+        med, best = timeit(lambda: ops.eq_conv(x, wgt, b, act=True, norm=True, precision=a.precision), a.iters, flush)
+        out[f'conv3d_block_fwd[p{a.precision}]'] = dict(ms=med, best_ms=best, TFs=flops / med / 1e9,
+                                                     GBs=8 * x.numel() / med / 1e6)
+        x2 = ops.to_cl(torch.randn(N, C, S, S, S, device=dev))
+        w2 = torch.randn(C, C * S, 1, 1, device=dev)
+        med, best = timeit(lambda: ops.eq_conv(x2, w2, b, act=True, norm=True, kind=ops.KIND_COLLAPSE, depth=S,
+                                               precision=0), a.iters, flush)
+        out['collapse_fwd'] = dict(ms=med, GBs=4 * x2.numel() / med / 1e6)
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == '__main__':
+    main()
