@@ -111,24 +111,32 @@ template <> struct Vec<1> {
 };
 
 struct CornerOfs {
-    int64_t o[8];   // element offsets (before channel) in ATen order: tnw tne tsw tse bnw bne bsw bse
-    float w[8];
+    unsigned o[8];  // element offsets (before channel) in ATen order: tnw tne tsw tse bnw bne bsw bse
+    float w[8];     // (a single cube is < 2^31 elements, checked on the host, so 32-bit offsets suffice)
 };
 
-__device__ __forceinline__ CornerOfs corner_offsets(const Samp& s, int S, int C) {
+__device__ __forceinline__ CornerOfs corner_offsets(int x0, int y0, int z0, float wx1, float wy1, float wz1,
+                                                    int S, int C) {
     CornerOfs c;
-    const int x1 = min(s.x0 + 1, S - 1), y1 = min(s.y0 + 1, S - 1), z1 = min(s.z0 + 1, S - 1);
-    // a +1 corner that falls outside only happens at ix == S-1 where its weight is exactly 0
-    const int64_t zs0 = (int64_t)s.z0 * S, zs1 = (int64_t)z1 * S;
-    c.o[0] = ((zs0 + s.y0) * S + s.x0) * C;  c.w[0] = s.wx0 * s.wy0 * s.wz0;
-    c.o[1] = ((zs0 + s.y0) * S + x1) * C;    c.w[1] = s.wx1 * s.wy0 * s.wz0;
-    c.o[2] = ((zs0 + y1) * S + s.x0) * C;    c.w[2] = s.wx0 * s.wy1 * s.wz0;
-    c.o[3] = ((zs0 + y1) * S + x1) * C;      c.w[3] = s.wx1 * s.wy1 * s.wz0;
-    c.o[4] = ((zs1 + s.y0) * S + s.x0) * C;  c.w[4] = s.wx0 * s.wy0 * s.wz1;
-    c.o[5] = ((zs1 + s.y0) * S + x1) * C;    c.w[5] = s.wx1 * s.wy0 * s.wz1;
-    c.o[6] = ((zs1 + y1) * S + s.x0) * C;    c.w[6] = s.wx0 * s.wy1 * s.wz1;
-    c.o[7] = ((zs1 + y1) * S + x1) * C;      c.w[7] = s.wx1 * s.wy1 * s.wz1;
+    const int sy = S * C, sz = S * sy;
+    // a +1 corner that falls outside only happens at ix == S-1 where its weight is exactly 0: clamp it
+    const int dx = (x0 + 1 < S) ? C : 0, dy = (y0 + 1 < S) ? sy : 0, dz = (z0 + 1 < S) ? sz : 0;
+    const unsigned base = (unsigned)(z0 * sz + y0 * sy + x0 * C);
+    const float wx0 = 1.f - wx1, wy0 = 1.f - wy1, wz0 = 1.f - wz1;   // == (floor+1) - ix exactly
+    const float w00 = wy0 * wz0, w10 = wy1 * wz0, w01 = wy0 * wz1, w11 = wy1 * wz1;
+    c.o[0] = base;                c.w[0] = wx0 * w00;
+    c.o[1] = base + dx;           c.w[1] = wx1 * w00;
+    c.o[2] = base + dy;           c.w[2] = wx0 * w10;
+    c.o[3] = base + dy + dx;      c.w[3] = wx1 * w10;
+    c.o[4] = base + dz;           c.w[4] = wx0 * w01;
+    c.o[5] = base + dz + dx;      c.w[5] = wx1 * w01;
+    c.o[6] = base + dz + dy;      c.w[6] = wx0 * w11;
+    c.o[7] = base + dz + dy + dx; c.w[7] = wx1 * w11;
     return c;
+}
+
+__device__ __forceinline__ CornerOfs corner_offsets(const Samp& s, int S, int C) {
+    return corner_offsets(s.x0, s.y0, s.z0, s.wx1, s.wy1, s.wz1, S, C);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -150,7 +158,40 @@ __host__ __device__ inline BrickGrid brick_grid(int S, int bx, int by, int bz) {
     return g;
 }
 
-template <int MODE, int VEC>
+// Packed per-voxel sampling state exchanged between lanes: floor corner (10 bits per axis) + the
+// three fractional weights.  (fx+1)-ix == 1-(ix-fx) exactly in fp32, so the floor-side weights are
+// rebuilt on the receiving lane without changing a bit.
+struct PackedSamp {
+    int base;            // x0 | y0 << 10 | z0 << 20
+    float wx1, wy1, wz1;
+};
+
+__device__ __forceinline__ PackedSamp pack_samp(const Samp& s) {
+    PackedSamp p;
+    p.base = s.x0 | (s.y0 << 10) | (s.z0 << 20);
+    p.wx1 = s.wx1; p.wy1 = s.wy1; p.wz1 = s.wz1;
+    return p;
+}
+
+__device__ __forceinline__ PackedSamp shfl_samp(const PackedSamp& p, int src) {
+    PackedSamp r;
+    r.base = __shfl_sync(0xffffffffu, p.base, src);
+    r.wx1 = __shfl_sync(0xffffffffu, p.wx1, src);
+    r.wy1 = __shfl_sync(0xffffffffu, p.wy1, src);
+    r.wz1 = __shfl_sync(0xffffffffu, p.wz1, src);
+    return r;
+}
+
+__device__ __forceinline__ CornerOfs corner_offsets(const PackedSamp& p, int S, int C) {
+    return corner_offsets(p.base & 1023, (p.base >> 10) & 1023, (p.base >> 20) & 1023, p.wx1, p.wy1, p.wz1, S, C);
+}
+
+// Forward.  A warp owns 32 output voxels (an 8 x 4 slab of the CTA's 8x8x4 brick).  Phase 1: lane l
+// generates the sample position of voxel l (the ~300-instruction camera chain runs once per 32 voxels,
+// not once per lane-group).  Phase 2: the warp walks the 32 voxels 32/LPV at a time; the packed
+// sampling state is broadcast with 4 shuffles and each LPV-lane group gathers its voxel's 8 corners
+// with coalesced 128-bit loads and writes one contiguous 4*C-byte run.
+template <int MODE, int VEC, bool ONE_CHUNK>
 __global__ void __launch_bounds__(256)
 resample_fwd_kernel(const float* __restrict__ vol, const float* __restrict__ cam, float* __restrict__ out,
                     int views_per_obj, int N, int C, int S, int lpv_log2) {
@@ -160,34 +201,56 @@ resample_fwd_kernel(const float* __restrict__ vol, const float* __restrict__ cam
     int b = blockIdx.x - n * bg.per_cam();
     const int bi = b % bg.nbx; b /= bg.nbx;
     const int bj = b % bg.nby; const int bk = b / bg.nby;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lpv = 1 << lpv_log2;
-    const int sub = threadIdx.x & (lpv - 1);
-    const int grp = threadIdx.x >> lpv_log2;
-    const int ngrp = blockDim.x >> lpv_log2;
+    const int sub = lane & (lpv - 1);
+    const int grp = lane >> lpv_log2;          // voxel slot inside one gather step
+    const int vps = 32 >> lpv_log2;            // voxels per gather step
 
     __shared__ float cm[LF_CAM_STRIDE];
     if (threadIdx.x < LF_CAM_STRIDE) cm[threadIdx.x] = cam[(int64_t)n * LF_CAM_STRIDE + threadIdx.x];
     __syncthreads();
 
-    const float* vb = vol + (int64_t)(MODE == 0 ? n / views_per_obj : n) * S3 * C;
-    for (int lv = grp; lv < BX * BY * BZ; lv += ngrp) {
-        const int i = bi * BX + (lv % BX);
-        const int j = bj * BY + (lv / BX) % BY;
-        const int k = bk * BZ + lv / (BX * BY);
-        if (i >= S || j >= S || k >= S) continue;
+    // phase 1: this lane's voxel
+    const int lv = warp * 32 + lane;
+    const int vi = bi * BX + (lv % BX), vj = bj * BY + (lv / BX) % BY, vk = bk * BZ + lv / (BX * BY);
+    const bool inside = vi < S && vj < S && vk < S;
+    PackedSamp mine;
+    {
         float gx, gy, gz;
-        gen_grid<MODE>(cm, S, i, j, k, gx, gy, gz);
-        const Samp s = make_samp(gx, gy, gz, S);
-        const CornerOfs co = corner_offsets(s, S, C);
-        float* ob = out + ((int64_t)n * S3 + ((int64_t)k * S + j) * S + i) * C;
-        for (int c = sub * VEC; c < C; c += lpv * VEC) {
+        gen_grid<MODE>(cm, S, min(vi, S - 1), min(vj, S - 1), min(vk, S - 1), gx, gy, gz);
+        mine = pack_samp(make_samp(gx, gy, gz, S));
+    }
+    const unsigned inside_mask = __ballot_sync(0xffffffffu, inside);
+
+    // phase 2
+    const float* vb = vol + (int64_t)(MODE == 0 ? n / views_per_obj : n) * S3 * C;
+    float* on = out + (int64_t)n * S3 * C;
+    const int row0 = (bk * BZ + warp / 2) * S + bj * BY + (warp & 1) * 4;   // (k*S + j) of this warp's slab row 0
+    for (int step = 0; step < lpv; ++step) {
+        const int src = step * vps + grp;
+        const PackedSamp ps = shfl_samp(mine, src);
+        if (!((inside_mask >> src) & 1u)) continue;
+        const CornerOfs co = corner_offsets(ps, S, C);
+        const unsigned opos = (unsigned)(((row0 + (src >> 3)) * S + bi * BX + (src & 7)) * C);
+        // one 64-bit base address per voxel; the other 7 corners are small non-negative deltas from it
+        const unsigned d1 = co.o[1] - co.o[0], d2 = co.o[2] - co.o[0], d4 = co.o[4] - co.o[0];
+        for (unsigned c = sub * VEC; c < (unsigned)C; c += lpv * VEC) {
+            const float* p0 = vb + (co.o[0] + c);
             typename Vec<VEC>::T val[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) val[q] = Vec<VEC>::load(vb + co.o[q] + c);
+            val[0] = Vec<VEC>::load(p0);
+            val[1] = Vec<VEC>::load(p0 + d1);
+            val[2] = Vec<VEC>::load(p0 + d2);
+            val[3] = Vec<VEC>::load(p0 + (d2 + d1));
+            val[4] = Vec<VEC>::load(p0 + d4);
+            val[5] = Vec<VEC>::load(p0 + (d4 + d1));
+            val[6] = Vec<VEC>::load(p0 + (d4 + d2));
+            val[7] = Vec<VEC>::load(p0 + (d4 + d2 + d1));
             typename Vec<VEC>::T acc = Vec<VEC>::zero();
 #pragma unroll
             for (int q = 0; q < 8; ++q) Vec<VEC>::fma(acc, co.w[q], val[q]);
-            Vec<VEC>::store(ob + c, acc);
+            Vec<VEC>::store(on + (opos + c), acc);
+            if (ONE_CHUNK) break;
         }
     }
 }
@@ -233,7 +296,7 @@ resample_bwd_vol_kernel(const float* __restrict__ gout, const float* __restrict_
 // ------------------------------------------------------------------------------------------
 constexpr int kCamGradTerms = 17;          // M[12], vp x0,y0,w,h, znear
 constexpr int CBX = 16, CBY = 16, CBZ = 8;  // bwd_cam brick: 2048 voxels per block
-constexpr int kBwdCamChunk = CBX * CBY * CBZ;
+
 
 template <int VEC>
 __global__ void __launch_bounds__(256)
@@ -243,10 +306,11 @@ resample_o2c_bwd_cam_kernel(const float* __restrict__ gout, const float* __restr
     const int S3 = S * S * S;
     const int n = blockIdx.x / blocks_per_cam;
     const int b = blockIdx.x - n * blocks_per_cam;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lpv = 1 << lpv_log2;
-    const int sub = threadIdx.x & (lpv - 1);
-    const int grp = threadIdx.x >> lpv_log2;
-    const int ngrp = blockDim.x >> lpv_log2;
+    const int sub = lane & (lpv - 1);
+    const int grp = lane >> lpv_log2;
+    const int vps = 32 >> lpv_log2;
 
     __shared__ float cm[LF_CAM_STRIDE];
     if (threadIdx.x < LF_CAM_STRIDE) cm[threadIdx.x] = cam[(int64_t)n * LF_CAM_STRIDE + threadIdx.x];
@@ -257,19 +321,22 @@ resample_o2c_bwd_cam_kernel(const float* __restrict__ gout, const float* __restr
     for (int t = 0; t < kCamGradTerms; ++t) acc[t] = 0.f;
 
     const float* vb = vol + (int64_t)(n / views_per_obj) * S3 * C;
+    const float* gn = gout + (int64_t)n * S3 * C;
     const BrickGrid bg = brick_grid(S, CBX, CBY, CBZ);
     int bb_ = b;
     const int bi = bb_ % bg.nbx; bb_ /= bg.nbx;
     const int bj = bb_ % bg.nby; const int bk = bb_ / bg.nby;
-    // warp-uniform trip count (the shuffles below use the full mask); voxels outside the cube are
-    // clamped to a valid one and their result dropped
-    for (int lv0 = 0; lv0 < kBwdCamChunk; lv0 += ngrp) {
-        const int lv = lv0 + grp;
-        int i = bi * CBX + (lv % CBX), j = bj * CBY + (lv / CBX) % CBY, k = bk * CBZ + lv / (CBX * CBY);
-        const bool valid = (lv < kBwdCamChunk) && i < S && j < S && k < S;
-        i = min(i, S - 1); j = min(j, S - 1); k = min(k, S - 1);
-        const int p = (k * S + j) * S + i;
-        // --- forward recompute of the grid (same op order as gen_grid<0>) keeping intermediates
+
+    // the 16x16x8 brick is walked as 8 sub-bricks of 8x8x4; a warp owns an 8x4 slab of each
+    for (int sb = 0; sb < 8; ++sb) {
+        const int lv = warp * 32 + lane;
+        const int vi = bi * CBX + (sb & 1) * 8 + (lv % 8);
+        const int vj = bj * CBY + ((sb >> 1) & 1) * 8 + (lv / 8) % 8;
+        const int vk = bk * CBZ + (sb >> 2) * 4 + lv / 64;
+        const bool inside = vi < S && vj < S && vk < S;
+        const int i = min(vi, S - 1), j = min(vj, S - 1), k = min(vk, S - 1);
+        // --- phase 1: forward recompute of this lane's grid point (same op order as gen_grid<0>),
+        //     keeping the intermediates the chain rule needs
         const float tu = linspace_at(0.f, 1.f, S, i);
         const float tv = linspace_at(0.f, 1.f, S, j);
         const float tz = linspace_at(0.f, 1.f, S, k);
@@ -284,41 +351,53 @@ resample_o2c_bwd_cam_kernel(const float* __restrict__ gout, const float* __restr
         const float gy = (cm[4] * x + cm[5] * y + cm[6] * z + cm[7]) / half;
         const float gz = (cm[8] * x + cm[9] * y + cm[10] * z + cm[11]) / half;
         const Samp s = make_samp(gx, gy, gz, S);
-        const CornerOfs co = corner_offsets(s, S, C);
-        const float* gb = gout + ((int64_t)n * S3 + p) * C;
+        const PackedSamp mine = pack_samp(s);
+        const int my_pos = inside ? (k * S + j) * S + i : -1;
 
-        // d(sample)/d(ix,iy,iz) contracted with grad_out over this lane's channels
-        float dx = 0.f, dy = 0.f, dz = 0.f;
-        for (int c = sub * VEC; c < C; c += lpv * VEC) {
-            typename Vec<VEC>::T val[8];
+        // --- phase 2: gather + contraction with grad_out, 32/LPV voxels per step
+        float mdx = 0.f, mdy = 0.f, mdz = 0.f;      // d(sum_c go*sample)/d(ix,iy,iz) of MY voxel
+        for (int step = 0; step < lpv; ++step) {
+            const int src = step * vps + grp;
+            const PackedSamp ps = shfl_samp(mine, src);
+            const int pos = __shfl_sync(0xffffffffu, my_pos, src);
+            float dx = 0.f, dy = 0.f, dz = 0.f;
+            if (pos >= 0) {
+                const CornerOfs co = corner_offsets(ps, S, C);
+                const float wx0 = 1.f - ps.wx1, wy0 = 1.f - ps.wy1, wz0 = 1.f - ps.wz1;
+                const float* gb = gn + (int64_t)pos * C;
+                for (int c = sub * VEC; c < C; c += lpv * VEC) {
+                    typename Vec<VEC>::T val[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) val[q] = Vec<VEC>::load(vb + co.o[q] + c);
-            const typename Vec<VEC>::T g = Vec<VEC>::load(gb + c);
-            // corner order: q = zbit*4 + ybit*2 + xbit
-            const float e01 = Vec<VEC>::dot(g, Vec<VEC>::sub(val[1], val[0]));
-            const float e23 = Vec<VEC>::dot(g, Vec<VEC>::sub(val[3], val[2]));
-            const float e45 = Vec<VEC>::dot(g, Vec<VEC>::sub(val[5], val[4]));
-            const float e67 = Vec<VEC>::dot(g, Vec<VEC>::sub(val[7], val[6]));
-            dx += e01 * s.wy0 * s.wz0 + e23 * s.wy1 * s.wz0 + e45 * s.wy0 * s.wz1 + e67 * s.wy1 * s.wz1;
-            const float f02 = Vec<VEC>::dot(g, Vec<VEC>::sub(val[2], val[0]));
-            const float f13 = Vec<VEC>::dot(g, Vec<VEC>::sub(val[3], val[1]));
-            const float f46 = Vec<VEC>::dot(g, Vec<VEC>::sub(val[6], val[4]));
-            const float f57 = Vec<VEC>::dot(g, Vec<VEC>::sub(val[7], val[5]));
-            dy += f02 * s.wx0 * s.wz0 + f13 * s.wx1 * s.wz0 + f46 * s.wx0 * s.wz1 + f57 * s.wx1 * s.wz1;
-            const float h04 = Vec<VEC>::dot(g, Vec<VEC>::sub(val[4], val[0]));
-            const float h15 = Vec<VEC>::dot(g, Vec<VEC>::sub(val[5], val[1]));
-            const float h26 = Vec<VEC>::dot(g, Vec<VEC>::sub(val[6], val[2]));
-            const float h37 = Vec<VEC>::dot(g, Vec<VEC>::sub(val[7], val[3]));
-            dz += h04 * s.wx0 * s.wy0 + h15 * s.wx1 * s.wy0 + h26 * s.wx0 * s.wy1 + h37 * s.wx1 * s.wy1;
+                    for (int q = 0; q < 8; ++q) val[q] = Vec<VEC>::load(vb + co.o[q] + c);
+                    const typename Vec<VEC>::T g = Vec<VEC>::load(gb + c);
+                    // corner order: q = zbit*4 + ybit*2 + xbit
+                    float d[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) d[q] = Vec<VEC>::dot(g, val[q]);
+                    dx += (d[1] - d[0]) * wy0 * wz0 + (d[3] - d[2]) * ps.wy1 * wz0
+                        + (d[5] - d[4]) * wy0 * ps.wz1 + (d[7] - d[6]) * ps.wy1 * ps.wz1;
+                    dy += (d[2] - d[0]) * wx0 * wz0 + (d[3] - d[1]) * ps.wx1 * wz0
+                        + (d[6] - d[4]) * wx0 * ps.wz1 + (d[7] - d[5]) * ps.wx1 * ps.wz1;
+                    dz += (d[4] - d[0]) * wx0 * wy0 + (d[5] - d[1]) * ps.wx1 * wy0
+                        + (d[6] - d[2]) * wx0 * ps.wy1 + (d[7] - d[3]) * ps.wx1 * ps.wy1;
+                }
+            }
+            for (int o = lpv >> 1; o > 0; o >>= 1) {
+                dx += __shfl_xor_sync(0xffffffffu, dx, o);
+                dy += __shfl_xor_sync(0xffffffffu, dy, o);
+                dz += __shfl_xor_sync(0xffffffffu, dz, o);
+            }
+            // hand the result back to the lane that owns this voxel (lane == step*vps + group index)
+            const int from = (lane - step * vps) << lpv_log2;     // leader lane of my group, if mine is in this step
+            const float rx = __shfl_sync(0xffffffffu, dx, from & 31);
+            const float ry = __shfl_sync(0xffffffffu, dy, from & 31);
+            const float rz = __shfl_sync(0xffffffffu, dz, from & 31);
+            if (lane >= step * vps && lane < (step + 1) * vps) { mdx = rx; mdy = ry; mdz = rz; }
         }
-        for (int o = lpv >> 1; o > 0; o >>= 1) {
-            dx += __shfl_xor_sync(0xffffffffu, dx, o);
-            dy += __shfl_xor_sync(0xffffffffu, dy, o);
-            dz += __shfl_xor_sync(0xffffffffu, dz, o);
-        }
-        if (sub == 0 && valid) {
-            // chain: grid -> object coords -> (M, x, y, z) -> (viewport, znear)
-            const float gox = dx * s.mx / half, goy = dy * s.my / half, goz = dz * s.mz / half;
+
+        // --- phase 3: chain rule for my voxel: grid -> object coords -> (M, x, y, z) -> (viewport, znear)
+        if (inside) {
+            const float gox = mdx * s.mx / half, goy = mdy * s.my / half, goz = mdz * s.mz / half;
             acc[0] += gox * x; acc[1] += gox * y; acc[2] += gox * z; acc[3] += gox;
             acc[4] += goy * x; acc[5] += goy * y; acc[6] += goy * z; acc[7] += goy;
             acc[8] += goz * x; acc[9] += goz * y; acc[10] += goz * z; acc[11] += goz;
@@ -326,16 +405,15 @@ resample_o2c_bwd_cam_kernel(const float* __restrict__ gout, const float* __restr
             const float ly = cm[1] * gox + cm[5] * goy + cm[9] * goz;
             const float lz = cm[2] * gox + cm[6] * goy + cm[10] * goz;
             const float lu = lx * z / cm[18];     // dL/du
-            const float lv = ly * z / cm[19];     // dL/dv
+            const float lv2 = ly * z / cm[19];    // dL/dv
             acc[12] += lu; acc[14] += lu * tu;
-            acc[13] += lv; acc[15] += lv * tv;
+            acc[13] += lv2; acc[15] += lv2 * tv;
             acc[16] += lz + lx * a + ly * bb;     // dL/dznear  (z = tz*z_span + znear)
         }
     }
 
     // block reduction
     __shared__ float red[8][kCamGradTerms];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
     for (int t = 0; t < kCamGradTerms; ++t) {
         const float r = warp_sum(acc[t]);
@@ -384,10 +462,11 @@ static int launch_fwd(const float* vol, const float* cam, float* out, int vpo, i
     LF_CHECK_ARG(blocks < (1ll << 31), "resample: too many bricks");
     if (C % 4 == 0) {
         const int l = lpv_log2_for(C, 4);
-        resample_fwd_kernel<MODE, 4><<<(unsigned)blocks, 256, 0, st>>>(vol, cam, out, vpo, N, C, S, l);
+        if (C == (4 << l)) resample_fwd_kernel<MODE, 4, true><<<(unsigned)blocks, 256, 0, st>>>(vol, cam, out, vpo, N, C, S, l);
+        else resample_fwd_kernel<MODE, 4, false><<<(unsigned)blocks, 256, 0, st>>>(vol, cam, out, vpo, N, C, S, l);
     } else {
         const int l = lpv_log2_for(C, 1);
-        resample_fwd_kernel<MODE, 1><<<(unsigned)blocks, 256, 0, st>>>(vol, cam, out, vpo, N, C, S, l);
+        resample_fwd_kernel<MODE, 1, false><<<(unsigned)blocks, 256, 0, st>>>(vol, cam, out, vpo, N, C, S, l);
     }
     LF_RETURN_LAUNCH();
 }
