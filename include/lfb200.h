@@ -99,6 +99,16 @@ typedef struct {
 
 int lf_conv_fwd(const lf_conv_desc* desc, const float* x, const float* w, const float* bias,
                 float* y, float* rnorm, void* stream);
+/* tcgen05 path (precision 1|2): `w` passed to lf_conv_fwd must point to weights pre-packed by
+ * lf_conv_tc_pack_weights (bf16 hi part followed by the bf16 lo part, UMMA no-swizzle K-major layout
+ * [part][tap][Cin_pad/8][Cout_pad][8]); lf_conv_tc_weight_bytes gives the buffer size.  Shapes the
+ * tensor-core kernel does not cover (lf_conv_tc_supported == 0, e.g. Cin % 4 != 0, depth-collapse/expand)
+ * must be run with precision 0. */
+int64_t lf_conv_tc_weight_bytes(int taps, int cin, int cout);
+int lf_conv_tc_pack_weights(const float* w_packed /* [taps][Cin][Cout] fp32 */, void* out,
+                            int taps, int cin, int cout, void* stream);
+int lf_conv_tc_supported(const lf_conv_desc* desc);
+
 /* du = d(loss)/d(pre-activation conv output incl. scale&bias) from gy, y (post-norm output), rnorm.
  * PixelNorm + LeakyReLU backward fused.  Elements are y[(o*gd + t)*inner + p][c]; one norm group =
  * all (t, c) of a fixed (o, p): gd = 1 for ordinary convs (outer = positions, inner = 1); for the

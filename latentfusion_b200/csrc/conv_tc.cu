@@ -1,9 +1,494 @@
-// tcgen05 implicit-GEMM convolution (placeholder until the UMMA path lands; reports "unsupported").
+// tcgen05 implicit-GEMM convolution for sm_100a — the dense contraction of the LatentFusion hot path
+// (3x3x3 / 3x3 / 1x1 Equalized convs, channels-last) on the 5th-gen tensor cores with the
+// He-scale + bias + LeakyReLU + PixelNorm epilogue fused.
+//
+// GEMM view per CTA step:  D[128 positions, Cout] += A_tap[128 positions, Cin] * W_tap[Cin, Cout]
+//   * A is never im2col'ed.  A strip of (R + 2h) input rows x (W + 2h) columns of one depth plane is staged
+//     once in shared memory as bf16 in the UMMA *no-swizzle K-major* canonical layout
+//         [k-chunk of 8 channels][flattened padded position][8 x bf16]          (one 16-byte row per position)
+//     With that layout a filter tap (dz,dy,dx) is nothing but a different descriptor START ADDRESS
+//     (+ (dy*P + dx) * 16 bytes inside the plane, another ring slot for dz): the 27 taps of a 3x3x3 filter
+//     are 27 tcgen05.mma instructions reading the same staged bytes.  M-tiles are 128 consecutive flattened
+//     positions of the padded-pitch space; the <= 2h garbage columns per row are dropped in the epilogue.
+//   * The CTA marches along depth with a ring of staged planes, so every input plane is read from
+//     L2/HBM once per strip (plus the row halo), converted fp32 -> bf16 on the fly by 4 producer warps.
+//   * Accumulators live in TMEM (double buffered, NT tiles x Cout columns each); one elected thread issues
+//     the MMAs; 4 epilogue warps read TMEM with tcgen05.ld (one output position = one thread = all Cout
+//     channels in registers, so PixelNorm is a thread-local reduction) and write channels-last fp32.
+//   * Precision: operands are bf16, accumulation fp32.  "bf16x3" (precision 1) runs three passes
+//     hi*hi + lo*hi + hi*lo (x = hi + lo, both bf16) accumulating in the fp32 output => ~2^-16 relative
+//     per product, i.e. fp32-parity grade; "bf16" (precision 2) is the single hi*hi pass.
+//
+// Pipelines (mbarriers): slab_full/slab_empty[ring] (producers <-> MMA), acc_full/acc_empty[2] (MMA <-> epilogue).
+// Every wait is bounded: a pipeline bug traps instead of hanging the GPU.
 #include "common.cuh"
+
+#include <cuda_bf16.h>
+
 namespace lf {
-int conv_tc_supported(const lf_conv_desc*) { return 0; }
-int conv_tc_launch(const lf_conv_desc*, const float*, const float*, const float*, float*, float*, cudaStream_t) {
-    set_error("conv: tcgen05 path not built");
-    return LF_EUNSUPPORTED;
+namespace tc {
+
+constexpr int kProducerWarps = 4;
+constexpr int kThreads = 32 * (kProducerWarps + 1 + 4);    // producers | MMA | epilogue
+constexpr int kMaxRing = 4;
+constexpr int kMaxTiles = 5;
+
+enum PassMode { PASS_ONLY = 0, PASS_FIRST = 1, PASS_MID = 2, PASS_LAST = 3 };
+
+struct Params {
+    const float* x; const uint16_t* wpk; const float* bias; float* y; float* rnorm;
+    int n, d, h, w;            // extent (d = 1 for 2-D)
+    int cin, cout, cin_pad, cout_pad;
+    int k, hz;                 // kernel size (1|3); hz = depth halo (k/2 for 3-D, 0 for 2-D)
+    int R, NT, P, pos_alloc, ring, DC;
+    int nstrips, ndchunks, items;
+    float scale; int act; float slope; int norm;
+    int a_part;                // 0: hi = bf16(x), 1: lo = bf16(x - hi)
+    int pass_mode;
+    uint32_t idesc;
+    uint32_t slab_bytes, w_bytes;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t it = 0; it < (1u << 26); ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    printf("lfb200 conv_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
+           (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+    __trap();
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> f32, M=128, N from idesc, K=16
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// UMMA shared-memory matrix descriptor, no-swizzle K-major canonical layout
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout 0)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b, int part) {
+    __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+    if (part) {
+        ha = __float2bfloat16_rn(a - __bfloat162float(ha));
+        hb = __float2bfloat16_rn(b - __bfloat162float(hb));
+    }
+    return (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ Params p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    const uint32_t slabs = smem_u32(smem);                              // ring * slab_bytes
+    const uint32_t wsm = slabs + p.ring * p.slab_bytes;                 // packed bf16 weights
+    uint8_t* tail = smem + (size_t)p.ring * p.slab_bytes + p.w_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);                 // [ring] full, [ring] empty, [2] acc_full, [2] acc_empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxRing + 4);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxRing);
+    const uint32_t bar_accf = smem_u32(bars + 2 * kMaxRing), bar_acce = smem_u32(bars + 2 * kMaxRing + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- one-time setup: weights -> smem, barriers, TMEM
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(p.wpk);
+        uint4* dst = reinterpret_cast<uint4*>(smem + (size_t)p.ring * p.slab_bytes);
+        for (uint32_t i = threadIdx.x; i < p.w_bytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+        fence_proxy_async();
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.ring; ++i) { mbar_init(bar_full + 8 * i, kProducerWarps * 32); mbar_init(bar_empty + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kProducerWarps) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int halo = p.k / 2;
+    const int rows_in = p.R + 2 * halo;
+    const int kchunks = p.cin_pad / 8;
+    const uint32_t lbo_a = (uint32_t)p.pos_alloc * 16u;
+    const int q4 = p.cin_pad / 4;                       // float4 units per position
+
+    if (warp < kProducerWarps) {
+        // =========================== PRODUCERS: global fp32 -> bf16 UMMA slab ===========================
+        uint32_t kcount = 0;                            // planes produced by this CTA so far
+        const int tid = threadIdx.x;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+            int it = item;
+            const int dchunk = it % p.ndchunks; it /= p.ndchunks;
+            const int strip = it % p.nstrips; const int n = it / p.nstrips;
+            const int d0 = dchunk * p.DC, d1 = min(p.d, d0 + p.DC);
+            const int y0 = strip * p.R;
+            for (int e = d0 - p.hz; e <= d1 - 1 + p.hz; ++e, ++kcount) {
+                const uint32_t slot = kcount % p.ring;
+                mbar_wait(bar_empty + 8 * slot, ((kcount / p.ring) & 1) ^ 1);
+                if (e >= 0 && e < p.d) {
+                    uint8_t* slab = smem + (size_t)slot * p.slab_bytes;
+                    const float* plane = p.x + ((int64_t)n * p.d + e) * p.h * p.w * (int64_t)p.cin;
+                    const int units = rows_in * p.P * q4;
+                    for (int u0 = tid; u0 < units; u0 += 4 * kProducerWarps * 32) {
+                        float4 v[4];
+                        int upos[4], uq[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int u = u0 + j * kProducerWarps * 32;
+                            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            upos[j] = -1; uq[j] = 0;
+                            if (u < units) {
+                                const int pos = u / q4, q = u - pos * q4;
+                                const int r = pos / p.P, c = pos - r * p.P;
+                                const int yy = y0 + r - halo, xx = c - halo;
+                                upos[j] = pos; uq[j] = q;
+                                if (yy >= 0 && yy < p.h && xx >= 0 && xx < p.w && q * 4 < p.cin)
+                                    v[j] = ldg4(plane + ((int64_t)yy * p.w + xx) * p.cin + q * 4);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (upos[j] < 0) continue;
+                            const uint32_t lo = pack_bf16x2(v[j].x, v[j].y, p.a_part);
+                            const uint32_t hi = pack_bf16x2(v[j].z, v[j].w, p.a_part);
+                            uint8_t* dst = slab + (size_t)(uq[j] >> 1) * lbo_a + (size_t)upos[j] * 16 + (uq[j] & 1) * 8;
+                            *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
+                        }
+                    }
+                    fence_proxy_async();                // generic-proxy stores -> visible to the tensor core
+                }
+                mbar_arrive(bar_full + 8 * slot);
+            }
+        }
+    } else if (warp == kProducerWarps) {
+        // =========================== MMA ISSUER (one thread) ===========================
+        if (lane == 0) {
+            uint32_t kbase = 0;                         // running plane count at the start of the item
+            uint32_t step = 0;                          // running step (accumulator) count
+            const uint32_t lbo_b = (uint32_t)p.cout_pad * 16u;
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+                const int dchunk = item % p.ndchunks;
+                const int d0 = dchunk * p.DC, d1 = min(p.d, d0 + p.DC);
+                const int nplanes = (d1 - d0) + 2 * p.hz;
+                int waited = 0;                         // planes of this item whose full barrier we passed
+                for (int d = d0; d < d1; ++d, ++step) {
+                    const int need = (d - d0) + 2 * p.hz + 1;        // planes 0 .. need-1 must be staged
+                    for (; waited < need; ++waited) {
+                        const uint32_t kc = kbase + waited;
+                        mbar_wait(bar_full + 8 * (kc % p.ring), (kc / p.ring) & 1);
+                    }
+                    const uint32_t buf = step & 1;
+                    mbar_wait(bar_acce + 8 * buf, ((step >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    for (int t = 0; t < p.NT; ++t) {
+                        const uint32_t d_tmem = tmem_base + (buf * p.NT + t) * p.cout_pad;
+                        uint32_t acc = 0;
+                        for (int dz = 0; dz <= 2 * p.hz; ++dz) {
+                            const int e = d + dz - p.hz;
+                            if (e < 0 || e >= p.d) continue;           // zero plane: contributes nothing
+                            const uint32_t kc = kbase + (uint32_t)(e - (d0 - p.hz));
+                            const uint32_t slab = slabs + (kc % p.ring) * p.slab_bytes;
+                            for (int dy = 0; dy < p.k; ++dy) {
+                                for (int dx = 0; dx < p.k; ++dx) {
+                                    const int tap = (dz * p.k + dy) * p.k + dx;
+                                    const uint32_t a0 = slab + (uint32_t)(t * 128 + dy * p.P + dx) * 16u;
+                                    const uint32_t b0 = wsm + (uint32_t)(tap * kchunks) * lbo_b;
+                                    for (int ks = 0; ks < p.cin_pad / 16; ++ks) {
+                                        const uint64_t ad = make_desc(a0 + 2 * ks * lbo_a, lbo_a, 128);
+                                        const uint64_t bd = make_desc(b0 + 2 * ks * lbo_b, lbo_b, 128);
+                                        umma_bf16(d_tmem, ad, bd, p.idesc, acc);
+                                        acc = 1;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    umma_commit(bar_accf + 8 * buf);                   // accumulators of this step complete
+                    // release planes that no later step of this item reads
+                    const int first_rel = (d - d0);                    // plane index d - hz relative to item
+                    const int last_rel = (d == d1 - 1) ? nplanes - 1 : first_rel;
+                    for (int pl = first_rel; pl <= last_rel; ++pl) umma_commit(bar_empty + 8 * ((kbase + pl) % p.ring));
+                }
+                kbase += nplanes;
+            }
+        }
+    } else {
+        // =========================== EPILOGUE (4 warps = 128 TMEM lanes) ===========================
+        const int wq = warp & 3;                       // TMEM lane quarter this warp may access
+        uint32_t step = 0;
+        const float inv_c = 1.f / (float)p.cout;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+            int it = item;
+            const int dchunk = it % p.ndchunks; it /= p.ndchunks;
+            const int strip = it % p.nstrips; const int n = it / p.nstrips;
+            const int d0 = dchunk * p.DC, d1 = min(p.d, d0 + p.DC);
+            const int y0 = strip * p.R;
+            for (int d = d0; d < d1; ++d, ++step) {
+                const uint32_t buf = step & 1;
+                mbar_wait(bar_accf + 8 * buf, (step >> 1) & 1);
+                tc_fence_after();
+                for (int t = 0; t < p.NT; ++t) {
+                    const int q = t * 128 + wq * 32 + lane;
+                    const int r = q / p.P, c = q - r * p.P;
+                    const bool valid = (r < p.R) && (c < p.w) && (y0 + r < p.h);
+                    const int64_t opos = (((int64_t)n * p.d + d) * p.h + (y0 + r)) * p.w + c;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (buf * p.NT + t) * p.cout_pad;
+                    float* yp = p.y + opos * p.cout;
+                    const bool raw_out = (p.pass_mode == PASS_FIRST || p.pass_mode == PASS_MID);
+                    const bool add_in = (p.pass_mode == PASS_MID || p.pass_mode == PASS_LAST);
+                    float ss = 0.f;
+                    if (p.norm && !raw_out) {
+                        for (int cb = 0; cb < p.cout_pad; cb += 16) {
+                            float v[16];
+                            tmem_ld16(taddr + cb, v);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const int co = cb + i;
+                                if (co < p.cout) {
+                                    float a = v[i];
+                                    if (add_in && valid) a += yp[co];
+                                    a = a * p.scale + (p.bias ? __ldg(p.bias + co) : 0.f);
+                                    if (p.act) a = a > 0.f ? a : a * p.slope;
+                                    ss += a * a;
+                                }
+                            }
+                        }
+                    }
+                    const float rn = sqrtf(ss * inv_c + 1e-8f);
+                    for (int cb = 0; cb < p.cout_pad; cb += 16) {
+                        float v[16];
+                        tmem_ld16(taddr + cb, v);
+                        if (!valid) continue;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int co = cb + i;
+                            float a = v[i];
+                            if (co < p.cout) {
+                                if (add_in) a += yp[co];
+                                if (!raw_out) {
+                                    a = a * p.scale + (p.bias ? __ldg(p.bias + co) : 0.f);
+                                    if (p.act) a = a > 0.f ? a : a * p.slope;
+                                    if (p.norm) a = a / rn;
+                                }
+                            }
+                            v[i] = a;
+                        }
+                        if ((p.cout & 3) == 0) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4)
+                                if (cb + i < p.cout)
+                                    *reinterpret_cast<float4*>(yp + cb + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (cb + i < p.cout) yp[cb + i] = v[i];
+                        }
+                    }
+                    if (valid && p.norm && !raw_out && p.rnorm != nullptr) p.rnorm[opos] = rn;
+                }
+                tc_fence_before();
+                mbar_arrive(bar_acce + 8 * buf);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kProducerWarps) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// fp32 packed weights [taps][cin][cout] -> bf16 UMMA layout [part(hi,lo)][tap][k-chunk][cout_pad][8]
+__global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out,
+                                    int taps, int cin, int cout, int cin_pad, int cout_pad) {
+    const int64_t per_part = (int64_t)taps * (cin_pad / 8) * cout_pad * 8;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < per_part; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = e;
+        const int j = (int)(r % 8); r /= 8;
+        const int co = (int)(r % cout_pad); r /= cout_pad;
+        const int kc = (int)(r % (cin_pad / 8)); const int tap = (int)(r / (cin_pad / 8));
+        const int ci = kc * 8 + j;
+        float v = 0.f;
+        if (ci < cin && co < cout) v = w[((int64_t)tap * cin + ci) * cout + co];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        out[e] = __bfloat16_as_ushort(hi);
+        out[per_part + e] = __bfloat16_as_ushort(lo);
+    }
+}
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+struct Plan {
+    int cin_pad, cout_pad, P, R, NT, pos_alloc, ring, DC, nstrips, ndchunks, taps;
+    uint32_t slab_bytes, w_bytes, smem_bytes;
+};
+
+static bool make_plan(const lf_conv_desc* d, Plan& pl) {
+    if (!(d->ndim == 2 || d->ndim == 3)) return false;
+    if (!(d->k == 1 || d->k == 3)) return false;
+    if (d->cin % 4 != 0) return false;
+    pl.cin_pad = round_up(d->cin, 16);
+    pl.cout_pad = round_up(d->cout, 16);
+    if (pl.cout_pad > 256) return false;
+    const int halo = d->k / 2;
+    const int hz = (d->ndim == 3) ? halo : 0;
+    pl.taps = (d->ndim == 3) ? d->k * d->k * d->k : d->k * d->k;
+    pl.P = d->w + 2 * halo;
+    // accumulators: 2 buffers x NT tiles x cout_pad columns <= 512
+    int nt_max = 512 / (2 * pl.cout_pad);
+    if (nt_max > kMaxTiles) nt_max = kMaxTiles;
+    if (nt_max < 1) return false;
+    pl.w_bytes = (uint32_t)pl.taps * (pl.cin_pad / 8) * pl.cout_pad * 16;
+    const uint32_t budget = 227 * 1024 - 256;
+    if (pl.w_bytes + 4096 > budget) return false;
+    pl.ring = (hz > 0) ? kMaxRing : 2;
+    // largest R such that tiles and smem fit
+    int best_R = 0;
+    for (int R = min(d->h, (nt_max * 128) / pl.P); R >= 1; --R) {
+        int pos = (R + 2 * halo) * pl.P + 2 * halo;
+        pos = round_up(pos - 4, 8) + 4;                 // pos_alloc == 4 (mod 8): conflict-free producer stores
+        const uint32_t slab = (uint32_t)(pl.cin_pad / 8) * pos * 16;
+        if ((uint64_t)slab * pl.ring + pl.w_bytes <= budget && ((uint32_t)pos * 16 >> 4) < 16384) { best_R = R; break; }
+    }
+    if (best_R == 0) return false;
+    pl.R = best_R;
+    pl.NT = (pl.R * pl.P + 127) / 128;
+    int pos = (pl.R + 2 * halo) * pl.P + 2 * halo;
+    pl.pos_alloc = round_up(pos - 4, 8) + 4;
+    pl.slab_bytes = (uint32_t)(pl.cin_pad / 8) * pl.pos_alloc * 16;
+    pl.smem_bytes = pl.slab_bytes * pl.ring + pl.w_bytes + 256;
+    // the last tile may read up to (NT*128 + (k-1)*P + k-1 - pos_alloc) positions past a k-chunk: it must stay
+    // inside the allocation; chunks are followed by other chunks / the weight buffer, check the very last one
+    const int overrun = pl.NT * 128 + (d->k - 1) * pl.P + (d->k - 1) - pl.pos_alloc;
+    if (overrun > 0 && (uint32_t)overrun * 16 > pl.w_bytes) return false;
+    pl.nstrips = (d->h + pl.R - 1) / pl.R;
+    // depth chunking: enough work items to fill the machine
+    pl.DC = d->d;
+    if (hz > 0) {
+        const int sms = sm_count();
+        while (pl.DC > 4 && (int64_t)d->n * pl.nstrips * ((d->d + pl.DC - 1) / pl.DC) < 2 * sms) pl.DC = (pl.DC + 1) / 2;
+    }
+    pl.ndchunks = (d->d + pl.DC - 1) / pl.DC;
+    return true;
+}
+
+}  // namespace tc
+
+int conv_tc_supported(const lf_conv_desc* d) {
+    tc::Plan pl;
+    return tc::make_plan(d, pl) ? 1 : 0;
+}
+
+int conv_tc_launch(const lf_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
+                   float* rnorm, cudaStream_t st) {
+    tc::Plan pl;
+    LF_CHECK_ARG(tc::make_plan(d, pl), "conv_tc: unsupported shape");
+    LF_CHECK_ARG(x && w && y, "conv_tc: null pointer");
+    tc::Params p;
+    p.x = x; p.bias = bias; p.y = y; p.rnorm = rnorm;
+    p.n = d->n; p.d = d->d; p.h = d->h; p.w = d->w;
+    p.cin = d->cin; p.cout = d->cout; p.cin_pad = pl.cin_pad; p.cout_pad = pl.cout_pad;
+    p.k = d->k; p.hz = (d->ndim == 3) ? d->k / 2 : 0;
+    p.R = pl.R; p.NT = pl.NT; p.P = pl.P; p.pos_alloc = pl.pos_alloc; p.ring = pl.ring; p.DC = pl.DC;
+    p.nstrips = pl.nstrips; p.ndchunks = pl.ndchunks; p.items = d->n * pl.nstrips * pl.ndchunks;
+    p.scale = d->scale; p.act = d->act; p.slope = d->slope; p.norm = d->norm;
+    p.slab_bytes = pl.slab_bytes; p.w_bytes = pl.w_bytes;
+    // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1,
+    // K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(pl.cout_pad >> 3) << 17) | ((128u >> 4) << 24);
+    const uint16_t* wpk = reinterpret_cast<const uint16_t*>(w);
+    const size_t part = (size_t)pl.w_bytes / 2;          // elements per precision part
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error("conv_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return (int)e; }
+        attr_set = true;
+    }
+    const int grid = min(p.items, sm_count());
+    auto launch = [&](int a_part, int w_part, int mode) {
+        tc::Params q = p;
+        q.a_part = a_part; q.wpk = wpk + (size_t)w_part * part; q.pass_mode = mode;
+        tc::conv_tc_kernel<<<grid, tc::kThreads, pl.smem_bytes, st>>>(q);
+    };
+    if (d->precision == 2) {
+        launch(0, 0, tc::PASS_ONLY);
+    } else {
+        launch(0, 0, tc::PASS_FIRST);
+        launch(1, 0, tc::PASS_MID);
+        launch(0, 1, tc::PASS_LAST);
+    }
+    LF_RETURN_LAUNCH();
+}
+
 }  // namespace lf
+
+using namespace lf;
+
+extern "C" int64_t lf_conv_tc_weight_bytes(int taps, int cin, int cout) {
+    if (taps <= 0 || cin <= 0 || cout <= 0) return 0;
+    const int64_t cin_pad = (cin + 15) / 16 * 16, cout_pad = (cout + 15) / 16 * 16;
+    return 2 * taps * cin_pad * cout_pad * 2;
+}
+
+extern "C" int lf_conv_tc_pack_weights(const float* w_packed, void* out, int taps, int cin, int cout, void* stream) {
+    LF_CHECK_ARG(w_packed && out && taps > 0 && cin > 0 && cout > 0, "conv_tc_pack_weights: bad arguments");
+    const int cin_pad = (cin + 15) / 16 * 16, cout_pad = (cout + 15) / 16 * 16;
+    const int64_t per_part = (int64_t)taps * cin_pad * cout_pad;
+    tc::pack_weights_kernel<<<(unsigned)((per_part + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        w_packed, reinterpret_cast<uint16_t*>(out), taps, cin, cout, cin_pad, cout_pad);
+    LF_RETURN_LAUNCH();
+}
+
+extern "C" int lf_conv_tc_supported(const lf_conv_desc* desc) {
+    if (desc == nullptr) return 0;
+    return conv_tc_supported(desc);
+}

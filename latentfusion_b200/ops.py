@@ -229,6 +229,29 @@ def _unpack_weight_grad(gw, weight_shape, kind, depth):
     return gw.permute(2, 0, 1).reshape(-1, cin, 1, 1).contiguous()            # [c][d][ci]
 
 
+_TC_PACK_CACHE = {}
+
+
+def _tc_pack(wf, key):
+    """fp32 packed weights [taps][Cin][Cout] -> bf16 hi|lo UMMA layout for the tcgen05 kernel (cached per
+    parameter version; the pack itself is one small kernel)."""
+    hit = _TC_PACK_CACHE.get(key)
+    if hit is not None:
+        return hit
+    taps, cin, cout = wf.shape
+    nbytes = L.lib().lf_conv_tc_weight_bytes(taps, cin, cout)
+    out = torch.empty(nbytes // 2, device=wf.device, dtype=torch.int16)
+    _call('lf_conv_tc_pack_weights', L.lib().lf_conv_tc_pack_weights, (_p(wf), _p(out), taps, cin, cout, _stream()))
+    if len(_TC_PACK_CACHE) > 256:
+        _TC_PACK_CACHE.clear()
+    _TC_PACK_CACHE[key] = out
+    return out
+
+
+def _tc_ok(desc):
+    return desc.precision != 0 and bool(L.lib().lf_conv_tc_supported(ctypes.byref(desc)))
+
+
 def _desc(kind, nd, n, d, h, w, cin, cout, k, scale, act, slope, norm, precision):
     ndim = {KIND_CONV: nd, KIND_COLLAPSE: 1, KIND_EXPAND: -1}[kind]
     return L.ConvDesc(ndim, n, d, h, w, cin, cout, k, scale, int(act), slope, int(norm), int(precision))
@@ -289,11 +312,18 @@ class _EqConv(torch.autograd.Function):
         rnorm = torch.empty(positions, device=dev, dtype=torch.float32) if norm else None
         desc = _desc(kind, nd, n, d, h, w, gcin, gcout, k, scale, act, slope, norm, precision)
         taps = wf.shape[0]
+        wkey = (weight.data_ptr(), weight._version, tuple(weight.shape), kind)
+        if _tc_ok(desc):
+            wf_arg = _tc_pack(wf, wkey + ('f',))
+        else:                      # shapes the tensor-core kernel does not cover run on the exact fp32 path
+            desc.precision = 0
+            wf_arg = wf
         _call(_conv_name(kind, nd, k, 'fwd'), L.lib().lf_conv_fwd,
-              (ctypes.byref(desc), _p(x), _p(wf), _p(bpk), _p(y), _p(rnorm), _stream()),
+              (ctypes.byref(desc), _p(x), _p(wf_arg), _p(bpk), _p(y), _p(rnorm), _stream()),
               kernels=2 if (norm and (kind == KIND_EXPAND or gcout > 64)) else 1,
               nbytes=4 * (x.numel() + y.numel()), flops=2 * positions * taps * gcin * gcout)
         ctx.save_for_backward(x, y, rnorm, wb)
+        ctx.wkey = wkey
         ctx.cfg = (kind, depth, act, slope, norm, precision, nd, n, d, h, w, gcin, gcout, k, scale,
                    tuple(weight.shape), bias is not None)
         return y
@@ -324,8 +354,13 @@ class _EqConv(torch.autograd.Function):
             bkind = {KIND_CONV: KIND_CONV, KIND_COLLAPSE: KIND_EXPAND, KIND_EXPAND: KIND_COLLAPSE}[kind]
             bnd = {KIND_CONV: nd, KIND_COLLAPSE: 2, KIND_EXPAND: 3}[kind]
             bdesc = _desc(bkind, bnd, n, d, h, w, cout, cin, k, scale, 0, 0.0, 0, precision)
+            if _tc_ok(bdesc):
+                wb_arg = _tc_pack(wb, ctx.wkey + ('b',))
+            else:
+                bdesc.precision = 0
+                wb_arg = wb
             _call(_conv_name(kind, nd, k, 'bwd_data'), lib.lf_conv_fwd,
-                  (ctypes.byref(bdesc), _p(du), _p(wb), None, _p(gx), None, _stream()),
+                  (ctypes.byref(bdesc), _p(du), _p(wb_arg), None, _p(gx), None, _stream()),
                   nbytes=4 * (du.numel() + gx.numel()),
                   flops=2 * (n * h * w * (d if kind == KIND_CONV else 1)) * wb.shape[0] * cin * cout)
         if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
