@@ -24,12 +24,14 @@
 #include "common.cuh"
 
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace lf {
 namespace tc {
 
-constexpr int kProducerWarps = 4;
-constexpr int kThreads = 32 * (kProducerWarps + 1 + 4);    // producers | MMA | epilogue
+constexpr int kProducerWarps = 7;
+constexpr int kMmaWarps = 5;                               // issuer warp m owns M-tiles m, m+4, ...
+constexpr int kThreads = 32 * (kProducerWarps + kMmaWarps + 4);   // producers | MMA issuers | epilogue
 constexpr int kMaxRing = 4;
 constexpr int kMaxTiles = 5;
 
@@ -47,7 +49,17 @@ struct Params {
     int pass_mode;
     uint32_t idesc;
     uint32_t slab_bytes, w_bytes;
+    int debug;                    // dev only (LFB200_TC_DEBUG): 1 skip MMAs, 2 skip producer work, 4 skip epilogue work
+    uint64_t magic_q4, magic_P;   // ceil(2^40 / divisor): exact n / divisor for n < 2^20, divisor < 2^12
 };
+
+__device__ __forceinline__ int fast_div(int n, uint64_t magic) { return (int)(((uint64_t)(uint32_t)n * magic) >> 40); }
+
+// dev-only timeline of CTA 0 (LFB200_TC_DEBUG & 8): [role][event][2] SM clock stamps
+__device__ long long g_dbg[3][64][2];
+__device__ __forceinline__ void dbg_stamp(const Params& p, int role, int idx, int which) {
+    if ((p.debug & 8) && blockIdx.x == 0 && idx < 64) g_dbg[role][idx][which] = clock64();
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -75,6 +87,12 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -87,6 +105,18 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// same, with the two descriptors given as (lo, hi) 32-bit halves (cheap to update in the issue loop)
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 // UMMA shared-memory matrix descriptor, no-swizzle K-major canonical layout
@@ -108,15 +138,119 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));    // one instruction for two values
+    return r;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b, int part) {
-    __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-    if (part) {
-        ha = __float2bfloat16_rn(a - __bfloat162float(ha));
-        hb = __float2bfloat16_rn(b - __bfloat162float(hb));
+    uint32_t h = cvt_bf16x2(a, b);
+    if (part) {      // residual: x - bf16(x), itself rounded to bf16
+        const float ra = a - __uint_as_float(h << 16), rb = b - __uint_as_float(h & 0xffff0000u);
+        h = cvt_bf16x2(ra, rb);
     }
-    return (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+    return h;
 }
 
+// One output position per thread: its Cout accumulators come out of TMEM into registers, so the
+// Equalized/Block epilogue (He scale, bias, LeakyReLU, PixelNorm over channels) is thread-local.
+// NCH = Cout_pad/16 known at compile time (registers hold the whole row); NCH == 0 is the generic
+// two-pass variant for wide layers.  Branch-free: bias is staged zero-padded in smem, LeakyReLU is
+// max(a, slope*a) with slope folded to 1 when disabled, PixelNorm multiplies by a per-row reciprocal.
+template <int NCH, int MODE>
+__device__ __forceinline__ void epilogue_tile(const Params& p, const float* __restrict__ bias_s, uint32_t taddr,
+                                              int64_t opos, bool valid) {
+    constexpr bool kRaw = (MODE == PASS_FIRST || MODE == PASS_MID);
+    constexpr bool kAdd = (MODE == PASS_MID || MODE == PASS_LAST);
+    float* yp = p.y + opos * p.cout;
+    const float slope = p.act ? p.slope : 1.f;
+    if (NCH > 0) {
+        float v[NCH > 0 ? NCH * 16 : 16];
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            float t16[16];
+            tmem_ld16(taddr + ch * 16, t16);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[ch * 16 + i] = t16[i];
+        }
+        if (valid) {
+            if (kAdd) {
+#pragma unroll
+                for (int i = 0; i < NCH * 16; i += 4) {
+                    if (i < p.cout) {
+                        const float4 o = *reinterpret_cast<const float4*>(yp + i);
+                        v[i] += o.x; v[i + 1] += o.y; v[i + 2] += o.z; v[i + 3] += o.w;
+                    }
+                }
+            }
+            if (!kRaw) {
+                float ss = 0.f;
+#pragma unroll
+                for (int i = 0; i < NCH * 16; ++i) {
+                    float a = v[i] * p.scale + bias_s[i];
+                    a = fmaxf(a, a * slope);
+                    v[i] = a;
+                    ss += a * a;
+                }
+                if (p.norm) {
+                    const float rn = sqrtf(ss / (float)p.cout + 1e-8f);
+                    const float inv = 1.f / rn;
+#pragma unroll
+                    for (int i = 0; i < NCH * 16; ++i) v[i] *= inv;
+                    if (p.rnorm != nullptr) p.rnorm[opos] = rn;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NCH * 16; i += 4)
+                if (i < p.cout) *reinterpret_cast<float4*>(yp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+        __syncwarp();
+    } else {
+        float ss = 0.f;
+        if (p.norm && !kRaw) {
+            for (int cb = 0; cb < p.cout_pad; cb += 16) {
+                float v[16];
+                __syncwarp();
+                tmem_ld16(taddr + cb, v);
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float a = v[i];
+                        if (kAdd && cb + i < p.cout) a += yp[cb + i];
+                        a = a * p.scale + bias_s[cb + i];
+                        a = fmaxf(a, a * slope);
+                        ss += a * a;
+                    }
+                }
+            }
+        }
+        const float rn = sqrtf(ss / (float)p.cout + 1e-8f);
+        const float inv = (p.norm && !kRaw) ? 1.f / rn : 1.f;
+        for (int cb = 0; cb < p.cout_pad; cb += 16) {
+            float v[16];
+            __syncwarp();
+            tmem_ld16(taddr + cb, v);
+            if (valid) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float a = v[i];
+                    if (cb + i < p.cout) {
+                        if (kAdd) a += yp[cb + i];
+                        if (!kRaw) {
+                            a = a * p.scale + bias_s[cb + i];
+                            a = fmaxf(a, a * slope) * inv;
+                        }
+                        yp[cb + i] = a;
+                    }
+                }
+            }
+        }
+        if (valid && p.norm && !kRaw && p.rnorm != nullptr) p.rnorm[opos] = rn;
+        __syncwarp();
+    }
+}
+
+template <int NCH>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -126,10 +260,14 @@ conv_tc_kernel(const __grid_constant__ Params p) {
     uint8_t* tail = smem + (size_t)p.ring * p.slab_bytes + p.w_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail);                 // [ring] full, [ring] empty, [2] acc_full, [2] acc_empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxRing + 4);
+    float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxRing + 6);     // [cout_pad], zero padded
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxRing);
     const uint32_t bar_accf = smem_u32(bars + 2 * kMaxRing), bar_acce = smem_u32(bars + 2 * kMaxRing + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index broadcast from lane 0 so the compiler knows it is warp-uniform: everything derived from it
+    // (tile id, TMEM/descriptor addresses) can then live in uniform registers, which UTCHMMA consumes directly
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
 
     // ---- one-time setup: weights -> smem, barriers, TMEM
     {
@@ -137,10 +275,12 @@ conv_tc_kernel(const __grid_constant__ Params p) {
         uint4* dst = reinterpret_cast<uint4*>(smem + (size_t)p.ring * p.slab_bytes);
         for (uint32_t i = threadIdx.x; i < p.w_bytes / 16; i += kThreads) dst[i] = __ldg(src + i);
         fence_proxy_async();
+        for (int i = threadIdx.x; i < p.cout_pad; i += kThreads)
+            bias_s[i] = (p.bias != nullptr && i < p.cout) ? p.bias[i] : 0.f;
     }
     if (threadIdx.x == 0) {
-        for (int i = 0; i < p.ring; ++i) { mbar_init(bar_full + 8 * i, kProducerWarps * 32); mbar_init(bar_empty + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, 128); }
+        for (int i = 0; i < p.ring; ++i) { mbar_init(bar_full + 8 * i, kProducerWarps * 32); mbar_init(bar_empty + 8 * i, min(p.NT, kMmaWarps)); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, min(p.NT, kMmaWarps)); mbar_init(bar_acce + 8 * i, 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kProducerWarps) {
@@ -171,47 +311,63 @@ conv_tc_kernel(const __grid_constant__ Params p) {
             for (int e = d0 - p.hz; e <= d1 - 1 + p.hz; ++e, ++kcount) {
                 const uint32_t slot = kcount % p.ring;
                 mbar_wait(bar_empty + 8 * slot, ((kcount / p.ring) & 1) ^ 1);
-                if (e >= 0 && e < p.d) {
+                if (tid == 0) dbg_stamp(p, 0, kcount, 0);
+                if (e >= 0 && e < p.d && !(p.debug & 2)) {
                     uint8_t* slab = smem + (size_t)slot * p.slab_bytes;
                     const float* plane = p.x + ((int64_t)n * p.d + e) * p.h * p.w * (int64_t)p.cin;
                     const int units = rows_in * p.P * q4;
-                    for (int u0 = tid; u0 < units; u0 += 4 * kProducerWarps * 32) {
-                        float4 v[4];
-                        int upos[4], uq[4];
+                    constexpr int kBatch = 8;           // loads in flight per thread
+                    for (int u0 = tid; u0 < units; u0 += kBatch * kProducerWarps * 32) {
+                        float4 v[kBatch];
+                        int udst[kBatch];               // byte offset inside the slab, -1 = nothing to do
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                        for (int j = 0; j < kBatch; ++j) {
                             const int u = u0 + j * kProducerWarps * 32;
                             v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            upos[j] = -1; uq[j] = 0;
+                            udst[j] = -1;
                             if (u < units) {
-                                const int pos = u / q4, q = u - pos * q4;
-                                const int r = pos / p.P, c = pos - r * p.P;
+                                const int pos = fast_div(u, p.magic_q4), q = u - pos * q4;
+                                const int r = fast_div(pos, p.magic_P), c = pos - r * p.P;
                                 const int yy = y0 + r - halo, xx = c - halo;
-                                upos[j] = pos; uq[j] = q;
+                                udst[j] = (q >> 1) * (int)lbo_a + pos * 16 + (q & 1) * 8;
                                 if (yy >= 0 && yy < p.h && xx >= 0 && xx < p.w && q * 4 < p.cin)
                                     v[j] = ldg4(plane + ((int64_t)yy * p.w + xx) * p.cin + q * 4);
                             }
                         }
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (upos[j] < 0) continue;
+                        for (int j = 0; j < kBatch; ++j) {
+                            if (udst[j] < 0) continue;
                             const uint32_t lo = pack_bf16x2(v[j].x, v[j].y, p.a_part);
                             const uint32_t hi = pack_bf16x2(v[j].z, v[j].w, p.a_part);
-                            uint8_t* dst = slab + (size_t)(uq[j] >> 1) * lbo_a + (size_t)upos[j] * 16 + (uq[j] & 1) * 8;
-                            *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
+                            *reinterpret_cast<uint2*>(slab + udst[j]) = make_uint2(lo, hi);
                         }
                     }
                     fence_proxy_async();                // generic-proxy stores -> visible to the tensor core
                 }
                 mbar_arrive(bar_full + 8 * slot);
+                if (tid == 0) dbg_stamp(p, 0, kcount, 1);
             }
         }
-    } else if (warp == kProducerWarps) {
-        // =========================== MMA ISSUER (one thread) ===========================
-        if (lane == 0) {
+    } else if (warp < kProducerWarps + kMmaWarps) {
+        // =========================== MMA ISSUERS (warp m owns M-tile m) ===========================
+        // The whole warp runs this loop in lock-step so every descriptor/address lives in UNIFORM registers
+        // (UTCHMMA takes uniform operands; a lane-0-only branch makes the compiler shuttle them through
+        // R2UR + an elect waterfall, ~12 instructions per MMA); only the issue itself is elected.
+        const int my_tile = warp - kProducerWarps;
+        if (my_tile < p.NT) {
             uint32_t kbase = 0;                         // running plane count at the start of the item
             uint32_t step = 0;                          // running step (accumulator) count
             const uint32_t lbo_b = (uint32_t)p.cout_pad * 16u;
+            // descriptor pieces (16-byte units): lo = start | LBO << 16 ; hi = SBO(128 B) | version 1 << 14
+            const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+            const uint32_t a_lo_const = (lbo_a >> 4) << 16, b_lo_const = (lbo_b >> 4) << 16;
+            const uint32_t a_kstride = 2 * (lbo_a >> 4), b_kstride = 2 * (lbo_b >> 4);
+            const uint32_t tap_stride = (uint32_t)kchunks * (lbo_b >> 4);
+            const int ksteps = p.cin_pad / 16;
+            // hot-loop operands copied out of the (constant-bank) parameter block: the "memory" clobber of the
+            // MMA asm would otherwise force a constant reload (LDCU, ~40 cycles) on every loop test
+            const int K = p.k, HZ = p.hz, NT = p.NT, RING = p.ring, DEPTH = p.d, DBG = p.debug;
+            const uint32_t PP = (uint32_t)p.P, IDESC = p.idesc, COUT_PAD = (uint32_t)p.cout_pad, SLAB = p.slab_bytes;
             for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
                 const int dchunk = item % p.ndchunks;
                 const int d0 = dchunk * p.DC, d1 = min(p.d, d0 + p.DC);
@@ -226,34 +382,43 @@ conv_tc_kernel(const __grid_constant__ Params p) {
                     const uint32_t buf = step & 1;
                     mbar_wait(bar_acce + 8 * buf, ((step >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    for (int t = 0; t < p.NT; ++t) {
-                        const uint32_t d_tmem = tmem_base + (buf * p.NT + t) * p.cout_pad;
+                    if (my_tile == 0 && lane == 0) dbg_stamp(p, 1, step, 0);
+                    // Issue loop kept to a handful of instructions per MMA: the descriptor's high word is
+                    // constant, the low word is (LBO field | start>>4) and only the start changes, by +1 per
+                    // dx, +P per dy, +2*LBO per k-step (all in 16-byte units).
+                    for (int t = my_tile; t < NT; t += kMmaWarps) {
+                        const uint32_t d_tmem = tmem_base + (buf * NT + t) * COUT_PAD;
                         uint32_t acc = 0;
-                        for (int dz = 0; dz <= 2 * p.hz; ++dz) {
-                            const int e = d + dz - p.hz;
-                            if (e < 0 || e >= p.d) continue;           // zero plane: contributes nothing
-                            const uint32_t kc = kbase + (uint32_t)(e - (d0 - p.hz));
-                            const uint32_t slab = slabs + (kc % p.ring) * p.slab_bytes;
-                            for (int dy = 0; dy < p.k; ++dy) {
-                                for (int dx = 0; dx < p.k; ++dx) {
-                                    const int tap = (dz * p.k + dy) * p.k + dx;
-                                    const uint32_t a0 = slab + (uint32_t)(t * 128 + dy * p.P + dx) * 16u;
-                                    const uint32_t b0 = wsm + (uint32_t)(tap * kchunks) * lbo_b;
-                                    for (int ks = 0; ks < p.cin_pad / 16; ++ks) {
-                                        const uint64_t ad = make_desc(a0 + 2 * ks * lbo_a, lbo_a, 128);
-                                        const uint64_t bd = make_desc(b0 + 2 * ks * lbo_b, lbo_b, 128);
-                                        umma_bf16(d_tmem, ad, bd, p.idesc, acc);
+                        for (int dz = 0; dz <= 2 * HZ; ++dz) {
+                            const int e = d + dz - HZ;
+                            if (e < 0 || e >= DEPTH) continue;         // zero plane: contributes nothing
+                            const uint32_t kc = kbase + (uint32_t)(e - (d0 - HZ));
+                            uint32_t a_row = a_lo_const | (((slabs + (kc % RING) * SLAB) >> 4) + (uint32_t)t * 128u);
+                            uint32_t b_cur = b_lo_const | ((wsm >> 4) + (uint32_t)(dz * K * K) * tap_stride);
+                            for (int dy = 0; dy < K; ++dy) {
+                                uint32_t a_cur = a_row;
+                                for (int dx = 0; dx < K; ++dx) {
+                                    uint32_t ak = a_cur, bk = b_cur;
+                                    for (int ks = 0; ks < ksteps; ++ks) {
+                                        if (!(DBG & 1) && elect_one()) umma_bf16_lohi(d_tmem, ak, desc_hi, bk, desc_hi, IDESC, acc);
                                         acc = 1;
+                                        ak += a_kstride; bk += b_kstride;
                                     }
+                                    a_cur += 1;
+                                    b_cur += tap_stride;
                                 }
+                                a_row += PP;
                             }
                         }
                     }
-                    umma_commit(bar_accf + 8 * buf);                   // accumulators of this step complete
+                    if (elect_one()) umma_commit(bar_accf + 8 * buf);  // accumulators of this step complete
+                    if (my_tile == 0 && lane == 0) dbg_stamp(p, 1, step, 1);
                     // release planes that no later step of this item reads
                     const int first_rel = (d - d0);                    // plane index d - hz relative to item
                     const int last_rel = (d == d1 - 1) ? nplanes - 1 : first_rel;
-                    for (int pl = first_rel; pl <= last_rel; ++pl) umma_commit(bar_empty + 8 * ((kbase + pl) % p.ring));
+                    for (int pl = first_rel; pl <= last_rel; ++pl)
+                        if (elect_one()) umma_commit(bar_empty + 8 * ((kbase + pl) % p.ring));
+                    __syncwarp();
                 }
                 kbase += nplanes;
             }
@@ -262,7 +427,6 @@ conv_tc_kernel(const __grid_constant__ Params p) {
         // =========================== EPILOGUE (4 warps = 128 TMEM lanes) ===========================
         const int wq = warp & 3;                       // TMEM lane quarter this warp may access
         uint32_t step = 0;
-        const float inv_c = 1.f / (float)p.cout;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
             int it = item;
             const int dchunk = it % p.ndchunks; it /= p.ndchunks;
@@ -273,67 +437,23 @@ conv_tc_kernel(const __grid_constant__ Params p) {
                 const uint32_t buf = step & 1;
                 mbar_wait(bar_accf + 8 * buf, (step >> 1) & 1);
                 tc_fence_after();
-                for (int t = 0; t < p.NT; ++t) {
+                if (wq == 0 && lane == 0) dbg_stamp(p, 2, step, 0);
+                for (int t = 0; t < ((p.debug & 4) ? 0 : p.NT); ++t) {
                     const int q = t * 128 + wq * 32 + lane;
-                    const int r = q / p.P, c = q - r * p.P;
+                    const int r = fast_div(q, p.magic_P), c = q - r * p.P;
                     const bool valid = (r < p.R) && (c < p.w) && (y0 + r < p.h);
                     const int64_t opos = (((int64_t)n * p.d + d) * p.h + (y0 + r)) * p.w + c;
                     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (buf * p.NT + t) * p.cout_pad;
-                    float* yp = p.y + opos * p.cout;
-                    const bool raw_out = (p.pass_mode == PASS_FIRST || p.pass_mode == PASS_MID);
-                    const bool add_in = (p.pass_mode == PASS_MID || p.pass_mode == PASS_LAST);
-                    float ss = 0.f;
-                    if (p.norm && !raw_out) {
-                        for (int cb = 0; cb < p.cout_pad; cb += 16) {
-                            float v[16];
-                            tmem_ld16(taddr + cb, v);
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const int co = cb + i;
-                                if (co < p.cout) {
-                                    float a = v[i];
-                                    if (add_in && valid) a += yp[co];
-                                    a = a * p.scale + (p.bias ? __ldg(p.bias + co) : 0.f);
-                                    if (p.act) a = a > 0.f ? a : a * p.slope;
-                                    ss += a * a;
-                                }
-                            }
-                        }
+                    switch (p.pass_mode) {
+                        case PASS_ONLY:  epilogue_tile<NCH, PASS_ONLY>(p, bias_s, taddr, opos, valid); break;
+                        case PASS_FIRST: epilogue_tile<NCH, PASS_FIRST>(p, bias_s, taddr, opos, valid); break;
+                        case PASS_MID:   epilogue_tile<NCH, PASS_MID>(p, bias_s, taddr, opos, valid); break;
+                        default:         epilogue_tile<NCH, PASS_LAST>(p, bias_s, taddr, opos, valid); break;
                     }
-                    const float rn = sqrtf(ss * inv_c + 1e-8f);
-                    for (int cb = 0; cb < p.cout_pad; cb += 16) {
-                        float v[16];
-                        tmem_ld16(taddr + cb, v);
-                        if (!valid) continue;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int co = cb + i;
-                            float a = v[i];
-                            if (co < p.cout) {
-                                if (add_in) a += yp[co];
-                                if (!raw_out) {
-                                    a = a * p.scale + (p.bias ? __ldg(p.bias + co) : 0.f);
-                                    if (p.act) a = a > 0.f ? a : a * p.slope;
-                                    if (p.norm) a = a / rn;
-                                }
-                            }
-                            v[i] = a;
-                        }
-                        if ((p.cout & 3) == 0) {
-#pragma unroll
-                            for (int i = 0; i < 16; i += 4)
-                                if (cb + i < p.cout)
-                                    *reinterpret_cast<float4*>(yp + cb + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (cb + i < p.cout) yp[cb + i] = v[i];
-                        }
-                    }
-                    if (valid && p.norm && !raw_out && p.rnorm != nullptr) p.rnorm[opos] = rn;
                 }
                 tc_fence_before();
                 mbar_arrive(bar_acce + 8 * buf);
+                if (wq == 0 && lane == 0) dbg_stamp(p, 2, step, 1);
             }
         }
     }
@@ -383,12 +503,13 @@ static bool make_plan(const lf_conv_desc* d, Plan& pl) {
     const int hz = (d->ndim == 3) ? halo : 0;
     pl.taps = (d->ndim == 3) ? d->k * d->k * d->k : d->k * d->k;
     pl.P = d->w + 2 * halo;
+    if (pl.P >= 4096 || pl.cin_pad > 1024) return false;
     // accumulators: 2 buffers x NT tiles x cout_pad columns <= 512
     int nt_max = 512 / (2 * pl.cout_pad);
     if (nt_max > kMaxTiles) nt_max = kMaxTiles;
     if (nt_max < 1) return false;
     pl.w_bytes = (uint32_t)pl.taps * (pl.cin_pad / 8) * pl.cout_pad * 16;
-    const uint32_t budget = 227 * 1024 - 256;
+    const uint32_t budget = 227 * 1024 - 256 - 1024;
     if (pl.w_bytes + 4096 > budget) return false;
     pl.ring = (hz > 0) ? kMaxRing : 2;
     // largest R such that tiles and smem fit
@@ -405,7 +526,7 @@ static bool make_plan(const lf_conv_desc* d, Plan& pl) {
     int pos = (pl.R + 2 * halo) * pl.P + 2 * halo;
     pl.pos_alloc = round_up(pos - 4, 8) + 4;
     pl.slab_bytes = (uint32_t)(pl.cin_pad / 8) * pl.pos_alloc * 16;
-    pl.smem_bytes = pl.slab_bytes * pl.ring + pl.w_bytes + 256;
+    pl.smem_bytes = pl.slab_bytes * pl.ring + pl.w_bytes + 256 + 1024;
     // the last tile may read up to (NT*128 + (k-1)*P + k-1 - pos_alloc) positions past a k-chunk: it must stay
     // inside the allocation; chunks are followed by other chunks / the weight buffer, check the very last one
     const int overrun = pl.NT * 128 + (d->k - 1) * pl.P + (d->k - 1) - pl.pos_alloc;
@@ -442,22 +563,29 @@ int conv_tc_launch(const lf_conv_desc* d, const float* x, const float* w, const 
     p.nstrips = pl.nstrips; p.ndchunks = pl.ndchunks; p.items = d->n * pl.nstrips * pl.ndchunks;
     p.scale = d->scale; p.act = d->act; p.slope = d->slope; p.norm = d->norm;
     p.slab_bytes = pl.slab_bytes; p.w_bytes = pl.w_bytes;
+    { const char* dbg = getenv("LFB200_TC_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+    p.magic_q4 = ((1ull << 40) + (pl.cin_pad / 4) - 1) / (uint64_t)(pl.cin_pad / 4);
+    p.magic_P = ((1ull << 40) + pl.P - 1) / (uint64_t)pl.P;
     // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1,
     // K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(pl.cout_pad >> 3) << 17) | ((128u >> 4) << 24);
     const uint16_t* wpk = reinterpret_cast<const uint16_t*>(w);
     const size_t part = (size_t)pl.w_bytes / 2;          // elements per precision part
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    void (*kern)(tc::Params) = nullptr;
+    switch (((d->cout & 3) == 0 && pl.cout_pad <= 32) ? pl.cout_pad / 16 : 0) {
+        case 1: kern = tc::conv_tc_kernel<1>; break;
+        case 2: kern = tc::conv_tc_kernel<2>; break;
+        default: kern = tc::conv_tc_kernel<0>; break;
+    }
+    {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("conv_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return (int)e; }
-        attr_set = true;
     }
     const int grid = min(p.items, sm_count());
     auto launch = [&](int a_part, int w_part, int mode) {
         tc::Params q = p;
         q.a_part = a_part; q.wpk = wpk + (size_t)w_part * part; q.pass_mode = mode;
-        tc::conv_tc_kernel<<<grid, tc::kThreads, pl.smem_bytes, st>>>(q);
+        kern<<<grid, tc::kThreads, pl.smem_bytes, st>>>(q);
     };
     if (d->precision == 2) {
         launch(0, 0, tc::PASS_ONLY);
@@ -486,6 +614,10 @@ extern "C" int lf_conv_tc_pack_weights(const float* w_packed, void* out, int tap
     tc::pack_weights_kernel<<<(unsigned)((per_part + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         w_packed, reinterpret_cast<uint16_t*>(out), taps, cin, cout, cin_pad, cout_pad);
     LF_RETURN_LAUNCH();
+}
+
+extern "C" int lf_debug_tc_timeline(long long* host_out /* [3][64][2] */) {
+    return (int)cudaMemcpyFromSymbol(host_out, tc::g_dbg, sizeof(long long) * 3 * 64 * 2);
 }
 
 extern "C" int lf_conv_tc_supported(const lf_conv_desc* desc) {

@@ -7,6 +7,7 @@ kernels index (``[N][D][H][W][C]``).
 """
 import ctypes
 import math
+import weakref
 
 import torch
 
@@ -235,16 +236,16 @@ _TC_PACK_CACHE = {}
 def _tc_pack(wf, key):
     """fp32 packed weights [taps][Cin][Cout] -> bf16 hi|lo UMMA layout for the tcgen05 kernel (cached per
     parameter version; the pack itself is one small kernel)."""
-    hit = _TC_PACK_CACHE.get(key)
-    if hit is not None:
-        return hit
+    hit = _TC_PACK_CACHE.get(key[1:])
+    if hit is not None and hit[0]() is key[0]:          # same live tensor object, same version
+        return hit[1]
     taps, cin, cout = wf.shape
     nbytes = L.lib().lf_conv_tc_weight_bytes(taps, cin, cout)
     out = torch.empty(nbytes // 2, device=wf.device, dtype=torch.int16)
     _call('lf_conv_tc_pack_weights', L.lib().lf_conv_tc_pack_weights, (_p(wf), _p(out), taps, cin, cout, _stream()))
     if len(_TC_PACK_CACHE) > 256:
         _TC_PACK_CACHE.clear()
-    _TC_PACK_CACHE[key] = out
+    _TC_PACK_CACHE[key[1:]] = (weakref.ref(key[0]), out)
     return out
 
 
@@ -312,7 +313,7 @@ class _EqConv(torch.autograd.Function):
         rnorm = torch.empty(positions, device=dev, dtype=torch.float32) if norm else None
         desc = _desc(kind, nd, n, d, h, w, gcin, gcout, k, scale, act, slope, norm, precision)
         taps = wf.shape[0]
-        wkey = (weight.data_ptr(), weight._version, tuple(weight.shape), kind)
+        wkey = (weight, id(weight), weight._version, kind)
         if _tc_ok(desc):
             wf_arg = _tc_pack(wf, wkey + ('f',))
         else:                      # shapes the tensor-core kernel does not cover run on the exact fp32 path

@@ -52,14 +52,18 @@ def test_conv_tc_forward_backward(nd, n, cin, cout, size, k, precision):
     ref = ref_conv(x, w, b, True, norm)
     tol = dict(atol=1e-4, rtol=1e-3) if precision == 1 else dict(atol=3e-2, rtol=3e-2)
     torch.testing.assert_close(y.double(), ref, **tol)
-    # backward to the input goes through the same kernel with flipped/transposed weights
-    g = torch.randn_like(y)
-    y.backward(g)
-    x0 = x.clone().requires_grad_(True)
-    y0 = ops.eq_conv(x0, w, b, act=True, norm=norm, precision=0)
-    y0.backward(g)
+    # backward to the input goes through the same kernel with flipped/transposed weights.  It is checked on
+    # the LINEAR layer (no LeakyReLU/PixelNorm): with the non-linearity, outputs within rounding distance of 0
+    # legitimately flip the LeakyReLU gate between two precisions, which is not a kernel property.
+    xl = x.clone().requires_grad_(True)
+    yl = ops.eq_conv(xl, w, b, act=False, norm=False, precision=precision)
+    g = torch.randn_like(yl)
+    yl.backward(g)
+    xr = x.double().clone().requires_grad_(True)
+    conv = F.conv3d if nd == 3 else F.conv2d
+    (conv(xr, w.double(), None, padding=k // 2) * math.sqrt(2.0 / w[0].numel())).backward(g.double())
     gtol = dict(atol=2e-4, rtol=2e-3) if precision == 1 else dict(atol=5e-2, rtol=5e-2)
-    torch.testing.assert_close(xt.grad, x0.grad, **gtol)
+    torch.testing.assert_close(xl.grad.double(), xr.grad, **gtol)
 
 
 def test_conv_tc_unsupported_shape_falls_back_to_exact_kernel():

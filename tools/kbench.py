@@ -76,7 +76,17 @@ def main():
         wgt = torch.randn(C, C, 3, 3, 3, device=dev)
         b = torch.randn(C, device=dev)
         flops = 2 * N * S ** 3 * 27 * C * C
-        med, best = timeit(lambda: ops.eq_conv(x, wgt, b, act=True, norm=True, precision=a.precision), a.iters, flush)
+        # straight through the C ABI (weights pre-packed once) so the number is the kernel, not the Python wrapper
+        import ctypes, math
+        from latentfusion_b200 import _lib as L
+        wf, _ = ops._pack_weight(wgt, ops.KIND_CONV, 0)
+        desc = ops._desc(ops.KIND_CONV, 3, N, S, S, S, C, C, 3, math.sqrt(2.0 / (27 * C)), True, 0.2, True, a.precision)
+        warg = ops._tc_pack(wf, (wgt, id(wgt), wgt._version, 0, 'f')) if a.precision else wf
+        y = torch.empty_like(x)
+        rn = torch.empty(N * S ** 3, device=dev)
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        args = (ctypes.byref(desc), ops._p(x), ops._p(warg), ops._p(b), ops._p(y), ops._p(rn), st)
+        med, best = timeit(lambda: L.check(L.lib().lf_conv_fwd(*args), 'conv'), a.iters, flush)
         out[f'conv3d_block_fwd[p{a.precision}]'] = dict(ms=med, best_ms=best, TFs=flops / med / 1e9,
                                                      GBs=8 * x.numel() / med / 1e6)
         x2 = ops.to_cl(torch.randn(N, C, S, S, S, device=dev))
@@ -84,6 +94,18 @@ def main():
         med, best = timeit(lambda: ops.eq_conv(x2, w2, b, act=True, norm=True, kind=ops.KIND_COLLAPSE, depth=S,
                                                precision=0), a.iters, flush)
         out['collapse_fwd'] = dict(ms=med, GBs=4 * x2.numel() / med / 1e6)
+    if os.environ.get('LFB200_TC_DEBUG') and int(os.environ['LFB200_TC_DEBUG']) & 8:
+        import ctypes, numpy as np
+        from latentfusion_b200 import _lib as L
+        buf = np.zeros((3, 64, 2), dtype=np.int64)
+        torch.cuda.synchronize()
+        L.lib()._handle if False else None
+        fn = ctypes.CDLL(L.LIB_PATH).lf_debug_tc_timeline
+        fn(buf.ctypes.data_as(ctypes.c_void_p))
+        t0 = buf[buf > 0].min()
+        for role, name in enumerate(('producer(plane)', 'mma(step)', 'epilogue(step)')):
+            rows = [(i, int(buf[role, i, 0] - t0), int(buf[role, i, 1] - t0)) for i in range(40) if buf[role, i, 0] > 0]
+            print(name, ' '.join(f'{i}:[{a},{b}]' for i, a, b in rows[:20]))
     print(json.dumps(out, indent=1))
 
 
