@@ -242,7 +242,9 @@ class Camera(nn.Module):
                           self.viewport_height), dim=1)
         k = torch.stack((self.u0, self.v0, self.fu, self.fv), dim=1)
         tail = torch.zeros(n, CAM_STRIDE - 23, device=dev)
-        const = torch.tensor([self.z_span, cube_size / 2.0], device=dev).expand(n, 2)
+        # (torch.full, not torch.tensor(list): no host->device copy, so the call is CUDA-graph capturable)
+        const = torch.cat((torch.full((n, 1), float(self.z_span), device=dev),
+                           torch.full((n, 1), cube_size / 2.0, device=dev)), dim=1)
         return torch.cat((m, vp, k, self.znear.unsqueeze(1), const, tail), dim=1)
 
     def c2o_block(self, cube_size):
@@ -256,9 +258,12 @@ class Camera(nn.Module):
         return torch.cat((m, vp, k, self.znear.unsqueeze(1), self.zfar.unsqueeze(1), cube, tail), dim=1)
 
     # ---- image <-> viewport crops (2-D; observation pre-processing and the loss head)
+    def _full_viewport(self):
+        z = torch.zeros(self.length, 1, device=self.device)
+        return torch.cat((z, z, z + float(self.width), z + float(self.height)), dim=1)
+
     def uncrop(self, image=None, scale_mode='nearest', scale=1.0):
-        full = self._like(viewport=torch.tensor((0, 0, self.width, self.height), dtype=torch.float32,
-                                                device=self.device).view(1, 4).expand(self.length, -1))
+        full = self._like(viewport=self._full_viewport())
         if image is None:
             return full
         w, h = int(self.width * scale), int(self.height * scale)

@@ -17,7 +17,9 @@ PRECISION_FP32 = 0      # exact fp32 FFMA path
 PRECISION_BF16X3 = 1    # tcgen05, bf16 hi/lo split (3 MMAs), ~2^-16 relative
 PRECISION_BF16 = 2      # tcgen05, plain bf16 operands, fp32 accumulate
 
-_default_precision = PRECISION_FP32
+import os as _os
+
+_default_precision = int(_os.environ.get('LFB200_PRECISION', PRECISION_FP32))
 
 
 def set_default_precision(p):

@@ -241,8 +241,12 @@ class GradientPoseEstimator(PoseEstimator):
 
     def __init__(self, *, learning_rate, num_samples, num_iters, converge_threshold, converge_patience,
                  lr_reduce_patience=25, lr_reduce_threshold=1e-5, lr_reduce_factor=0.5, track_stats=False,
-                 loss_schedules=None, optimizer='adamw', **kwargs):
+                 loss_schedules=None, optimizer='adamw', cuda_graph=True, graph_chunk=16, **kwargs):
         super().__init__(**kwargs)
+        # B200 path: capture one loop body as a CUDA graph (pose/refine_graph.py).  Falls back to the eager
+        # loop for configurations the graphed step does not cover (non-Adam optimisers, latent loss, custom
+        # loss functions, CPU tensors).
+        self.cuda_graph, self.graph_chunk = cuda_graph, graph_chunk
         self.learning_rate, self.num_samples, self.num_iters = learning_rate, num_samples, num_iters
         self.optimizer = optimizer
         self.lr_reduce_patience, self.lr_reduce_threshold = lr_reduce_patience, lr_reduce_threshold
@@ -277,7 +281,50 @@ class GradientPoseEstimator(PoseEstimator):
             raise ValueError(f"Unknow optimizer {name!r}")
         return table[name](*args, **kwargs)
 
+    def _can_graph(self, cameras):
+        return (self.cuda_graph and self.optimizer == 'adam' and self.loss_func is default_pose_loss
+                and self.loss_weights.get('latent', 0.0) == 0.0 and cameras.device.type == 'cuda')
+
+    def _optimize_camera_graphed(self, z_obj, target_obs, cameras, iters, ranking):
+        from .refine_graph import GraphedRefiner
+        refiner = GraphedRefiner(self, z_obj, target_obs, cameras, chunk=min(self.graph_chunk, max(iters, 1)))
+        refiner.capture()
+        stats, history, converge_count = {}, [], 0
+        gt_cam = target_obs.camera
+        gt_quat, gt_trans = gt_cam.quaternion.detach().cpu(), gt_cam.translation.detach().cpu()
+        step, done = 0, False
+        while step < iters and not done:
+            count = min(refiner.chunk, iters - step)
+            hist = refiner.run_chunk(step, count)
+            for i in range(count):
+                rank_loss = hist['rank'][i]
+                snapshot = refiner.camera_at(hist['lq'][i], hist['tr'][i])
+                if self.return_camera_history:
+                    history.append((rank_loss, snapshot))
+                delta = self._track_best_items(ranking, step, items=snapshot, loss=rank_loss)
+                if self.track_stats:
+                    angle = three.quaternion.angular_distance(snapshot.quaternion, gt_quat).squeeze()
+                    trans = torch.norm(snapshot.translation - gt_trans, dim=1).squeeze()
+                    weights = copy.copy(self.loss_weights)
+                    weights.update({k: s.get(step) for k, s in self.loss_schedules.items()})
+                    self._record_stat_dict(stats, {
+                        **{f'{k}_loss': hist['terms'][i][j] for j, k in enumerate(refiner.TERMS)},
+                        **{f'{k}_weight': v for k, v in weights.items()},
+                        'delta': delta, 'converge_count': converge_count, 'angle_dist': angle,
+                        'trans_dist': trans, 'optim_loss': hist['optim'][i], 'rank_loss': rank_loss})
+                if delta < self.converge_threshold:
+                    converge_count += 1
+                elif delta > self.converge_threshold:
+                    converge_count = 0
+                step += 1
+                if converge_count >= self.converge_patience:
+                    done = True          # iterations already replayed past this point are discarded
+                    break
+        return stats, history
+
     def _optimize_camera(self, z_obj, target_obs, cameras, iters, ranking):
+        if self._can_graph(cameras):
+            return self._optimize_camera_graphed(z_obj, target_obs, cameras, iters, ranking)
         params = [pu.parameterize_camera(c, optimize_viewport=True) for c in cameras]
         optimizers, schedulers = [], []
         for cam in params:

@@ -1,0 +1,168 @@
+"""CUDA-graph execution of the pose-refinement iteration.
+
+One body of the reference's ``GradientPoseEstimator._optimize_camera`` loop (pose/estimation.py:601-677)
+— camera assembly, ``render_latent_object`` forward, ``default_pose_loss``, backward to the 10 camera
+floats of each hypothesis, Adam step, ReduceLROnPlateau step — is expressed as device-only work (no
+``.item()``/``.cpu()`` inside), captured once into a ``torch.cuda.CUDAGraph`` and replayed.  The
+reference issues ~300 kernel launches and ~10 host synchronisations per iteration from Python; a replay
+is one ``cudaGraphLaunch``.
+
+Semantics kept identical to the reference's N independent optimisers:
+* Adam is elementwise, so N ``optim.Adam`` instances over ([3],[3],[4]) tensors equal one update over
+  ([N,3],[N,3],[N,4]) with a per-row learning rate (``torch/optim/adam.py`` single-tensor maths);
+* ``ReduceLROnPlateau(mode='min', threshold_mode='rel', cooldown=0, min_lr=0, eps=1e-8)`` is evaluated per
+  row on device with the same update order (optimizer step, then scheduler step on this iteration's loss);
+* per-iteration snapshots (ranking losses, loss terms, detached camera parameters) are written to device
+  history buffers and drained every ``chunk`` iterations, where the host replays the reference's ranking /
+  convergence bookkeeping iteration by iteration (extra iterations past convergence are discarded).
+"""
+import copy
+
+import torch
+
+from .. import ops
+from ..modules.geometry import Camera
+
+
+class _BatchedAdamPlateau:
+    """Adam + ReduceLROnPlateau for N independent hypotheses, state on device, capturable."""
+
+    def __init__(self, params, n, lr, patience, threshold, factor, betas=(0.9, 0.999), eps=1e-8):
+        dev = params[0].device
+        self.params = params
+        self.b1, self.b2, self.eps = betas[0], betas[1], eps
+        self.m = [torch.zeros_like(p) for p in params]
+        self.v = [torch.zeros_like(p) for p in params]
+        self.step_count = torch.zeros((), device=dev)
+        self.lr = torch.full((n, 1), float(lr), device=dev)
+        self.best = torch.full((n,), float('inf'), device=dev)
+        self.num_bad = torch.zeros(n, device=dev)
+        self.patience, self.threshold, self.factor = float(patience), float(threshold), float(factor)
+
+    @torch.no_grad()
+    def step(self, rank_loss):
+        self.step_count += 1
+        bc1 = 1 - self.b1 ** self.step_count
+        bc2_sqrt = (1 - self.b2 ** self.step_count).sqrt()
+        for p, m, v in zip(self.params, self.m, self.v):
+            g = p.grad
+            m.lerp_(g, 1 - self.b1)
+            v.mul_(self.b2).addcmul_(g, g, value=1 - self.b2)
+            denom = (v.sqrt() / bc2_sqrt).add_(self.eps)
+            p.addcdiv_(m, denom * (bc1 / self.lr), value=-1.0)      # p -= (lr / bc1) * m / denom
+        # ReduceLROnPlateau, mode='min', threshold_mode='rel'
+        better = rank_loss < self.best * (1.0 - self.threshold)
+        self.best.copy_(torch.where(better, rank_loss, self.best))
+        self.num_bad.copy_(torch.where(better, torch.zeros_like(self.num_bad), self.num_bad + 1))
+        reduce = self.num_bad > self.patience
+        new_lr = self.lr * self.factor
+        apply = reduce.unsqueeze(1) & ((self.lr - new_lr) > 1e-8)
+        self.lr.copy_(torch.where(apply, new_lr, self.lr))
+        self.num_bad.copy_(torch.where(reduce, torch.zeros_like(self.num_bad), self.num_bad))
+
+
+class GraphedRefiner:
+    """Owns the static tensors, the captured graph and the device-side history of one refinement run."""
+
+    TERMS = ('ov_depth', 'depth', 'iou', 'mask')
+
+    def __init__(self, estimator, z_obj, target_obs, cameras, chunk=16):
+        self.est = estimator
+        self.model = estimator.model
+        dev = self.model.device
+        self.n = n = len(cameras)
+        self.chunk = chunk
+        self.z_obj = z_obj
+        self.target = target_obs
+        self.template = cameras                                   # intrinsics / sizes (constant)
+        self.lq = cameras.log_quaternion.detach().clone().requires_grad_(True)
+        self.tr = cameras.translation.detach().clone().requires_grad_(True)
+        self.vp = cameras.viewport.detach().clone().requires_grad_(True)
+        self.opt = _BatchedAdamPlateau([self.lq, self.tr, self.vp], n, estimator.learning_rate,
+                                       estimator.lr_reduce_patience, estimator.lr_reduce_threshold,
+                                       estimator.lr_reduce_factor)
+        self.weights = dict(estimator.loss_weights)
+        self.sched_w = {k: torch.tensor(float(self.weights.get(k, 0.0)), device=dev) for k in estimator.loss_schedules}
+        # device history (one chunk)
+        self.h_rank = torch.zeros(chunk, n, device=dev)
+        self.h_optim = torch.zeros(chunk, n, device=dev)
+        self.h_terms = torch.zeros(chunk, len(self.TERMS), n, device=dev)
+        self.h_lq = torch.zeros(chunk, n, 3, device=dev)
+        self.h_tr = torch.zeros(chunk, n, 3, device=dev)
+        self.slot = torch.zeros(1, dtype=torch.long, device=dev)
+        self.graph = None
+
+    # ---- one iteration, device only ----
+    def _camera(self):
+        t = self.template
+        return Camera(t.intrinsic, None, t.z_span, self.vp, width=t.width, height=t.height,
+                      log_quaternion=self.lq, translation=self.tr)
+
+    def _iteration(self):
+        est = self.est
+        for p in (self.lq, self.tr, self.vp):
+            p.grad = None
+        cam = self._camera()
+        z_depth, _, z_mask_logits, _ = est._render_observation(self.z_obj, cam)
+        losses = est.loss_func(self.target, z_depth, z_mask_logits, cam)
+        rank = sum(self.weights.get(k, 0.0) * v for k, v in losses.items())
+        optim = rank
+        if self.sched_w:
+            optim = sum((self.sched_w[k] if k in self.sched_w else self.weights.get(k, 0.0)) * v
+                        for k, v in losses.items())
+        optim.mean().backward()
+        with torch.no_grad():
+            # snapshot BEFORE the update: the reference ranks the cameras that produced this loss
+            self.h_rank.index_copy_(0, self.slot, rank.detach().unsqueeze(0))
+            self.h_optim.index_copy_(0, self.slot, optim.detach().unsqueeze(0))
+            self.h_terms.index_copy_(0, self.slot, torch.stack([losses[k].detach() for k in self.TERMS]).unsqueeze(0))
+            self.h_lq.index_copy_(0, self.slot, self.lq.detach().unsqueeze(0))
+            self.h_tr.index_copy_(0, self.slot, self.tr.detach().unsqueeze(0))
+            self.slot.add_(1).remainder_(self.chunk)
+        self.opt.step(rank.detach())
+
+    def set_schedule_weights(self, step):
+        for k, sched in self.est.loss_schedules.items():
+            self.sched_w[k].fill_(float(sched.get(step)))
+
+    def capture(self):
+        ops.KernelTrace.enabled = False
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        state = self._save_state()
+        with torch.cuda.stream(side):
+            for _ in range(2):                      # warm-up on a side stream (allocator, packed-weight caches)
+                self._iteration()
+        torch.cuda.current_stream().wait_stream(side)
+        self._load_state(state)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._iteration()
+        self._load_state(state)                     # capture does not execute, but keep state pristine
+
+    def _save_state(self):
+        o = self.opt
+        return [t.detach().clone() for t in (self.lq, self.tr, self.vp, *o.m, *o.v, o.step_count, o.lr, o.best,
+                                             o.num_bad, self.slot)]
+
+    def _load_state(self, state):
+        o = self.opt
+        with torch.no_grad():
+            for dst, src in zip((self.lq, self.tr, self.vp, *o.m, *o.v, o.step_count, o.lr, o.best, o.num_bad,
+                                 self.slot), state):
+                dst.copy_(src)
+
+    def run_chunk(self, first_step, count):
+        """Replay `count` (<= chunk) iterations; returns host copies of this chunk's history."""
+        for i in range(count):
+            if self.est.loss_schedules:
+                self.set_schedule_weights(first_step + i)
+            self.graph.replay()
+        out = {k: getattr(self, 'h_' + k)[:count].cpu() for k in ('rank', 'optim', 'terms', 'lq', 'tr')}
+        return out
+
+    def camera_at(self, lq, tr):
+        """Full-frame (uncropped) detached camera for one iteration's snapshot, on the host."""
+        t = self.template
+        return Camera(t.intrinsic.detach().cpu(), None, t.z_span, None, width=t.width, height=t.height,
+                      log_quaternion=lq.clone(), translation=tr.clone())
