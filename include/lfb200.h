@@ -141,6 +141,25 @@ int lf_gru_gates1(const float* u_pre, const float* r_pre, const float* h, float*
 int lf_gru_gates2(const float* h, const float* update, const float* o, float* h_new,
                   int64_t numel, void* stream);
 
+/* ---- fused pose-loss head (recon/models.py:455-484 interpret_logits; modules/geometry.py:261-285 uncrop,
+ *      :555-558 denormalize_depth; pose/estimation.py:70-118 default_pose_loss; pose/utils.py:81-117) ----
+ * depth_logits, mask_logits [N][P][P] (the two heads of the Photographer); viewport [N][4] (x0,y0,x1,y1);
+ * tz [N] camera translation z; target_depth / target_mask [height][width] (one target observation).
+ * terms [N][4] = ov_depth, depth, iou, mask.  sums [N][8] is scratch carried from fwd to bwd. */
+typedef struct {
+    int n, p;              /* hypotheses, crop side */
+    int width, height;     /* full frame */
+    float z_span, eps;     /* Camera.z_span; denormalize_depth eps (0.01) */
+} lf_loss_desc;
+int lf_pose_loss_fwd(const lf_loss_desc* desc, const float* depth_logits, const float* mask_logits,
+                     const float* viewport, const float* tz, const float* target_depth, const float* target_mask,
+                     float* sums, float* terms, void* stream);
+int lf_pose_loss_bwd(const lf_loss_desc* desc, const float* depth_logits, const float* mask_logits,
+                     const float* viewport, const float* tz, const float* target_depth, const float* target_mask,
+                     const float* sums, const float* grad_terms /* [N][4] */,
+                     float* grad_depth_logits, float* grad_mask_logits, float* grad_viewport /* [N][4] */,
+                     float* grad_tz /* [N] */, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

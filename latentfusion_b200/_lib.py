@@ -28,8 +28,7 @@ class ConvDesc(ctypes.Structure):
 class LossDesc(ctypes.Structure):
     """lf_loss_desc (include/lfb200.h)."""
     _fields_ = [('n', c_int), ('p', c_int), ('width', c_int), ('height', c_int),
-                ('z_span', c_float), ('eps', c_float), ('w_depth', c_float), ('w_ov_depth', c_float),
-                ('w_iou', c_float), ('w_mask', c_float)]
+                ('z_span', c_float), ('eps', c_float)]
 
 
 _SIGNATURES = {
@@ -54,6 +53,8 @@ _SIGNATURES = {
     'lf_fuse_pool_bwd': (c_int, [c_f32p, c_f32p, c_f32p, c_int, c_int, c_i64, c_int, c_int, c_vp]),
     'lf_gru_gates1': (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_vp]),
     'lf_gru_gates2': (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_vp]),
+    'lf_pose_loss_fwd': (c_int, [ctypes.POINTER(LossDesc)] + [c_f32p] * 8 + [c_vp]),
+    'lf_pose_loss_bwd': (c_int, [ctypes.POINTER(LossDesc)] + [c_f32p] * 12 + [c_vp]),
 }
 
 _lib = None

@@ -517,3 +517,50 @@ def gru_gates1(u_pre, r_pre, h):
 
 def gru_gates2(h, update, o):
     return _GruGates2.apply(h, update, o)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused pose-loss head
+# ------------------------------------------------------------------------------------------------
+class _PoseLoss(torch.autograd.Function):
+    """interpret_logits + denormalize_depth + uncrop x2 + default_pose_loss terms in two full-frame passes.
+    Returns terms [N,4] = (ov_depth, depth, iou, mask); differentiable w.r.t. the two logit maps, the
+    viewport and the translation's z."""
+
+    @staticmethod
+    def forward(ctx, depth_logits, mask_logits, viewport, tz, target_depth, target_mask, z_span, eps, width, height):
+        _need_cuda(depth_logits, mask_logits, viewport, tz, target_depth, target_mask)
+        n, p = depth_logits.shape[0], depth_logits.shape[-1]
+        dl = depth_logits.detach().float().contiguous().view(n, p, p)
+        ml = mask_logits.detach().float().contiguous().view(n, p, p)
+        vp = viewport.detach().float().contiguous()
+        tzc = tz.detach().float().contiguous()
+        td = target_depth.detach().float().contiguous().view(height, width)
+        tm = target_mask.detach().float().contiguous().view(height, width)
+        desc = L.LossDesc(n, p, width, height, float(z_span), float(eps))
+        sums = torch.empty(n, 8, device=dl.device)
+        terms = torch.empty(n, 4, device=dl.device)
+        _call('lf_pose_loss_fwd', L.lib().lf_pose_loss_fwd,
+              (ctypes.byref(desc), _p(dl), _p(ml), _p(vp), _p(tzc), _p(td), _p(tm), _p(sums), _p(terms), _stream()),
+              kernels=3)
+        ctx.save_for_backward(dl, ml, vp, tzc, td, tm, sums)
+        ctx.cfg = (n, p, width, height, float(z_span), float(eps), tuple(depth_logits.shape), tuple(mask_logits.shape))
+        return terms
+
+    @staticmethod
+    def backward(ctx, gterms):
+        dl, ml, vp, tzc, td, tm, sums = ctx.saved_tensors
+        n, p, width, height, z_span, eps, dshape, mshape = ctx.cfg
+        desc = L.LossDesc(n, p, width, height, z_span, eps)
+        g_dl, g_ml = torch.empty_like(dl), torch.empty_like(ml)
+        g_vp, g_tz = torch.empty_like(vp), torch.empty_like(tzc)
+        gt = gterms.float().contiguous()
+        _call('lf_pose_loss_bwd', L.lib().lf_pose_loss_bwd,
+              (ctypes.byref(desc), _p(dl), _p(ml), _p(vp), _p(tzc), _p(td), _p(tm), _p(sums), _p(gt),
+               _p(g_dl), _p(g_ml), _p(g_vp), _p(g_tz), _stream()))
+        return g_dl.view(dshape), g_ml.view(mshape), g_vp, g_tz, None, None, None, None, None, None
+
+
+def pose_loss_terms(depth_logits, mask_logits, viewport, tz, target_depth, target_mask, z_span, eps=0.01,
+                    width=640, height=480):
+    return _PoseLoss.apply(depth_logits, mask_logits, viewport, tz, target_depth, target_mask, z_span, eps, width, height)

@@ -241,12 +241,12 @@ class GradientPoseEstimator(PoseEstimator):
 
     def __init__(self, *, learning_rate, num_samples, num_iters, converge_threshold, converge_patience,
                  lr_reduce_patience=25, lr_reduce_threshold=1e-5, lr_reduce_factor=0.5, track_stats=False,
-                 loss_schedules=None, optimizer='adamw', cuda_graph=True, graph_chunk=16, **kwargs):
+                 loss_schedules=None, optimizer='adamw', cuda_graph=True, graph_chunk=16, fused_loss=True, **kwargs):
         super().__init__(**kwargs)
         # B200 path: capture one loop body as a CUDA graph (pose/refine_graph.py).  Falls back to the eager
         # loop for configurations the graphed step does not cover (non-Adam optimisers, latent loss, custom
         # loss functions, CPU tensors).
-        self.cuda_graph, self.graph_chunk = cuda_graph, graph_chunk
+        self.cuda_graph, self.graph_chunk, self.fused_loss = cuda_graph, graph_chunk, fused_loss
         self.learning_rate, self.num_samples, self.num_iters = learning_rate, num_samples, num_iters
         self.optimizer = optimizer
         self.lr_reduce_patience, self.lr_reduce_threshold = lr_reduce_patience, lr_reduce_threshold
@@ -287,8 +287,15 @@ class GradientPoseEstimator(PoseEstimator):
 
     def _optimize_camera_graphed(self, z_obj, target_obs, cameras, iters, ranking):
         from .refine_graph import GraphedRefiner
-        refiner = GraphedRefiner(self, z_obj, target_obs, cameras, chunk=min(self.graph_chunk, max(iters, 1)))
-        refiner.capture()
+        refiner = getattr(self, '_refiner', None)
+        probe = (len(cameras), tuple(z_obj.shape), tuple(target_obs.depth.shape), cameras.width, cameras.height,
+                 cameras.z_span)
+        if refiner is not None and refiner.signature() == probe:
+            refiner.reset(z_obj, target_obs, cameras)           # same shapes: reuse the captured graph
+        else:
+            refiner = GraphedRefiner(self, z_obj, target_obs, cameras, chunk=self.graph_chunk)
+            refiner.capture()
+            self._refiner = refiner
         stats, history, converge_count = {}, [], 0
         gt_cam = target_obs.camera
         gt_quat, gt_trans = gt_cam.quaternion.detach().cpu(), gt_cam.translation.detach().cpu()

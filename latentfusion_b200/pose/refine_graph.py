@@ -72,12 +72,14 @@ class GraphedRefiner:
         dev = self.model.device
         self.n = n = len(cameras)
         self.chunk = chunk
-        self.z_obj = z_obj
-        self.target = target_obs
-        self.template = cameras                                   # intrinsics / sizes (constant)
+        # static copies: the captured graph is bound to these addresses; reset() refills them for a new run
+        self.z_obj = z_obj.detach().clone()
+        self.target = target_obs.clone()
+        self.template = cameras.detach().clone()                  # intrinsics / sizes
         self.lq = cameras.log_quaternion.detach().clone().requires_grad_(True)
         self.tr = cameras.translation.detach().clone().requires_grad_(True)
         self.vp = cameras.viewport.detach().clone().requires_grad_(True)
+        self.launches_per_iteration = 0
         self.opt = _BatchedAdamPlateau([self.lq, self.tr, self.vp], n, estimator.learning_rate,
                                        estimator.lr_reduce_patience, estimator.lr_reduce_threshold,
                                        estimator.lr_reduce_factor)
@@ -103,8 +105,16 @@ class GraphedRefiner:
         for p in (self.lq, self.tr, self.vp):
             p.grad = None
         cam = self._camera()
-        z_depth, _, z_mask_logits, _ = est._render_observation(self.z_obj, cam)
-        losses = est.loss_func(self.target, z_depth, z_mask_logits, cam)
+        ph = self.model.photographer
+        if est.fused_loss and ph.predict_depth and ph.predict_mask and not ph.predict_color:
+            # raw head outputs -> fused loss head (csrc/pose_loss.cu): no full-frame intermediates
+            logits, _, _ = ph.decode(self.z_obj, cam, interpret_logits=False)
+            terms = ops.pose_loss_terms(logits[:, 0], logits[:, 1], cam.viewport, cam.translation[:, 2],
+                                        self.target.depth, self.target.mask, cam.z_span, 0.01, cam.width, cam.height)
+            losses = {k: terms[:, i] for i, k in enumerate(self.TERMS)}
+        else:
+            z_depth, _, z_mask_logits, _ = est._render_observation(self.z_obj, cam)
+            losses = est.loss_func(self.target, z_depth, z_mask_logits, cam)
         rank = sum(self.weights.get(k, 0.0) * v for k, v in losses.items())
         optim = rank
         if self.sched_w:
@@ -125,14 +135,34 @@ class GraphedRefiner:
         for k, sched in self.est.loss_schedules.items():
             self.sched_w[k].fill_(float(sched.get(step)))
 
+    def signature(self):
+        return (self.n, tuple(self.z_obj.shape), tuple(self.target.depth.shape), self.template.width,
+                self.template.height, self.template.z_span)
+
+    @torch.no_grad()
+    def reset(self, z_obj, target_obs, cameras):
+        """Re-arm the captured graph for another run with same-shaped inputs (no re-capture)."""
+        self.z_obj.copy_(z_obj)
+        self.target.color.copy_(target_obs.color); self.target.depth.copy_(target_obs.depth)
+        self.target.mask.copy_(target_obs.mask)
+        self.template.intrinsic.copy_(cameras.intrinsic)
+        self.lq.copy_(cameras.log_quaternion); self.tr.copy_(cameras.translation); self.vp.copy_(cameras.viewport)
+        o = self.opt
+        for t in (*o.m, *o.v, o.step_count, o.num_bad):
+            t.zero_()
+        o.lr.fill_(float(self.est.learning_rate)); o.best.fill_(float('inf'))
+        self.slot.zero_()
+
     def capture(self):
         ops.KernelTrace.enabled = False
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         state = self._save_state()
         with torch.cuda.stream(side):
-            for _ in range(2):                      # warm-up on a side stream (allocator, packed-weight caches)
+            for i in range(2):                      # warm-up on a side stream (allocator, packed-weight caches)
+                before = ops.KernelTrace.launches
                 self._iteration()
+                self.launches_per_iteration = ops.KernelTrace.launches - before
         torch.cuda.current_stream().wait_stream(side)
         self._load_state(state)
         self.graph = torch.cuda.CUDAGraph()
@@ -158,6 +188,7 @@ class GraphedRefiner:
             if self.est.loss_schedules:
                 self.set_schedule_weights(first_step + i)
             self.graph.replay()
+        ops.KernelTrace.launches += count * self.launches_per_iteration   # lfb200 kernels inside the replays
         out = {k: getattr(self, 'h_' + k)[:count].cpu() for k in ('rank', 'optim', 'terms', 'lq', 'tr')}
         return out
 

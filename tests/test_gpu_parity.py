@@ -207,3 +207,38 @@ def test_full_size_properties(dev):
     lhs.backward()
     rhs = (v.grad * a).sum()
     torch.testing.assert_close(lhs.detach(), rhs, atol=1e-1, rtol=1e-3)
+
+
+def test_fused_pose_loss_head_vs_reference_formulas(g, dev):
+    """csrc/pose_loss.cu against the torch composition of the reference ops (interpret_logits ->
+    denormalize_depth -> uncrop x2 -> default_pose_loss): terms and all four gradient paths."""
+    from latentfusion_b200 import ops
+    from latentfusion_b200.pose import estimation
+    from latentfusion_b200.observation import Observation
+    P = 2 * g.meta['S']
+    torch.manual_seed(0)
+    logits = (torch.randn(2, 2, P, P, device=dev) * 2.0)
+    gt = ph.product_camera(g.cam('ref_cam_full'), dev)[0:1]
+    target = Observation(torch.zeros(1, 3, 480, 640, device=dev), g['target.depth'].to(dev), g['target.mask'].to(dev), gt)
+    w = torch.tensor([0.3, 1.0, 0.2, 0.1], device=dev)
+
+    def run(fused):
+        cam = ph.product_camera(g.cam('hyp_cam'), dev, requires_grad=True)
+        lg = logits.clone().requires_grad_(True)
+        if fused:
+            terms = ops.pose_loss_terms(lg[:, 0], lg[:, 1], cam.viewport, cam.translation[:, 2], target.depth,
+                                        target.mask, cam.z_span, 0.01, cam.width, cam.height)
+        else:
+            depth, mask = torch.tanh(lg[:, 0:1]), torch.sigmoid(lg[:, 1:2])
+            depth = (depth + 1) * (mask > 0.5) - 1
+            losses = estimation.default_pose_loss(target, cam.denormalize_depth(depth), lg[:, 1:2], cam)
+            terms = torch.stack([losses[k] for k in ('ov_depth', 'depth', 'iou', 'mask')], dim=1)
+        (terms * w).sum(dim=1).mean().backward()
+        return terms.detach(), lg.grad, cam.viewport.grad, cam.translation.grad
+
+    t1, gl1, gv1, gt1 = run(True)
+    t0, gl0, gv0, gt0 = run(False)
+    torch.testing.assert_close(t1, t0, atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(gl1, gl0, atol=1e-6, rtol=2e-3)
+    torch.testing.assert_close(gv1, gv0, atol=1e-5, rtol=2e-3)
+    torch.testing.assert_close(gt1, gt0, atol=1e-5, rtol=2e-3)
