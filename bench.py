@@ -226,6 +226,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG', 'WARN')      # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group('nccl', device_id=dev)
     ops.set_default_precision(args.precision)
 
