@@ -108,6 +108,14 @@ int64_t lf_conv_tc_weight_bytes(int taps, int cin, int cout);
 int lf_conv_tc_pack_weights(const float* w_packed /* [taps][Cin][Cout] fp32 */, void* out,
                             int taps, int cin, int cout, void* stream);
 int lf_conv_tc_supported(const lf_conv_desc* desc);
+/* Backward-data of a Block conv with the PixelNorm/LeakyReLU backward (lf_actnorm_bwd) fused into the operand
+ * staging of the tcgen05 kernel: gx = conv_T(du) * scale with du = LeakyReLU'(y) * PixelNorm^T(gy) never written
+ * to HBM.  `desc` describes the backward conv (cin = forward Cout, cout = forward Cin, act = norm = 0);
+ * fwd_* are the forward layer's epilogue flags; y_fwd / rnorm_fwd its saved output and norm.  Returns
+ * LF_EUNSUPPORTED for shapes outside the kernel's coverage (caller then runs lf_actnorm_bwd + lf_conv_fwd). */
+int lf_conv_bwd_data_fused(const lf_conv_desc* desc, const float* gy, const float* y_fwd, const float* rnorm_fwd,
+                           int fwd_act, float fwd_slope, int fwd_norm, const float* w_tc_packed, float* gx,
+                           void* stream);
 
 /* du = d(loss)/d(pre-activation conv output incl. scale&bias) from gy, y (post-norm output), rnorm.
  * PixelNorm + LeakyReLU backward fused.  Elements are y[(o*gd + t)*inner + p][c]; one norm group =

@@ -39,6 +39,9 @@ enum PassMode { PASS_ONLY = 0, PASS_FIRST = 1, PASS_MID = 2, PASS_LAST = 3 };
 
 struct Params {
     const float* x; const uint16_t* wpk; const float* bias; float* y; float* rnorm;
+    // fused backward prologue (bwd-data of a Block conv): x = upstream grad g, pro_y = the layer's output y,
+    // pro_r = its saved PixelNorm denominators; the producers stage du = LeakyReLU'(y) * PixelNorm^T(g) on the fly
+    const float* pro_y; const float* pro_r; int pro_act, pro_norm, pro_lg; float pro_slope;
     int n, d, h, w;            // extent (d = 1 for 2-D)
     int cin, cout, cin_pad, cout_pad;
     int k, hz;                 // kernel size (1|3); hz = depth halo (k/2 for 3-D, 0 for 2-D)
@@ -316,6 +319,7 @@ conv_tc_kernel(const __grid_constant__ Params p) {
                     uint8_t* slab = smem + (size_t)slot * p.slab_bytes;
                     const float* plane = p.x + ((int64_t)n * p.d + e) * p.h * p.w * (int64_t)p.cin;
                     const int units = rows_in * p.P * q4;
+                    if (p.pro_y == nullptr) {
                     constexpr int kBatch = 8;           // loads in flight per thread
                     for (int u0 = tid; u0 < units; u0 += kBatch * kProducerWarps * 32) {
                         float4 v[kBatch];
@@ -340,6 +344,60 @@ conv_tc_kernel(const __grid_constant__ Params p) {
                             const uint32_t lo = pack_bf16x2(v[j].x, v[j].y, p.a_part);
                             const uint32_t hi = pack_bf16x2(v[j].z, v[j].w, p.a_part);
                             *reinterpret_cast<uint2*>(slab + udst[j]) = make_uint2(lo, hi);
+                        }
+                    }
+                    } else {
+                        // ---- fused PixelNorm/LeakyReLU backward: du = gate(y) * (g - y * mean_c(g*y)) / r
+                        // a position's channels sit on 2^pro_lg consecutive lanes (q4 is a power of two that
+                        // divides 32 and the producer thread count), so mean_c is an xor-shuffle reduction
+                        const float* yplane = p.pro_y + ((int64_t)n * p.d + e) * p.h * p.w * (int64_t)p.cin;
+                        const float* rplane = p.pro_r + ((int64_t)n * p.d + e) * p.h * p.w;
+                        const float inv_c = 1.f / (float)p.cin;
+                        const int units_pad = (units + 31) & ~31;
+                        constexpr int kB2 = 4;
+                        for (int u0 = tid; u0 < units_pad; u0 += kB2 * kProducerWarps * 32) {
+                            float4 g4[kB2], y4[kB2];
+                            float rr[kB2];
+                            int udst[kB2];
+#pragma unroll
+                            for (int j = 0; j < kB2; ++j) {
+                                const int u = u0 + j * kProducerWarps * 32;
+                                g4[j] = make_float4(0.f, 0.f, 0.f, 0.f); y4[j] = g4[j]; rr[j] = 1.f; udst[j] = -1;
+                                if (u < units) {
+                                    const int pos = fast_div(u, p.magic_q4), q = u - pos * q4;
+                                    const int r = fast_div(pos, p.magic_P), c = pos - r * p.P;
+                                    const int yy = y0 + r - halo, xx = c - halo;
+                                    udst[j] = (q >> 1) * (int)lbo_a + pos * 16 + (q & 1) * 8;
+                                    if (yy >= 0 && yy < p.h && xx >= 0 && xx < p.w) {
+                                        const int64_t gp = (int64_t)yy * p.w + xx;
+                                        g4[j] = ldg4(plane + gp * p.cin + q * 4);
+                                        y4[j] = ldg4(yplane + gp * p.cin + q * 4);
+                                        if (p.pro_norm) rr[j] = __ldg(rplane + gp);
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < kB2; ++j) {
+                                float4 g = g4[j];
+                                const float4 yv = y4[j];
+                                if (p.pro_norm) {
+                                    float dot = g.x * yv.x + g.y * yv.y + g.z * yv.z + g.w * yv.w;
+                                    for (int o = 1; o < (1 << p.pro_lg); o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                                    dot *= inv_c;
+                                    const float ir = 1.f / rr[j];
+                                    g.x = (g.x - yv.x * dot) * ir; g.y = (g.y - yv.y * dot) * ir;
+                                    g.z = (g.z - yv.z * dot) * ir; g.w = (g.w - yv.w * dot) * ir;
+                                }
+                                if (p.pro_act) {
+                                    g.x = yv.x > 0.f ? g.x : g.x * p.pro_slope; g.y = yv.y > 0.f ? g.y : g.y * p.pro_slope;
+                                    g.z = yv.z > 0.f ? g.z : g.z * p.pro_slope; g.w = yv.w > 0.f ? g.w : g.w * p.pro_slope;
+                                }
+                                if (udst[j] >= 0) {
+                                    const uint32_t lo = pack_bf16x2(g.x, g.y, p.a_part);
+                                    const uint32_t hi = pack_bf16x2(g.z, g.w, p.a_part);
+                                    *reinterpret_cast<uint2*>(slab + udst[j]) = make_uint2(lo, hi);
+                                }
+                            }
                         }
                     }
                     fence_proxy_async();                // generic-proxy stores -> visible to the tensor core
@@ -521,6 +579,11 @@ static bool make_plan(const lf_conv_desc* d, Plan& pl) {
         if ((uint64_t)slab * pl.ring + pl.w_bytes <= budget && ((uint32_t)pos * 16 >> 4) < 16384) { best_R = R; break; }
     }
     if (best_R == 0) return false;
+    if (hz == 0) {
+        // 2-D layers have no depth to chunk: shrink the strips until there are enough work items for the machine
+        const int sms = sm_count();
+        while (best_R > 2 && (int64_t)d->n * ((d->h + best_R - 1) / best_R) < 2 * sms) best_R = (best_R + 1) / 2;
+    }
     pl.R = best_R;
     pl.NT = (pl.R * pl.P + 127) / 128;
     int pos = (pl.R + 2 * halo) * pl.P + 2 * halo;
@@ -549,13 +612,30 @@ int conv_tc_supported(const lf_conv_desc* d) {
     return tc::make_plan(d, pl) ? 1 : 0;
 }
 
+struct TcPrologue { const float* y; const float* rnorm; int act, norm; float slope; };
+
+int conv_tc_launch_ex(const lf_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
+                      float* rnorm, const TcPrologue* pro, cudaStream_t st);
+
 int conv_tc_launch(const lf_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
                    float* rnorm, cudaStream_t st) {
+    return conv_tc_launch_ex(d, x, w, bias, y, rnorm, nullptr, st);
+}
+
+int conv_tc_launch_ex(const lf_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
+                      float* rnorm, const TcPrologue* pro, cudaStream_t st) {
     tc::Plan pl;
     LF_CHECK_ARG(tc::make_plan(d, pl), "conv_tc: unsupported shape");
     LF_CHECK_ARG(x && w && y, "conv_tc: null pointer");
     tc::Params p;
     p.x = x; p.bias = bias; p.y = y; p.rnorm = rnorm;
+    p.pro_y = pro ? pro->y : nullptr; p.pro_r = pro ? pro->rnorm : nullptr;
+    p.pro_act = pro ? pro->act : 0; p.pro_norm = pro ? pro->norm : 0; p.pro_slope = pro ? pro->slope : 1.f; p.pro_lg = 0;
+    if (pro) {
+        const int q4 = pl.cin_pad / 4;
+        LF_CHECK_ARG(d->cin == pl.cin_pad && (q4 & (q4 - 1)) == 0 && q4 <= 32, "conv_tc: fused backward prologue needs Cin in {16,32,64,128}");
+        while ((1 << p.pro_lg) < q4) ++p.pro_lg;
+    }
     p.n = d->n; p.d = d->d; p.h = d->h; p.w = d->w;
     p.cin = d->cin; p.cout = d->cout; p.cin_pad = pl.cin_pad; p.cout_pad = pl.cout_pad;
     p.k = d->k; p.hz = (d->ndim == 3) ? d->k / 2 : 0;
@@ -614,6 +694,23 @@ extern "C" int lf_conv_tc_pack_weights(const float* w_packed, void* out, int tap
     tc::pack_weights_kernel<<<(unsigned)((per_part + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         w_packed, reinterpret_cast<uint16_t*>(out), taps, cin, cout, cin_pad, cout_pad);
     LF_RETURN_LAUNCH();
+}
+
+extern "C" int lf_conv_bwd_data_fused(const lf_conv_desc* desc, const float* gy, const float* y_fwd,
+                                      const float* rnorm_fwd, int fwd_act, float fwd_slope, int fwd_norm,
+                                      const float* w_tc_packed, float* gx, void* stream) {
+    if (desc == nullptr || desc->precision == 0 || !conv_tc_supported(desc)) {
+        set_error("conv_bwd_data_fused: needs a tcgen05-supported shape and precision 1|2");
+        return LF_EUNSUPPORTED;
+    }
+    const int q4 = ((desc->cin + 15) / 16 * 16) / 4;
+    if (desc->cin % 16 != 0 || (q4 & (q4 - 1)) != 0 || q4 > 32) {
+        set_error("conv_bwd_data_fused: Cin must be 16, 32, 64 or 128");
+        return LF_EUNSUPPORTED;
+    }
+    LF_CHECK_ARG(gy && y_fwd && w_tc_packed && gx && (!fwd_norm || rnorm_fwd), "conv_bwd_data_fused: null pointer");
+    TcPrologue pro{y_fwd, rnorm_fwd, fwd_act, fwd_norm, fwd_slope};
+    return conv_tc_launch_ex(desc, gy, w_tc_packed, nullptr, gx, nullptr, &pro, (cudaStream_t)stream);
 }
 
 extern "C" int lf_debug_tc_timeline(long long* host_out /* [3][64][2] */) {

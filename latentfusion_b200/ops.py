@@ -196,6 +196,23 @@ def resample_c2o(vol, cam_block):
 KIND_CONV, KIND_COLLAPSE, KIND_EXPAND = 0, 1, 2
 
 
+_PACK_CACHE = {}
+
+
+def _pack_weight_cached(weight, kind, depth):
+    """_pack_weight memoised per live parameter object and version (weights are frozen in the pose loop, so the
+    flip/permute kernels run once, not once per convolution call)."""
+    key = (id(weight), weight._version, kind, depth)
+    hit = _PACK_CACHE.get(key)
+    if hit is not None and hit[0]() is weight:
+        return hit[1], hit[2]
+    wf, wb = _pack_weight(weight.detach(), kind, depth)
+    if len(_PACK_CACHE) > 512:
+        _PACK_CACHE.clear()
+    _PACK_CACHE[key] = (weakref.ref(weight), wf, wb)
+    return wf, wb
+
+
 def _pack_weight(weight, kind, depth):
     """[Cout,Cin,k..] (reference layout) -> packed [taps][Cin][Cout] and its bwd-data twin."""
     if kind == KIND_CONV:
@@ -304,7 +321,7 @@ class _EqConv(torch.autograd.Function):
             gcin, gcout, positions = cin, cout, n * h * w
         fan_in = int(math.prod(weight.shape[1:]))
         scale = math.sqrt(2.0 / fan_in)
-        wf, wb = _pack_weight(weight.detach(), kind, depth)
+        wf, wb = _pack_weight_cached(weight, kind, depth)
         if bias is None:
             bpk = None
         elif kind == KIND_EXPAND:
@@ -337,35 +354,50 @@ class _EqConv(torch.autograd.Function):
         (kind, depth, act, slope, norm, precision, nd, n, d, h, w, cin, cout, k, scale, wshape, has_bias) = ctx.cfg
         gy = to_cl(gy)
         lib = L.lib()
-        if act or norm:
-            du = torch.empty_like(gy)
-            if kind == KIND_EXPAND:
-                outer, gd, inner = n, d, h * w
-            elif kind == KIND_COLLAPSE:
-                outer, gd, inner = n * h * w, 1, 1
-            else:
-                outer, gd, inner = n * d * h * w, 1, 1
-            _call('lf_actnorm_bwd', lib.lf_actnorm_bwd, (_p(gy), _p(y), _p(rnorm), _p(du), outer, gd, inner, cout,
-                                                        int(act), slope, int(norm), _stream()),
-                  nbytes=4 * 3 * gy.numel())
-        else:
-            du = gy
+        need_w = ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2])
         gx = gw = gb = None
-        if ctx.needs_input_grad[0]:
+        du = None
+        bkind = {KIND_CONV: KIND_CONV, KIND_COLLAPSE: KIND_EXPAND, KIND_EXPAND: KIND_COLLAPSE}[kind]
+        bnd = {KIND_CONV: nd, KIND_COLLAPSE: 2, KIND_EXPAND: 3}[kind]
+        bdesc = _desc(bkind, bnd, n, d, h, w, cout, cin, k, scale, 0, 0.0, 0, precision)
+        bflops = 2 * (n * h * w * (d if kind == KIND_CONV else 1)) * wb.shape[0] * cin * cout
+        fused_done = False
+        if (ctx.needs_input_grad[0] and (act or norm) and not need_w and kind == KIND_CONV and _tc_ok(bdesc)
+                and cout in (16, 32, 64, 128)):
+            # pose-loop case: PixelNorm/LeakyReLU backward fused into the tcgen05 kernel's operand staging
             gx = torch.empty_like(x)
-            # bwd-data = the same implicit GEMM with flipped/transposed weights, no epilogue
-            bkind = {KIND_CONV: KIND_CONV, KIND_COLLAPSE: KIND_EXPAND, KIND_EXPAND: KIND_COLLAPSE}[kind]
-            bnd = {KIND_CONV: nd, KIND_COLLAPSE: 2, KIND_EXPAND: 3}[kind]
-            bdesc = _desc(bkind, bnd, n, d, h, w, cout, cin, k, scale, 0, 0.0, 0, precision)
-            if _tc_ok(bdesc):
-                wb_arg = _tc_pack(wb, ctx.wkey + ('b',))
+            wb_arg = _tc_pack(wb, ctx.wkey + ('b',))
+            _call(_conv_name(kind, nd, k, 'bwd_data_fused'), lib.lf_conv_bwd_data_fused,
+                  (ctypes.byref(bdesc), _p(gy), _p(y), _p(rnorm), int(act), slope, int(norm), _p(wb_arg), _p(gx),
+                   _stream()), kernels=3 if precision == 1 else 1,
+                  nbytes=4 * (2 * gy.numel() + gx.numel()), flops=bflops)
+            fused_done = True
+        if not fused_done:
+            if act or norm:
+                du = torch.empty_like(gy)
+                if kind == KIND_EXPAND:
+                    outer, gd, inner = n, d, h * w
+                elif kind == KIND_COLLAPSE:
+                    outer, gd, inner = n * h * w, 1, 1
+                else:
+                    outer, gd, inner = n * d * h * w, 1, 1
+                _call('lf_actnorm_bwd', lib.lf_actnorm_bwd, (_p(gy), _p(y), _p(rnorm), _p(du), outer, gd, inner, cout,
+                                                            int(act), slope, int(norm), _stream()),
+                      nbytes=4 * 3 * gy.numel())
             else:
-                bdesc.precision = 0
-                wb_arg = wb
-            _call(_conv_name(kind, nd, k, 'bwd_data'), lib.lf_conv_fwd,
-                  (ctypes.byref(bdesc), _p(du), _p(wb_arg), None, _p(gx), None, _stream()),
-                  nbytes=4 * (du.numel() + gx.numel()),
-                  flops=2 * (n * h * w * (d if kind == KIND_CONV else 1)) * wb.shape[0] * cin * cout)
+                du = gy
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty_like(x)
+                # bwd-data = the same implicit GEMM with flipped/transposed weights, no epilogue
+                if _tc_ok(bdesc):
+                    wb_arg = _tc_pack(wb, ctx.wkey + ('b',))
+                else:
+                    bdesc.precision = 0
+                    wb_arg = wb
+                _call(_conv_name(kind, nd, k, 'bwd_data'), lib.lf_conv_fwd,
+                      (ctypes.byref(bdesc), _p(du), _p(wb_arg), None, _p(gx), None, _stream()),
+                      kernels=3 if bdesc.precision == 1 else 1,
+                      nbytes=4 * (du.numel() + gx.numel()), flops=bflops)
         if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
             taps = wb.shape[0]
             gwp = torch.zeros(taps, cin, cout, device=x.device, dtype=torch.float32)
