@@ -82,6 +82,17 @@ __device__ __forceinline__ void gen_grid(const float* __restrict__ cm, int S, in
     }
 }
 
+// packed 2 x fp32 FMA (Blackwell FFMA2): d.xy = a * b.xy + c.xy with a scalar broadcast
+__device__ __forceinline__ void ffma2_bcast(float a, float bx, float by, float& cx, float& cy) {
+    unsigned long long ra, rb, rc, rd;
+    ra = ((unsigned long long)__float_as_uint(a) << 32) | __float_as_uint(a);
+    rb = ((unsigned long long)__float_as_uint(by) << 32) | __float_as_uint(bx);
+    rc = ((unsigned long long)__float_as_uint(cy) << 32) | __float_as_uint(cx);
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    cx = __uint_as_float((unsigned)rd);
+    cy = __uint_as_float((unsigned)(rd >> 32));
+}
+
 template <int VEC> struct Vec;
 template <> struct Vec<4> {
     typedef float4 T;
@@ -89,7 +100,8 @@ template <> struct Vec<4> {
     static __device__ __forceinline__ void store(float* p, T v) { __stcs(reinterpret_cast<float4*>(p), v); }
     static __device__ __forceinline__ T zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
     static __device__ __forceinline__ void fma(T& acc, float w, T v) {
-        acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+        ffma2_bcast(w, v.x, v.y, acc.x, acc.y);
+        ffma2_bcast(w, v.z, v.w, acc.z, acc.w);
     }
     static __device__ __forceinline__ float dot(T a, T b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
     static __device__ __forceinline__ T sub(T a, T b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
@@ -295,11 +307,11 @@ resample_bwd_vol_kernel(const float* __restrict__ gout, const float* __restrict_
 // camera (deterministic, no atomics).
 // ------------------------------------------------------------------------------------------
 constexpr int kCamGradTerms = 17;          // M[12], vp x0,y0,w,h, znear
-constexpr int CBX = 16, CBY = 16, CBZ = 8;  // bwd_cam brick: 2048 voxels per block
+constexpr int CBX = 16, CBY = 8, CBZ = 8;   // bwd_cam brick: 1024 voxels per block
 
 
 template <int VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 resample_o2c_bwd_cam_kernel(const float* __restrict__ gout, const float* __restrict__ vol,
                             const float* __restrict__ cam, float* __restrict__ ws,
                             int views_per_obj, int N, int C, int S, int lpv_log2, int blocks_per_cam) {
@@ -327,12 +339,12 @@ resample_o2c_bwd_cam_kernel(const float* __restrict__ gout, const float* __restr
     const int bi = bb_ % bg.nbx; bb_ /= bg.nbx;
     const int bj = bb_ % bg.nby; const int bk = bb_ / bg.nby;
 
-    // the 16x16x8 brick is walked as 8 sub-bricks of 8x8x4; a warp owns an 8x4 slab of each
-    for (int sb = 0; sb < 8; ++sb) {
+    // the 16x8x8 brick is walked as 4 sub-bricks of 8x8x4; a warp owns an 8x4 slab of each
+    for (int sb = 0; sb < 4; ++sb) {
         const int lv = warp * 32 + lane;
         const int vi = bi * CBX + (sb & 1) * 8 + (lv % 8);
-        const int vj = bj * CBY + ((sb >> 1) & 1) * 8 + (lv / 8) % 8;
-        const int vk = bk * CBZ + (sb >> 2) * 4 + lv / 64;
+        const int vj = bj * CBY + (lv / 8) % 8;
+        const int vk = bk * CBZ + (sb >> 1) * 4 + lv / 64;
         const bool inside = vi < S && vj < S && vk < S;
         const int i = min(vi, S - 1), j = min(vj, S - 1), k = min(vk, S - 1);
         // --- phase 1: forward recompute of this lane's grid point (same op order as gen_grid<0>),
@@ -427,18 +439,18 @@ resample_o2c_bwd_cam_kernel(const float* __restrict__ gout, const float* __restr
     }
 }
 
+// stage 2: one warp per (camera, term); lanes stride over the block partials, fixed-order fp64 tree
 __global__ void resample_o2c_bwd_cam_finish(const float* __restrict__ ws, float* __restrict__ gcam,
                                             int blocks_per_cam) {
     const int n = blockIdx.x;
-    const int t = threadIdx.x;
+    const int t = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (t >= LF_CAMGRAD_STRIDE) return;
-    float r = 0.f;
-    if (t < kCamGradTerms) {
-        double a = 0.0;
-        for (int b = 0; b < blocks_per_cam; ++b) a += (double)ws[((int64_t)n * blocks_per_cam + b) * kCamGradTerms + t];
-        r = (float)a;
-    }
-    gcam[(int64_t)n * LF_CAMGRAD_STRIDE + t] = r;
+    double a = 0.0;
+    if (t < kCamGradTerms)
+        for (int b = lane; b < blocks_per_cam; b += 32) a += (double)ws[((int64_t)n * blocks_per_cam + b) * kCamGradTerms + t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) gcam[(int64_t)n * LF_CAMGRAD_STRIDE + t] = (float)a;
 }
 
 static int lpv_log2_for(int C, int vec) {
@@ -526,7 +538,7 @@ extern "C" int lf_resample_o2c_bwd_cam(const float* gout, const float* vol, cons
         const int l = lpv_log2_for(C, 1);
         resample_o2c_bwd_cam_kernel<1><<<N * bpc, 256, 0, st>>>(gout, vol, cam, ws, N / B, N, C, S, l, bpc);
     }
-    resample_o2c_bwd_cam_finish<<<N, 32, 0, st>>>(ws, gcam, bpc);
+    resample_o2c_bwd_cam_finish<<<N, 32 * LF_CAMGRAD_STRIDE, 0, st>>>(ws, gcam, bpc);
     LF_RETURN_LAUNCH();
 }
 

@@ -362,8 +362,10 @@ class _EqConv(torch.autograd.Function):
         bdesc = _desc(bkind, bnd, n, d, h, w, cout, cin, k, scale, 0, 0.0, 0, precision)
         bflops = 2 * (n * h * w * (d if kind == KIND_CONV else 1)) * wb.shape[0] * cin * cout
         fused_done = False
-        if (ctx.needs_input_grad[0] and (act or norm) and not need_w and kind == KIND_CONV and _tc_ok(bdesc)
-                and cout in (16, 32, 64, 128)):
+        # (single-pass bf16 only: in the 3-pass bf16x3 mode recomputing the prologue per pass costs more than
+        #  materialising du once)
+        if (ctx.needs_input_grad[0] and (act or norm) and not need_w and kind == KIND_CONV and precision == PRECISION_BF16
+                and _tc_ok(bdesc) and cout in (16, 32, 64, 128)):
             # pose-loop case: PixelNorm/LeakyReLU backward fused into the tcgen05 kernel's operand staging
             gx = torch.empty_like(x)
             wb_arg = _tc_pack(wb, ctx.wkey + ('b',))

@@ -242,3 +242,36 @@ def test_fused_pose_loss_head_vs_reference_formulas(g, dev):
     torch.testing.assert_close(gl1, gl0, atol=1e-6, rtol=2e-3)
     torch.testing.assert_close(gv1, gv0, atol=1e-5, rtol=2e-3)
     torch.testing.assert_close(gt1, gt0, atol=1e-5, rtol=2e-3)
+
+
+@pytest.mark.parametrize('precision', [1])
+def test_tensor_core_bf16x3_path_meets_fp32_tolerance(g, dev, precision):
+    """The tcgen05 bf16x3 convolution path (bench.py's default) against the golden vectors of the unmodified
+    reference at the SAME fp32 tolerances as the exact kernels: render logits, losses, camera gradients, and the
+    three-iteration estimator trajectory."""
+    from latentfusion_b200 import ops
+    old = ops.get_default_precision()
+    ops.set_default_precision(precision)
+    try:
+        ph.smoke_check()
+        test_gradient_estimator_three_iterations_vs_golden(g, dev)
+    finally:
+        ops.set_default_precision(old)
+
+
+def test_bf16_path_stated_tolerance(g, dev):
+    """precision 2 (plain bf16 operands, fp32 accumulate) gets its own, looser stated bound: 5e-2 abs on the
+    O(1) logits of the golden configuration."""
+    from latentfusion_b200 import ops
+    from latentfusion_b200.recon.inference import LatentFusionModel
+    old = ops.get_default_precision()
+    ops.set_default_precision(2)
+    try:
+        sculptor, fuser, photographer = ph.build_product_models(g, dev)
+        model = LatentFusionModel(sculptor, fuser, photographer, g.meta['camera_dist'], dev)
+        cam = ph.product_camera(g.cam('hyp_cam'), dev)
+        y, _ = model.render_latent_object(g['z_obj_gru'].to(dev), cam)
+        torch.testing.assert_close(y['depth_logits'].cpu(), g['render.depth_logits'], atol=5e-2, rtol=5e-2)
+        torch.testing.assert_close(y['mask_logits'].cpu(), g['render.mask_logits'], atol=5e-2, rtol=5e-2)
+    finally:
+        ops.set_default_precision(old)
