@@ -149,6 +149,22 @@ int lf_gru_gates1(const float* u_pre, const float* r_pre, const float* h, float*
 int lf_gru_gates2(const float* h, const float* update, const float* o, float* h_new,
                   int64_t numel, void* stream);
 
+/* ---- camera algebra (modules/geometry.py:106-108,147-163,207-213,249-255; three/quaternion.py:287-311,39-93) ----
+ * The ten learnable floats of each hypothesis -> the object->camera constant block, and its analytic VJP
+ * (grad_block: only entries [0..15] and [20] are read). */
+int lf_camera_o2c_fwd(const float* log_quaternion /*[n][3]*/, const float* translation /*[n][3]*/,
+                      const float* viewport /*[n][4]*/, const float* intrinsic /*[n][12]*/,
+                      float* block /*[n][LF_CAM_STRIDE]*/, int n, float z_span, float cube_size, void* stream);
+int lf_camera_o2c_bwd(const float* log_quaternion, const float* translation, const float* grad_block,
+                      float* grad_log_quaternion, float* grad_translation, float* grad_viewport, int n, void* stream);
+/* Batched per-hypothesis optimiser (pose/estimation.py:582-594,664-666): torch.optim.Adam single-tensor maths with
+ * a per-row learning rate over param [n][width]; ReduceLROnPlateau(mode min, rel threshold, cooldown 0) per row. */
+int lf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int n, int width,
+                 const float* step_count /*[1], already incremented*/, const float* lr /*[n]*/,
+                 float beta1, float beta2, float eps, void* stream);
+int lf_plateau_step(const float* rank_loss /*[n]*/, float* lr, float* best, float* num_bad, int n,
+                    float threshold, float patience, float factor, void* stream);
+
 /* ---- fused pose-loss head (recon/models.py:455-484 interpret_logits; modules/geometry.py:261-285 uncrop,
  *      :555-558 denormalize_depth; pose/estimation.py:70-118 default_pose_loss; pose/utils.py:81-117) ----
  * depth_logits, mask_logits [N][P][P] (the two heads of the Photographer); viewport [N][4] (x0,y0,x1,y1);

@@ -54,6 +54,10 @@ _SIGNATURES = {
     'lf_fuse_pool_bwd': (c_int, [c_f32p, c_f32p, c_f32p, c_int, c_int, c_i64, c_int, c_int, c_vp]),
     'lf_gru_gates1': (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_vp]),
     'lf_gru_gates2': (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_vp]),
+    'lf_camera_o2c_fwd': (c_int, [c_f32p] * 5 + [c_int, c_float, c_float, c_vp]),
+    'lf_camera_o2c_bwd': (c_int, [c_f32p] * 6 + [c_int, c_vp]),
+    'lf_adam_step': (c_int, [c_f32p] * 4 + [c_int, c_int, c_f32p, c_f32p, c_float, c_float, c_float, c_vp]),
+    'lf_plateau_step': (c_int, [c_f32p] * 4 + [c_int, c_float, c_float, c_float, c_vp]),
     'lf_pose_loss_fwd': (c_int, [ctypes.POINTER(LossDesc)] + [c_f32p] * 8 + [c_vp]),
     'lf_pose_loss_bwd': (c_int, [ctypes.POINTER(LossDesc)] + [c_f32p] * 12 + [c_vp]),
 }

@@ -236,6 +236,10 @@ class Camera(nn.Module):
 
     # ---- constant blocks consumed by csrc/resample.cu (layout: include/lfb200.h)
     def o2c_block(self, cube_size):
+        if self.intrinsic.is_cuda:
+            # one kernel (+ one for the analytic VJP) instead of ~60 tiny launches and their autograd
+            return ops.camera_o2c_block(self.log_quaternion, self.translation, self.viewport, self.intrinsic,
+                                        self.z_span, cube_size)
         n, dev = self.length, self.device
         m = self.cam_to_obj[:, :3, :].reshape(n, 12)
         vp = torch.stack((self.viewport[:, 0], self.viewport[:, 1], self.viewport_width,

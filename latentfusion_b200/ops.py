@@ -598,3 +598,53 @@ class _PoseLoss(torch.autograd.Function):
 def pose_loss_terms(depth_logits, mask_logits, viewport, tz, target_depth, target_mask, z_span, eps=0.01,
                     width=640, height=480):
     return _PoseLoss.apply(depth_logits, mask_logits, viewport, tz, target_depth, target_mask, z_span, eps, width, height)
+
+
+# ------------------------------------------------------------------------------------------------
+# camera algebra + batched optimiser
+# ------------------------------------------------------------------------------------------------
+class _CameraO2CBlock(torch.autograd.Function):
+    """(log_quaternion, translation, viewport) -> [N, LF_CAM_STRIDE] object->camera block, analytic VJP."""
+
+    @staticmethod
+    def forward(ctx, lq, tr, vp, intrinsic, z_span, cube_size):
+        _need_cuda(lq, tr, vp, intrinsic)
+        n = lq.shape[0]
+        lqc, trc, vpc = (t.detach().float().contiguous() for t in (lq, tr, vp))
+        kc = intrinsic.detach().float().contiguous()
+        block = torch.empty(n, L.CAM_STRIDE, device=lq.device, dtype=torch.float32)
+        _call('lf_camera_o2c_fwd', L.lib().lf_camera_o2c_fwd,
+              (_p(lqc), _p(trc), _p(vpc), _p(kc), _p(block), n, float(z_span), float(cube_size), _stream()))
+        ctx.save_for_backward(lqc, trc)
+        return block
+
+    @staticmethod
+    def backward(ctx, gblock):
+        lqc, trc = ctx.saved_tensors
+        n = lqc.shape[0]
+        gb = gblock.float().contiguous()
+        g_lq, g_tr = torch.empty_like(lqc), torch.empty_like(trc)
+        g_vp = torch.empty(n, 4, device=lqc.device, dtype=torch.float32)
+        _call('lf_camera_o2c_bwd', L.lib().lf_camera_o2c_bwd,
+              (_p(lqc), _p(trc), _p(gb), _p(g_lq), _p(g_tr), _p(g_vp), n, _stream()))
+        return g_lq, g_tr, g_vp, None, None, None
+
+
+def camera_o2c_block(log_quaternion, translation, viewport, intrinsic, z_span, cube_size):
+    return _CameraO2CBlock.apply(log_quaternion, translation, viewport, intrinsic, z_span, cube_size)
+
+
+def adam_step_(param, grad, exp_avg, exp_avg_sq, step_count, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    """In-place torch.optim.Adam update of param [N,W] with a per-row learning rate lr [N]."""
+    _need_cuda(param, grad, exp_avg, exp_avg_sq, step_count, lr)
+    n, width = param.shape
+    _call('lf_adam_step', L.lib().lf_adam_step,
+          (_p(param), _p(grad.contiguous()), _p(exp_avg), _p(exp_avg_sq), n, width, _p(step_count), _p(lr),
+           beta1, beta2, eps, _stream()))
+
+
+def plateau_step_(rank_loss, lr, best, num_bad, threshold, patience, factor):
+    _need_cuda(rank_loss, lr, best, num_bad)
+    _call('lf_plateau_step', L.lib().lf_plateau_step,
+          (_p(rank_loss.contiguous()), _p(lr), _p(best), _p(num_bad), rank_loss.shape[0], float(threshold),
+           float(patience), float(factor), _stream()))

@@ -33,7 +33,7 @@ class _BatchedAdamPlateau:
         self.b1, self.b2, self.eps = betas[0], betas[1], eps
         self.m = [torch.zeros_like(p) for p in params]
         self.v = [torch.zeros_like(p) for p in params]
-        self.step_count = torch.zeros((), device=dev)
+        self.step_count = torch.zeros(1, device=dev)
         self.lr = torch.full((n, 1), float(lr), device=dev)
         self.best = torch.full((n,), float('inf'), device=dev)
         self.num_bad = torch.zeros(n, device=dev)
@@ -41,6 +41,12 @@ class _BatchedAdamPlateau:
 
     @torch.no_grad()
     def step(self, rank_loss):
+        if self.params[0].is_cuda:
+            self.step_count += 1
+            for p, m, v in zip(self.params, self.m, self.v):
+                ops.adam_step_(p, p.grad, m, v, self.step_count, self.lr, self.b1, self.b2, self.eps)
+            ops.plateau_step_(rank_loss, self.lr, self.best, self.num_bad, self.threshold, self.patience, self.factor)
+            return
         self.step_count += 1
         bc1 = 1 - self.b1 ** self.step_count
         bc2_sqrt = (1 - self.b2 ** self.step_count).sqrt()

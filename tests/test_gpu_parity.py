@@ -275,3 +275,20 @@ def test_bf16_path_stated_tolerance(g, dev):
         torch.testing.assert_close(y['mask_logits'].cpu(), g['render.mask_logits'], atol=5e-2, rtol=5e-2)
     finally:
         ops.set_default_precision(old)
+
+
+def test_camera_block_kernel_vs_torch_chain(g, dev):
+    """csrc/camera.cu (forward + analytic VJP) against the differentiable torch camera algebra on CPU."""
+    d = g.cam('hyp_cam')
+    cpu = ph.product_camera(d, 'cpu', requires_grad=True)
+    gpu = ph.product_camera(d, dev, requires_grad=True)
+    b_cpu, b_gpu = cpu.o2c_block(1.0), gpu.o2c_block(1.0)
+    torch.testing.assert_close(b_gpu.cpu(), b_cpu.detach(), atol=1e-5, rtol=1e-5)
+    torch.manual_seed(0)
+    w = torch.zeros_like(b_cpu)
+    w[:, :16] = torch.randn(2, 16)
+    w[:, 20] = torch.randn(2)
+    (b_cpu * w).sum().backward()
+    (b_gpu * w.to(dev)).sum().backward()
+    for k in ('log_quaternion', 'translation', 'viewport'):
+        torch.testing.assert_close(getattr(gpu, k).grad.cpu(), getattr(cpu, k).grad, atol=1e-4, rtol=1e-4)
