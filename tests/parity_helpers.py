@@ -150,3 +150,34 @@ def smoke_check():
                                        g['z_obj_gru'][0], ocam)
     torch.testing.assert_close(y['depth_logits'].detach().cpu()[0], logits[:, 0:1], **OUT_TOL)
     torch.cuda.synchronize()
+
+
+class oracle_dtype:
+    """Run the PyTorch oracle in another floating type (fp64 = ground truth for conditioning checks)."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        import torch.nn.functional as F
+        from oracle import lf_oracle as O
+        self._O, self._old_resample, self._old_default = O, O.resample, torch.get_default_dtype()
+        dt = self.dtype
+        O.resample = lambda vol, grid: F.grid_sample(vol.to(dt), grid.to(dt), padding_mode='border', align_corners=False)
+        torch.set_default_dtype(dt)
+        return self
+
+    def __exit__(self, *exc):
+        self._O.resample = self._old_resample
+        torch.set_default_dtype(self._old_default)
+
+
+def assert_grad_close_to_fp64(ours, g32, g64, what=''):
+    """Camera gradients are cancelling sums (lever arm ~ camera distance): the reference's own fp32 arithmetic
+    deviates from fp64 by err32.  Ours must be as good as that up to a factor, or within 2e-3 of the gradient's
+    scale."""
+    scale = g64.abs().max()
+    err32 = (g32.double() - g64).abs().max()
+    err = (ours.double() - g64).abs().max()
+    bound = max(3.0 * float(err32), 2e-3 * float(scale))
+    assert float(err) <= bound, f'{what}: |ours - fp64| = {float(err):.4g} > {bound:.4g} (fp32 reference error {float(err32):.4g}, scale {float(scale):.4g})'
