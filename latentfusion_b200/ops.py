@@ -16,6 +16,7 @@ from . import _lib as L
 PRECISION_FP32 = 0      # exact fp32 FFMA path
 PRECISION_BF16X3 = 1    # tcgen05, bf16 hi/lo split (3 MMAs), ~2^-16 relative
 PRECISION_BF16 = 2      # tcgen05, plain bf16 operands, fp32 accumulate
+PRECISION_MIXED = 3     # forward bf16x3 (fp32-grade outputs), backward-data single-pass bf16
 
 import os as _os
 
@@ -330,7 +331,8 @@ class _EqConv(torch.autograd.Function):
             bpk = bias.detach().float().contiguous()
         y = empty_cl(out_shape, dev)
         rnorm = torch.empty(positions, device=dev, dtype=torch.float32) if norm else None
-        desc = _desc(kind, nd, n, d, h, w, gcin, gcout, k, scale, act, slope, norm, precision)
+        desc = _desc(kind, nd, n, d, h, w, gcin, gcout, k, scale, act, slope, norm,
+                     PRECISION_BF16X3 if precision == PRECISION_MIXED else precision)
         taps = wf.shape[0]
         wkey = (weight, id(weight), weight._version, kind)
         if _tc_ok(desc):
@@ -354,6 +356,8 @@ class _EqConv(torch.autograd.Function):
         (kind, depth, act, slope, norm, precision, nd, n, d, h, w, cin, cout, k, scale, wshape, has_bias) = ctx.cfg
         gy = to_cl(gy)
         lib = L.lib()
+        if precision == PRECISION_MIXED:
+            precision = PRECISION_BF16
         need_w = ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2])
         gx = gw = gb = None
         du = None

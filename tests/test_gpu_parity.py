@@ -306,3 +306,31 @@ def test_camera_block_kernel_vs_torch_chain(g, dev):
     (b_gpu * w.to(dev)).sum().backward()
     for k in ('log_quaternion', 'translation', 'viewport'):
         torch.testing.assert_close(getattr(gpu, k).grad.cpu(), getattr(cpu, k).grad, atol=1e-4, rtol=1e-4)
+
+
+def test_mixed_precision_path_stated_tolerance(g, dev):
+    """precision 3: bf16x3 forward + single-pass bf16 backward-data.  Forward outputs meet the fp32 tolerance;
+    the camera gradients get the looser stated bound of 5e-2 (measured ~3e-2), which is why bench.py's
+    fp32-parity default is precision 1, not 3."""
+    import json
+    from latentfusion_b200 import ops
+    from latentfusion_b200.pose import estimation
+    from latentfusion_b200.observation import Observation
+    from latentfusion_b200.recon.inference import LatentFusionModel
+    old = ops.get_default_precision()
+    ops.set_default_precision(3)
+    try:
+        sculptor, fuser, photographer = ph.build_product_models(g, dev)
+        model = LatentFusionModel(sculptor, fuser, photographer, g.meta['camera_dist'], dev)
+        cam = ph.product_camera(g.cam('hyp_cam'), dev, requires_grad=True)
+        y, _ = model.render_latent_object(g['z_obj_gru'].to(dev), cam)
+        torch.testing.assert_close(y['depth_logits'].cpu(), g['render.depth_logits'], **OUT_TOL)
+        gt = ph.product_camera(g.cam('ref_cam_full'), dev)[0:1]
+        target = Observation(torch.zeros(1, 3, 480, 640, device=dev), g['target.depth'].to(dev), g['target.mask'].to(dev), gt)
+        losses = estimation.default_pose_loss(target, cam.denormalize_depth(y['depth'].squeeze(0)), y['mask_logits'].squeeze(0), cam)
+        w = json.loads(g.text('loss.weights'))
+        sum(w[k] * v for k, v in losses.items()).mean().backward()
+        for k in ('log_quaternion', 'translation', 'viewport'):
+            torch.testing.assert_close(getattr(cam, k).grad.cpu(), g[f'grad.{k}'], atol=5e-2, rtol=5e-2)
+    finally:
+        ops.set_default_precision(old)
