@@ -31,7 +31,8 @@ namespace tc {
 
 constexpr int kProducerWarps = 7;
 constexpr int kMmaWarps = 5;                               // issuer warp m owns M-tiles m, m+4, ...
-constexpr int kThreads = 32 * (kProducerWarps + kMmaWarps + 4);   // producers | MMA issuers | epilogue
+constexpr int kEpiWarps = 4;                               // one warp per TMEM lane quarter (8 measured slower)
+constexpr int kThreads = 32 * (kProducerWarps + kMmaWarps + kEpiWarps);   // producers | MMA issuers | epilogue
 constexpr int kMaxRing = 4;
 constexpr int kMaxTiles = 5;
 
@@ -283,7 +284,7 @@ conv_tc_kernel(const __grid_constant__ Params p) {
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.ring; ++i) { mbar_init(bar_full + 8 * i, kProducerWarps * 32); mbar_init(bar_empty + 8 * i, min(p.NT, kMmaWarps)); }
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, min(p.NT, kMmaWarps)); mbar_init(bar_acce + 8 * i, 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, min(p.NT, kMmaWarps)); mbar_init(bar_acce + 8 * i, 32 * kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kProducerWarps) {
@@ -484,6 +485,7 @@ conv_tc_kernel(const __grid_constant__ Params p) {
     } else {
         // =========================== EPILOGUE (4 warps = 128 TMEM lanes) ===========================
         const int wq = warp & 3;                       // TMEM lane quarter this warp may access
+        const int ehalf = (warp - kProducerWarps - kMmaWarps) >> 2;   // which half of the tiles this warp drains
         uint32_t step = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
             int it = item;
@@ -495,8 +497,8 @@ conv_tc_kernel(const __grid_constant__ Params p) {
                 const uint32_t buf = step & 1;
                 mbar_wait(bar_accf + 8 * buf, (step >> 1) & 1);
                 tc_fence_after();
-                if (wq == 0 && lane == 0) dbg_stamp(p, 2, step, 0);
-                for (int t = 0; t < ((p.debug & 4) ? 0 : p.NT); ++t) {
+                if (wq == 0 && ehalf == 0 && lane == 0) dbg_stamp(p, 2, step, 0);
+                for (int t = ehalf; t < ((p.debug & 4) ? 0 : p.NT); t += kEpiWarps / 4) {
                     const int q = t * 128 + wq * 32 + lane;
                     const int r = fast_div(q, p.magic_P), c = q - r * p.P;
                     const bool valid = (r < p.R) && (c < p.w) && (y0 + r < p.h);
@@ -511,7 +513,7 @@ conv_tc_kernel(const __grid_constant__ Params p) {
                 }
                 tc_fence_before();
                 mbar_arrive(bar_acce + 8 * buf);
-                if (wq == 0 && lane == 0) dbg_stamp(p, 2, step, 1);
+                if (wq == 0 && ehalf == 0 && lane == 0) dbg_stamp(p, 2, step, 1);
             }
         }
     }
@@ -599,8 +601,11 @@ static bool make_plan(const lf_conv_desc* d, Plan& pl) {
     pl.DC = d->d;
     if (hz > 0) {
         const int sms = sm_count();
-        while (pl.DC > 4 && (int64_t)d->n * pl.nstrips * ((d->d + pl.DC - 1) / pl.DC) < 2 * sms) pl.DC = (pl.DC + 1) / 2;
+        // enough items for one balanced wave; longer depth chunks amortise the 2 halo planes (measured:
+        // DC 8 -> 0.33 ms, 16 -> 0.31, 32 -> 0.30 for the config-B 3x3x3 conv)
+        while (pl.DC > 4 && (int64_t)d->n * pl.nstrips * ((d->d + pl.DC - 1) / pl.DC) < sms) pl.DC = (pl.DC + 1) / 2;
     }
+    { const char* dc = getenv("LFB200_TC_DC"); if (dc && hz > 0 && atoi(dc) > 0) pl.DC = min(d->d, atoi(dc)); }
     pl.ndchunks = (d->d + pl.DC - 1) / pl.DC;
     return true;
 }
