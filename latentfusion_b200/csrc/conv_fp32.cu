@@ -322,6 +322,37 @@ __global__ void actnorm_bwd_kernel(const float* __restrict__ gy, const float* __
     }
 }
 
+// fast path of the above for ordinary layers (gd == 1, C/4 a power of two <= 32): a position's channels sit on
+// C/4 consecutive lanes as float4s, the channel mean is an xor-shuffle over that lane group, every access is a
+// coalesced 128-bit load/store (the generic kernel above walks a position with one warp and scalar accesses).
+__global__ void __launch_bounds__(256)
+actnorm_bwd_vec_kernel(const float* __restrict__ gy, const float* __restrict__ y, const float* __restrict__ rnorm,
+                       float* __restrict__ du, int64_t positions, int c, int lg, int act, float slope, int norm) {
+    const int q4 = c >> 2;
+    const int64_t units = positions * q4;
+    const int64_t units_pad = (units + 31) & ~(int64_t)31;
+    const float inv_c = 1.f / (float)c;
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < units_pad; u += (int64_t)gridDim.x * blockDim.x) {
+        const bool live = u < units;
+        const int64_t uu = live ? u : units - 1;
+        const float4 g = ldg4(gy + uu * 4), yv = ldg4(y + uu * 4);
+        float4 o = g;
+        if (norm) {
+            float dot = g.x * yv.x + g.y * yv.y + g.z * yv.z + g.w * yv.w;
+            for (int s = 1; s < (1 << lg); s <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, s);
+            dot *= inv_c;
+            const float ir = 1.f / __ldg(rnorm + (uu >> lg));
+            o.x = (g.x - yv.x * dot) * ir; o.y = (g.y - yv.y * dot) * ir;
+            o.z = (g.z - yv.z * dot) * ir; o.w = (g.w - yv.w * dot) * ir;
+        }
+        if (act) {
+            o.x = yv.x > 0.f ? o.x : o.x * slope; o.y = yv.y > 0.f ? o.y : o.y * slope;
+            o.z = yv.z > 0.f ? o.z : o.z * slope; o.w = yv.w > 0.f ? o.w : o.w * slope;
+        }
+        if (live) *reinterpret_cast<float4*>(du + u * 4) = o;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // weight / bias gradient (training).  grad_w[tap][ci][co] += scale * sum_pos x[pos+tap][ci] * du[pos][co]
 // Each block takes a chunk of positions, loops over taps; partial [Cin x Cout] products reduced with
@@ -487,6 +518,19 @@ extern "C" int lf_actnorm_bwd(const float* gy, const float* y, const float* rnor
     LF_CHECK_ARG(gy && y && du, "actnorm_bwd: null pointer");
     LF_CHECK_ARG(!norm || rnorm, "actnorm_bwd: norm requires rnorm");
     LF_CHECK_ARG(outer > 0 && gd > 0 && inner > 0 && c > 0, "actnorm_bwd: bad extents");
+    const int q4 = c >> 2;
+    if (gd == 1 && (c & 3) == 0 && q4 >= 1 && q4 <= 32 && (q4 & (q4 - 1)) == 0) {
+        int lg = 0;
+        while ((1 << lg) < q4) ++lg;
+        const int64_t positions = outer * inner;
+        const int64_t units = positions * q4;
+        int64_t blocks = (units + 255) / 256;
+        const int64_t cap = (int64_t)sm_count() * 16;
+        if (blocks > cap) blocks = cap;
+        actnorm_bwd_vec_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(gy, y, rnorm, du, positions, c, lg,
+                                                                                 act, slope, norm);
+        LF_RETURN_LAUNCH();
+    }
     const int64_t groups = outer * inner;
     actnorm_bwd_kernel<<<(unsigned)((groups * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         gy, y, rnorm, du, outer, gd, inner, c, act, slope, norm);
