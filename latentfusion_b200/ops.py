@@ -250,6 +250,7 @@ def _unpack_weight_grad(gw, weight_shape, kind, depth):
     return gw.permute(2, 0, 1).reshape(-1, cin, 1, 1).contiguous()            # [c][d][ci]
 
 
+_FUSE_BWD = _os.environ.get('LFB200_FUSE_BWD', '0') == '1'
 _TC_PACK_CACHE = {}
 
 
@@ -366,9 +367,10 @@ class _EqConv(torch.autograd.Function):
         bdesc = _desc(bkind, bnd, n, d, h, w, cout, cin, k, scale, 0, 0.0, 0, precision)
         bflops = 2 * (n * h * w * (d if kind == KIND_CONV else 1)) * wb.shape[0] * cin * cout
         fused_done = False
-        # (single-pass bf16 only: in the 3-pass bf16x3 mode recomputing the prologue per pass costs more than
-        #  materialising du once)
-        if (ctx.needs_input_grad[0] and (act or norm) and not need_w and kind == KIND_CONV and precision == PRECISION_BF16
+        # Measured on B200 (config B 3x3x3): the fused staging makes the producers the bottleneck (0.57 ms) while
+        # the vectorised lf_actnorm_bwd (0.13 ms) + plain conv (0.32 ms) is faster, so fusion is opt-in
+        # (LFB200_FUSE_BWD=1) until the producer stage is widened.
+        if (_FUSE_BWD and ctx.needs_input_grad[0] and (act or norm) and not need_w and kind == KIND_CONV and precision == PRECISION_BF16
                 and _tc_ok(bdesc) and cout in (16, 32, 64, 128)):
             # pose-loop case: PixelNorm/LeakyReLU backward fused into the tcgen05 kernel's operand staging
             gx = torch.empty_like(x)
