@@ -73,3 +73,25 @@ def test_conv_tc_unsupported_shape_falls_back_to_exact_kernel():
     y1 = ops.eq_conv(x, w, None, precision=1)
     y0 = ops.eq_conv(x, w, None, precision=0)
     assert torch.equal(y1, y0)
+
+
+def test_fused_backward_staging_matches_unfused():
+    """lf_conv_bwd_data_fused (PixelNorm/LeakyReLU backward folded into the tcgen05 operand staging) against
+    lf_actnorm_bwd + lf_conv_fwd on the same tensors."""
+    dev = torch.device('cuda:0')
+    torch.manual_seed(3)
+    x = torch.randn(2, 32, 16, 16, 16, device=dev)
+    w = torch.randn(32, 32, 3, 3, 3, device=dev)
+    b = torch.randn(32, device=dev) * 0.1
+    grads = []
+    for fuse in (False, True):
+        ops._FUSE_BWD = fuse
+        try:
+            xt = x.clone().requires_grad_(True)
+            y = ops.eq_conv(xt, w, b, act=True, norm=True, precision=2)
+            torch.manual_seed(4)
+            y.backward(torch.randn_like(y))
+            grads.append(xt.grad)
+        finally:
+            ops._FUSE_BWD = False
+    torch.testing.assert_close(grads[1], grads[0], atol=2e-2, rtol=2e-2)
