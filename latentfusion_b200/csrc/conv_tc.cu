@@ -51,6 +51,7 @@ struct Params {
     float scale; int act; float slope; int norm;
     int a_part;                // 0: hi = bf16(x), 1: lo = bf16(x - hi)
     int pass_mode;
+    int dual, ncols;           // dual: B = [W_hi | W_lo] (N = 2*cout_pad): one pass yields x_hi*W_hi + x_hi*W_lo; ncols = MMA N
     uint32_t idesc;
     uint32_t slab_bytes, w_bytes;
     int debug;                    // dev only (LFB200_TC_DEBUG): 1 skip MMAs, 2 skip producer work, 4 skip epilogue work
@@ -176,6 +177,15 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const float* __re
             tmem_ld16(taddr + ch * 16, t16);
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[ch * 16 + i] = t16[i];
+        }
+        if (p.dual) {                                  // second half of the accumulator row: x_hi * W_lo
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                float t16[16];
+                tmem_ld16(taddr + p.cout_pad + ch * 16, t16);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[ch * 16 + i] += t16[i];
+            }
         }
         if (valid) {
             if (kAdd) {
@@ -416,7 +426,7 @@ conv_tc_kernel(const __grid_constant__ Params p) {
         if (my_tile < p.NT) {
             uint32_t kbase = 0;                         // running plane count at the start of the item
             uint32_t step = 0;                          // running step (accumulator) count
-            const uint32_t lbo_b = (uint32_t)p.cout_pad * 16u;
+            const uint32_t lbo_b = (uint32_t)p.ncols * 16u;
             // descriptor pieces (16-byte units): lo = start | LBO << 16 ; hi = SBO(128 B) | version 1 << 14
             const uint32_t desc_hi = (128u >> 4) | (1u << 14);
             const uint32_t a_lo_const = (lbo_a >> 4) << 16, b_lo_const = (lbo_b >> 4) << 16;
@@ -426,7 +436,7 @@ conv_tc_kernel(const __grid_constant__ Params p) {
             // hot-loop operands copied out of the (constant-bank) parameter block: the "memory" clobber of the
             // MMA asm would otherwise force a constant reload (LDCU, ~40 cycles) on every loop test
             const int K = p.k, HZ = p.hz, NT = p.NT, RING = p.ring, DEPTH = p.d, DBG = p.debug;
-            const uint32_t PP = (uint32_t)p.P, IDESC = p.idesc, COUT_PAD = (uint32_t)p.cout_pad, SLAB = p.slab_bytes;
+            const uint32_t PP = (uint32_t)p.P, IDESC = p.idesc, COUT_PAD = (uint32_t)p.ncols, SLAB = p.slab_bytes;
             for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
                 const int dchunk = item % p.ndchunks;
                 const int d0 = dchunk * p.DC, d1 = min(p.d, d0 + p.DC);
@@ -503,7 +513,7 @@ conv_tc_kernel(const __grid_constant__ Params p) {
                     const int r = fast_div(q, p.magic_P), c = q - r * p.P;
                     const bool valid = (r < p.R) && (c < p.w) && (y0 + r < p.h);
                     const int64_t opos = (((int64_t)n * p.d + d) * p.h + (y0 + r)) * p.w + c;
-                    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (buf * p.NT + t) * p.cout_pad;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (buf * p.NT + t) * p.ncols;
                     switch (p.pass_mode) {
                         case PASS_ONLY:  epilogue_tile<NCH, PASS_ONLY>(p, bias_s, taddr, opos, valid); break;
                         case PASS_FIRST: epilogue_tile<NCH, PASS_FIRST>(p, bias_s, taddr, opos, valid); break;
@@ -542,6 +552,10 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __res
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
         out[e] = __bfloat16_as_ushort(hi);
         out[per_part + e] = __bfloat16_as_ushort(lo);
+        // dual layout [tap][k-chunk][2*cout_pad][8]: rows [0,cout_pad) = hi, [cout_pad, 2*cout_pad) = lo
+        const int64_t drow = ((int64_t)tap * (cin_pad / 8) + kc) * (2 * cout_pad);
+        out[2 * per_part + (drow + co) * 8 + j] = __bfloat16_as_ushort(hi);
+        out[2 * per_part + (drow + cout_pad + co) * 8 + j] = __bfloat16_as_ushort(lo);
     }
 }
 
@@ -552,7 +566,7 @@ struct Plan {
     uint32_t slab_bytes, w_bytes, smem_bytes;
 };
 
-static bool make_plan(const lf_conv_desc* d, Plan& pl) {
+static bool make_plan(const lf_conv_desc* d, Plan& pl, bool dual = false) {
     if (!(d->ndim == 2 || d->ndim == 3)) return false;
     if (!(d->k == 1 || d->k == 3)) return false;
     if (d->cin % 4 != 0) return false;
@@ -565,10 +579,12 @@ static bool make_plan(const lf_conv_desc* d, Plan& pl) {
     pl.P = d->w + 2 * halo;
     if (pl.P >= 4096 || pl.cin_pad > 1024) return false;
     // accumulators: 2 buffers x NT tiles x cout_pad columns <= 512
-    int nt_max = 512 / (2 * pl.cout_pad);
+    const int ncols = pl.cout_pad * (dual ? 2 : 1);
+    if (ncols > 256) return false;
+    int nt_max = 512 / (2 * ncols);
     if (nt_max > kMaxTiles) nt_max = kMaxTiles;
     if (nt_max < 1) return false;
-    pl.w_bytes = (uint32_t)pl.taps * (pl.cin_pad / 8) * pl.cout_pad * 16;
+    pl.w_bytes = (uint32_t)pl.taps * (pl.cin_pad / 8) * ncols * 16;
     const uint32_t budget = 227 * 1024 - 256 - 1024;
     if (pl.w_bytes + 4096 > budget) return false;
     pl.ring = (hz > 0) ? kMaxRing : 2;
@@ -627,13 +643,13 @@ int conv_tc_launch(const lf_conv_desc* d, const float* x, const float* w, const 
     return conv_tc_launch_ex(d, x, w, bias, y, rnorm, nullptr, st);
 }
 
-int conv_tc_launch_ex(const lf_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
-                      float* rnorm, const TcPrologue* pro, cudaStream_t st) {
-    tc::Plan pl;
-    LF_CHECK_ARG(tc::make_plan(d, pl), "conv_tc: unsupported shape");
-    LF_CHECK_ARG(x && w && y, "conv_tc: null pointer");
+// one kernel launch: `wpk` points at the packed weight region to use (hi, lo or dual)
+static int conv_tc_launch_pass(const lf_conv_desc* d, const tc::Plan& pl, const float* x, const uint16_t* wpk,
+                               const float* bias, float* y, float* rnorm, const TcPrologue* pro, int a_part,
+                               int mode, int dual, cudaStream_t st) {
     tc::Params p;
-    p.x = x; p.bias = bias; p.y = y; p.rnorm = rnorm;
+    p.x = x; p.bias = bias; p.y = y; p.rnorm = rnorm; p.wpk = wpk;
+    p.a_part = a_part; p.pass_mode = mode; p.dual = dual;
     p.pro_y = pro ? pro->y : nullptr; p.pro_r = pro ? pro->rnorm : nullptr;
     p.pro_act = pro ? pro->act : 0; p.pro_norm = pro ? pro->norm : 0; p.pro_slope = pro ? pro->slope : 1.f; p.pro_lg = 0;
     if (pro) {
@@ -643,6 +659,7 @@ int conv_tc_launch_ex(const lf_conv_desc* d, const float* x, const float* w, con
     }
     p.n = d->n; p.d = d->d; p.h = d->h; p.w = d->w;
     p.cin = d->cin; p.cout = d->cout; p.cin_pad = pl.cin_pad; p.cout_pad = pl.cout_pad;
+    p.ncols = pl.cout_pad * (dual ? 2 : 1);
     p.k = d->k; p.hz = (d->ndim == 3) ? d->k / 2 : 0;
     p.R = pl.R; p.NT = pl.NT; p.P = pl.P; p.pos_alloc = pl.pos_alloc; p.ring = pl.ring; p.DC = pl.DC;
     p.nstrips = pl.nstrips; p.ndchunks = pl.ndchunks; p.items = d->n * pl.nstrips * pl.ndchunks;
@@ -653,9 +670,7 @@ int conv_tc_launch_ex(const lf_conv_desc* d, const float* x, const float* w, con
     p.magic_P = ((1ull << 40) + pl.P - 1) / (uint64_t)pl.P;
     // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1,
     // K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(pl.cout_pad >> 3) << 17) | ((128u >> 4) << 24);
-    const uint16_t* wpk = reinterpret_cast<const uint16_t*>(w);
-    const size_t part = (size_t)pl.w_bytes / 2;          // elements per precision part
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.ncols >> 3) << 17) | ((128u >> 4) << 24);
     void (*kern)(tc::Params) = nullptr;
     switch (((d->cout & 3) == 0 && pl.cout_pad <= 32) ? pl.cout_pad / 16 : 0) {
         case 1: kern = tc::conv_tc_kernel<1>; break;
@@ -667,19 +682,35 @@ int conv_tc_launch_ex(const lf_conv_desc* d, const float* x, const float* w, con
         if (e != cudaSuccess) { set_error("conv_tc: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return (int)e; }
     }
     const int grid = min(p.items, sm_count());
-    auto launch = [&](int a_part, int w_part, int mode) {
-        tc::Params q = p;
-        q.a_part = a_part; q.wpk = wpk + (size_t)w_part * part; q.pass_mode = mode;
-        kern<<<grid, tc::kThreads, pl.smem_bytes, st>>>(q);
-    };
-    if (d->precision == 2) {
-        launch(0, 0, tc::PASS_ONLY);
-    } else {
-        launch(0, 0, tc::PASS_FIRST);
-        launch(1, 0, tc::PASS_MID);
-        launch(0, 1, tc::PASS_LAST);
-    }
+    kern<<<grid, tc::kThreads, pl.smem_bytes, st>>>(p);
     LF_RETURN_LAUNCH();
+}
+
+int conv_tc_launch_ex(const lf_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
+                      float* rnorm, const TcPrologue* pro, cudaStream_t st) {
+    tc::Plan pl;
+    LF_CHECK_ARG(tc::make_plan(d, pl), "conv_tc: unsupported shape");
+    LF_CHECK_ARG(x && w && y, "conv_tc: null pointer");
+    // packed weights: [hi | lo | dual], each `part` elements (dual is two parts long)
+    const uint16_t* wbase = reinterpret_cast<const uint16_t*>(w);
+    const size_t part = (size_t)pl.w_bytes / 2;
+    if (d->precision == 2) return conv_tc_launch_pass(d, pl, x, wbase, bias, y, rnorm, pro, 0, tc::PASS_ONLY, 0, st);
+    static const bool no_dual = getenv("LFB200_TC_NO_DUAL") != nullptr;
+    if (!no_dual && pro == nullptr && (d->cout & 3) == 0 && pl.cout_pad <= 32) {
+        // bf16x3 in TWO passes: x_hi * [W_hi | W_lo] (one N = 2*Cout MMA per tap: the A tile is fetched from shared
+        // memory once for both products), then x_lo * W_hi accumulated in the epilogue
+        tc::Plan pd;
+        if (tc::make_plan(d, pd, true)) {
+            int e = conv_tc_launch_pass(d, pd, x, wbase + 2 * part, bias, y, rnorm, nullptr, 0, tc::PASS_FIRST, 1, st);
+            if (e != LF_OK) return e;
+            return conv_tc_launch_pass(d, pl, x, wbase, bias, y, rnorm, nullptr, 1, tc::PASS_LAST, 0, st);
+        }
+    }
+    int e = conv_tc_launch_pass(d, pl, x, wbase, bias, y, rnorm, pro, 0, tc::PASS_FIRST, 0, st);
+    if (e != LF_OK) return e;
+    e = conv_tc_launch_pass(d, pl, x, wbase, bias, y, rnorm, pro, 1, tc::PASS_MID, 0, st);
+    if (e != LF_OK) return e;
+    return conv_tc_launch_pass(d, pl, x, wbase + part, bias, y, rnorm, pro, 0, tc::PASS_LAST, 0, st);
 }
 
 }  // namespace lf
@@ -689,7 +720,7 @@ using namespace lf;
 extern "C" int64_t lf_conv_tc_weight_bytes(int taps, int cin, int cout) {
     if (taps <= 0 || cin <= 0 || cout <= 0) return 0;
     const int64_t cin_pad = (cin + 15) / 16 * 16, cout_pad = (cout + 15) / 16 * 16;
-    return 2 * taps * cin_pad * cout_pad * 2;
+    return 4 * taps * cin_pad * cout_pad * 2;       // hi | lo | dual (hi and lo interleaved per tap / k-chunk)
 }
 
 extern "C" int lf_conv_tc_pack_weights(const float* w_packed, void* out, int taps, int cin, int cout, void* stream) {

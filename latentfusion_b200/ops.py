@@ -270,6 +270,11 @@ def _tc_pack(wf, key):
     return out
 
 
+def _tc_passes(cout):
+    """kernel launches of one bf16x3 convolution: 2 when the dual-weight pass applies (Cout % 4 == 0, <= 32), else 3."""
+    return 2 if (cout % 4 == 0 and cout <= 32) else 3
+
+
 def _tc_ok(desc):
     return desc.precision != 0 and bool(L.lib().lf_conv_tc_supported(ctypes.byref(desc)))
 
@@ -343,7 +348,7 @@ class _EqConv(torch.autograd.Function):
             wf_arg = wf
         _call(_conv_name(kind, nd, k, 'fwd'), L.lib().lf_conv_fwd,
               (ctypes.byref(desc), _p(x), _p(wf_arg), _p(bpk), _p(y), _p(rnorm), _stream()),
-              kernels=2 if (norm and (kind == KIND_EXPAND or gcout > 64)) else 1,
+              kernels=(2 if (norm and (kind == KIND_EXPAND or gcout > 64)) else 1) if desc.precision != 1 else _tc_passes(gcout),
               nbytes=4 * (x.numel() + y.numel()), flops=2 * positions * taps * gcin * gcout)
         ctx.save_for_backward(x, y, rnorm, wb)
         ctx.wkey = wkey
@@ -404,7 +409,7 @@ class _EqConv(torch.autograd.Function):
                     wb_arg = wb
                 _call(_conv_name(kind, nd, k, 'bwd_data'), lib.lf_conv_fwd,
                       (ctypes.byref(bdesc), _p(du), _p(wb_arg), None, _p(gx), None, _stream()),
-                      kernels=3 if bdesc.precision == 1 else 1,
+                      kernels=_tc_passes(cin) if bdesc.precision == 1 else 1,
                       nbytes=4 * (du.numel() + gx.numel()), flops=bflops)
         if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
             taps = wb.shape[0]
