@@ -341,7 +341,7 @@ def run_ours(args):
     tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))        # dram bytes per launch from the committed ncu --set full captures
-    passes = 3 if args.precision in (1, 3) else 1
+    passes = 2 if args.precision in (1, 3) else 1        # bf16x3 = 3 tensor-core products issued in 2 kernel passes
     roof = None
     if ktrace:
         top = max(ktrace.items(), key=lambda kv: kv[1]['ms_total'])
@@ -355,7 +355,7 @@ def run_ours(args):
                     "frac": round(ach / peak, 4), "traffic": None if tr is None else tr * passes,
                     "peak_source": peaks['source'] + ' bf16 sustained',
                     "note": ("algorithmic flops 2*27*Cin*Cout*positions counted ONCE; the bf16x3 mode issues 3 tensor-core "
-                             "passes per call, so the MMA rate is 3x 'achieved'") if passes == 3 else
+                             "products per tap (in 2 kernel passes), so the MMA rate is 3x 'achieved'; traffic = 2 passes") if passes == 2 else
                             "algorithmic flops 2*27*Cin*Cout*positions"}
         else:
             peak = peaks['hbm_gbs']
