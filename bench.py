@@ -379,7 +379,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if args.precision == 0 else ("bf16x3" if args.precision == 1 else "bf16"),
             "data": "synthetic",
-            "config": {"workload": f"configs[1]: LF-synth(S={S},C={C}), V={V} ref views, N={N_HYP} hypotheses/GPU, "
+            "config": {"workload": f"configs[{1 if N_HYP == 8 else 2}]: LF-synth(S={S},C={C}), V={V} ref views, N={N_HYP} hypotheses/GPU, "
                                    f"128^2 render, fp32 storage; 1 iter = render fwd + pose loss + bwd to cameras + Adam",
                        "hypotheses_per_gpu": N_HYP, "hypothesis_renders_per_s": value * N_HYP,
                        "parallelism": f"hypotheses sharded x{world}, z_obj replicated",
@@ -425,10 +425,15 @@ def main():
                     help='0 exact fp32 FFMA convs; 1 tcgen05 bf16x3 split (fp32-parity grade, default); 2 tcgen05 bf16')
     ap.add_argument('--ref-device', default='cpu', help='reference arm device (cpu = the baseline; cuda = context)')
     ap.add_argument('--ref-hyp', type=int, default=2, help='hypotheses per reference step (bounded sample)')
+    ap.add_argument('--hypotheses', type=int, default=N_HYP,
+                    help='hypotheses per GPU (default 8 = BASELINE configs[1]; 64 = configs[2], adam_quick.toml at num_samples=64)')
     ap.add_argument('--no-kernel-events', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.hypotheses != N_HYP:
+        globals()['N_HYP'] = args.hypotheses
+        EST_ARGS.update(num_samples=args.hypotheses, ranking_size=args.hypotheses)
     if args.impl == 'reference':
         run_reference(args)
     else:

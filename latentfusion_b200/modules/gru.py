@@ -1,5 +1,14 @@
 """Convolutional GRU cell over latent volumes.  API/checkpoint mirror of reference
-``latentfusion/modules/gru.py`` (ConvGRUCell :7-46); gate math runs in two fused kernels."""
+``latentfusion/modules/gru.py`` (ConvGRUCell :7-46); gate math runs in two fused kernels.
+
+The reference concatenates ``[x, h]`` (2C+3 channels at the GRU fuser) and convolves once per gate.  A
+convolution is linear in its input channels, so here each gate is evaluated as ``conv_x(x) + conv_h(h)`` over
+the two channel groups (x zero-padded to a multiple of 4 channels): both halves then have shapes the tcgen05
+kernel takes (Cin % 4 == 0, packed weights resident in shared memory) and the ``torch.cat`` copy disappears.
+``precision=0`` keeps the single concatenated exact-fp32 convolution.
+"""
+import math
+
 import torch
 from torch import nn
 
@@ -19,9 +28,50 @@ class ConvGRUCell(nn.Module):
             return conv_module(in_channels=cin, out_channels=hidden_channels, kernel_size=kernel_size,
                                padding=self.padding, bias=bias)
         self.update_gate, self.reset_gate, self.out_gate = gate(), gate(), gate()
+        self._parts_cache = {}
+
+    # -- channel-group evaluation -----------------------------------------------------------------
+    def _weight_parts(self, name, gate, cx, cxp):
+        """(weight[:, :cx] zero-padded to cxp input channels, weight[:, cx:]) — cached while the weights are frozen."""
+        w = gate.module.weight
+        track = torch.is_grad_enabled() and w.requires_grad
+        key = (w._version, w.data_ptr(), cxp)
+        if not track:
+            hit = self._parts_cache.get(name)
+            if hit is not None and hit[0] == key:
+                return hit[1], hit[2]
+        wx = w[:, :cx]
+        if cxp != cx:
+            wx = torch.cat([wx, wx.new_zeros(w.shape[0], cxp - cx, *w.shape[2:])], dim=1)
+        wx, wh = wx.contiguous(), w[:, cx:].contiguous()
+        if not track:
+            wx, wh = wx.detach(), wh.detach()
+            self._parts_cache[name] = (key, wx, wh)
+        return wx, wh
+
+    def _gate(self, name, gate, xp, cx, h):
+        wx, wh = self._weight_parts(name, gate, cx, xp.shape[1])
+        fan_in = int(math.prod(gate.module.weight.shape[1:]))
+        prec = gate.precision
+        return (ops.eq_conv(xp, wx, gate.bias, precision=prec, fan_in=fan_in)
+                + ops.eq_conv(h, wh, None, precision=prec, fan_in=fan_in))
 
     def forward(self, x, h_cur):
-        x_in = torch.cat([x, h_cur], dim=1)
-        update, h_reset = ops.gru_gates1(self.update_gate(x_in), self.reset_gate(x_in), h_cur)
-        x_out = self.out_gate(torch.cat([x, h_reset], dim=1))
+        prec = self.update_gate.precision
+        if (ops.get_default_precision() if prec is None else prec) == ops.PRECISION_FP32 or not x.is_cuda:
+            x_in = torch.cat([x, h_cur], dim=1)
+            update, h_reset = ops.gru_gates1(self.update_gate(x_in), self.reset_gate(x_in), h_cur)
+            x_out = self.out_gate(torch.cat([x, h_reset], dim=1))
+            return ops.gru_gates2(h_cur, update, x_out)
+        cx = x.shape[1]
+        cxp = (cx + 3) // 4 * 4
+        if cxp != cx:
+            xp = ops.empty_cl((x.shape[0], cxp, *x.shape[2:]), x.device)
+            xp[:, :cx] = x
+            xp[:, cx:] = 0
+        else:
+            xp = x
+        update, h_reset = ops.gru_gates1(self._gate('u', self.update_gate, xp, cx, h_cur),
+                                         self._gate('r', self.reset_gate, xp, cx, h_cur), h_cur)
+        x_out = self._gate('o', self.out_gate, xp, cx, h_reset)
         return ops.gru_gates2(h_cur, update, x_out)

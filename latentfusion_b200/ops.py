@@ -294,7 +294,7 @@ class _EqConv(torch.autograd.Function):
     Reference: modules/equalized.py:57-64 + blocks.py:152-158 + modules/__init__.py:14-15."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, kind, depth, act, slope, norm, precision):
+    def forward(ctx, x, weight, bias, kind, depth, act, slope, norm, precision, fan_in=None):
         _need_cuda(x, weight, bias)
         x = to_cl(x)
         dev = x.device
@@ -326,7 +326,8 @@ class _EqConv(torch.autograd.Function):
             cout, k = cout_total // d, 1
             out_shape = (n, cout, d, h, w)
             gcin, gcout, positions = cin, cout, n * h * w
-        fan_in = int(math.prod(weight.shape[1:]))
+        if fan_in is None:             # a channel-group slice of a wider layer passes the full layer's fan-in
+            fan_in = int(math.prod(weight.shape[1:]))
         scale = math.sqrt(2.0 / fan_in)
         wf, wb = _pack_weight_cached(weight, kind, depth)
         if bias is None:
@@ -422,13 +423,13 @@ class _EqConv(torch.autograd.Function):
                 gw = _unpack_weight_grad(gwp, wshape, kind, depth)
             if has_bias and ctx.needs_input_grad[2]:
                 gb = gbp.t().reshape(-1) if kind == KIND_EXPAND else gbp.reshape(-1)
-        return gx, gw, gb, None, None, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None, None, None
 
 
-def eq_conv(x, weight, bias, act=False, slope=0.2, norm=False, kind=KIND_CONV, depth=0, precision=None):
+def eq_conv(x, weight, bias, act=False, slope=0.2, norm=False, kind=KIND_CONV, depth=0, precision=None, fan_in=None):
     if precision is None:
         precision = _default_precision
-    return _EqConv.apply(x, weight, bias, kind, depth, bool(act), float(slope), bool(norm), int(precision))
+    return _EqConv.apply(x, weight, bias, kind, depth, bool(act), float(slope), bool(norm), int(precision), fan_in)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -95,3 +95,44 @@ def test_fused_backward_staging_matches_unfused():
         finally:
             ops._FUSE_BWD = False
     torch.testing.assert_close(grads[1], grads[0], atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize('precision', [1, 2])
+def test_gru_cell_channel_group_split_matches_oracle(precision):
+    """ConvGRUCell on the tensor-core path evaluates each gate as conv_x(x) + conv_h(h) (modules/gru.py); the
+    oracle concatenates like the reference (modules/gru.py:36-43).  Includes the backward to x and h."""
+    from oracle import lf_oracle as O
+    from latentfusion_b200.modules.gru import ConvGRUCell
+    dev = torch.device('cuda:0')
+    torch.manual_seed(11)
+    C = 32
+    cell = ConvGRUCell(C + 3, C, kernel_size=3).to(dev)
+    for p in cell.parameters():
+        p.requires_grad_(False)
+    for g in (cell.update_gate, cell.reset_gate, cell.out_gate):
+        g.bias.normal_(0, 0.1)
+    x = torch.randn(1, C + 3, 12, 12, 12, device=dev)
+    h = torch.randn(1, C, 12, 12, 12, device=dev)
+    sd = {'gru.' + k: v.double().cpu() for k, v in cell.state_dict().items()}
+    xr, hr = x.double().cpu().requires_grad_(True), h.double().cpu().requires_grad_(True)
+    ref = O.gru_cell(sd, 'gru', xr, hr)
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    old = ops.get_default_precision()
+    ops.set_default_precision(precision)
+    try:
+        xt, ht = x.clone().requires_grad_(True), h.clone().requires_grad_(True)
+        ops.KernelTrace.reset(True)
+        out = cell(xt, ht)
+        names = [r[0] for r in ops.KernelTrace.records]
+        out.backward(g.float().to(dev))
+    finally:
+        ops.KernelTrace.reset(False)
+        ops.set_default_precision(old)
+    # every one of the 3 gates x 2 channel groups went through the tcgen05 kernel (its weights were packed for it)
+    assert names.count('lf_conv_tc_pack_weights') == 6, names
+    tol = dict(atol=2e-4, rtol=2e-3) if precision == 1 else dict(atol=5e-2, rtol=5e-2)
+    torch.testing.assert_close(out.double().cpu(), ref.detach(), **tol)
+    torch.testing.assert_close(xt.grad.double().cpu(), xr.grad, **tol)
+    torch.testing.assert_close(ht.grad.double().cpu(), hr.grad, **tol)
+

@@ -223,6 +223,46 @@ def test_full_size_properties(dev):
     torch.testing.assert_close(lhs.detach(), rhs, atol=1e-1, rtol=1e-3)
 
 
+def test_config2_batch_of_64_hypotheses_matches_single_runs(dev):
+    """BASELINE configs[2] extents (adam_quick.toml at num_samples=64: N=64, S=64, C=32 -> 2.1 GB tensors, element
+    indices past 2^29).  Hypotheses are independent, so the last hypothesis of the batch must be bit-identical to
+    the same hypothesis processed alone: resample forward, resample backward-to-camera, tcgen05 conv, depth collapse."""
+    from latentfusion_b200 import ops
+    from latentfusion_b200.modules.geometry import ObjectToCameraTransform
+    S, C, N = 64, 32, 64
+    cams, _ = ph.synthetic_cameras(N, S, seed=21)
+    cam = cams.to(dev)
+    last = cam[N - 1:N]
+    T = ObjectToCameraTransform(1.0)
+    torch.manual_seed(2)
+    vol = torch.randn(1, C, S, S, S, device=dev)
+    full = T(vol, cam)
+    one = T(vol, last)
+    assert torch.equal(full[N - 1:N], one)
+    w = torch.randn(32, C, 3, 3, 3, device=dev)
+    b = torch.randn(32, device=dev) * 0.1
+    for precision in (1, 2):
+        yf = ops.eq_conv(full, w, b, act=True, norm=True, precision=precision)
+        yo = ops.eq_conv(one, w, b, act=True, norm=True, precision=precision)
+        assert torch.equal(yf[N - 1:N], yo)
+    wc = torch.randn(32, C * S, 1, 1, device=dev)
+    pf = ops.eq_conv(full, wc, None, kind=ops.KIND_COLLAPSE, depth=S)
+    po = ops.eq_conv(one, wc, None, kind=ops.KIND_COLLAPSE, depth=S)
+    assert torch.equal(pf[N - 1:N], po)
+    del yf, yo, pf, po
+    # backward to the cameras: d<full, g>/d(cam block) row N-1 == the single-camera run
+    g = torch.randn_like(one)
+    blk = cam.o2c_block(1.0).detach().requires_grad_(True)
+    out = ops.resample_o2c(vol, blk)
+    gfull = torch.zeros_like(out)
+    gfull[N - 1:N] = g
+    out.backward(gfull)
+    blk1 = last.o2c_block(1.0).detach().requires_grad_(True)
+    ops.resample_o2c(vol, blk1).backward(g)
+    assert torch.equal(blk.grad[N - 1], blk1.grad[0])
+    assert torch.count_nonzero(blk.grad[:N - 1]) == 0
+
+
 def test_fused_pose_loss_head_vs_reference_formulas(g, dev):
     """csrc/pose_loss.cu against the torch composition of the reference ops (interpret_logits ->
     denormalize_depth -> uncrop x2 -> default_pose_loss): terms and all four gradient paths."""
