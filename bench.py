@@ -237,12 +237,15 @@ def run_ours(args):
     # ---- reconstruction (once per object, untimed here; reported separately): views shard over ranks,
     # per-view cubes are all-gathered (NCCL), the GRU recurrence runs replicated.
     from latentfusion_b200 import dist as lfdist
-    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(); t0.record()
-    with torch.no_grad():
-        z_obj = lfdist.build_latent_object_sharded(model, inp['ref_cams'], inp['color'], inp['mask'], rank, world)
-    t1.record(); torch.cuda.synchronize()
-    recon_ms = t0.elapsed_time(t1)
+    recon_times = []
+    for _ in range(2):                      # first call is cold (allocator, weight packing); report the second
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); t0.record()
+        with torch.no_grad():
+            z_obj = lfdist.build_latent_object_sharded(model, inp['ref_cams'], inp['color'], inp['mask'], rank, world)
+        t1.record(); torch.cuda.synchronize()
+        recon_times.append(t0.elapsed_time(t1))
+    recon_ms = recon_times[-1]
 
     # ---- per-rank hypotheses (weak scaling: N_HYP per GPU, independent -> no per-iteration collective)
     hyp_full = hypothesis_cameras(inp['gt'].uncrop(), N_HYP, seed=7 + rank)
@@ -384,7 +387,8 @@ def run_ours(args):
                        "hypotheses_per_gpu": N_HYP, "hypothesis_renders_per_s": value * N_HYP,
                        "parallelism": f"hypotheses sharded x{world}, z_obj replicated",
                        "l2": "per-step working set (>2 GB of activations) exceeds the 126 MB L2; no flush needed",
-                       "precision": args.precision, "recon_ms_once_per_object": round(recon_ms, 2)},
+                       "precision": args.precision, "recon_ms_once_per_object": round(recon_ms, 2),
+                       "recon_ms_first_call": round(recon_times[0], 2)},
             "e2e": {"value": e2e_value, "unit": "iters/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
                     "note": "one estimator.estimate(z_obj, host target obs, host cameras) call of K iterations / K: includes H2D of target+cameras (graph captured once, during warm-up), per-iteration D2H of losses and camera snapshots"},

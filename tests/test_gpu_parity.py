@@ -46,9 +46,10 @@ def test_c2o_resample_vs_golden(g, dev):
     torch.testing.assert_close(vol.grad.cpu(), g['c2o.grad_vol'], **OUT_TOL)
 
 
-@pytest.mark.parametrize('C,S,N', [(8, 16, 3), (32, 24, 2), (6, 9, 2), (1, 10, 2), (64, 12, 2)])
+@pytest.mark.parametrize('C,S,N', [(8, 16, 3), (32, 24, 2), (6, 9, 2), (1, 10, 2), (64, 12, 2), (16, 20, 2), (32, 33, 2)])
 def test_o2c_vs_oracle_shapes(dev, C, S, N):
-    """channel counts hitting the float4 path (C%4==0), the scalar path and multi-chunk groups."""
+    """channel counts hitting the depth-marching kernel (C in 16/32/64, incl. S not a multiple of the tile), the
+    brick kernel's float4 path (other C%4==0), its scalar path and multi-chunk groups."""
     from oracle import lf_oracle as O
     from latentfusion_b200.modules.geometry import ObjectToCameraTransform
     cams, _ = ph.synthetic_cameras(N, S, seed=C)
@@ -74,6 +75,41 @@ def test_o2c_vs_oracle_shapes(dev, C, S, N):
     (out * w.to(dev)).sum().backward()
     ours = torch.cat([cam.log_quaternion.grad, cam.translation.grad, cam.viewport.grad], 1).cpu()
     ph.assert_grad_close_to_fp64(ours, g32, g64, f'o2c camera grads C={C} S={S}')
+
+
+@pytest.mark.parametrize('C,S,V', [(16, 12, 3), (32, 17, 2), (64, 8, 2)])
+def test_c2o_vs_oracle_shapes(dev, C, S, V):
+    """camera->object resample on the depth-marching kernel against the oracle (distinct source cube per view)."""
+    from oracle import lf_oracle as O
+    from latentfusion_b200.modules.geometry import CameraToObjectTransform
+    cams, _ = ph.synthetic_cameras(V, S, seed=C + 1, perturb=False)
+    d = ph.cam_to_dict(cams)
+    torch.manual_seed(S)
+    vol = torch.randn(V, C, S, S, S)
+    ref = O.camera_to_object(vol, ph.oracle_camera(d))
+    out = CameraToObjectTransform(1.0)(vol.to(dev), ph.product_camera(d, dev))
+    torch.testing.assert_close(out.cpu(), ref, atol=5e-4, rtol=1e-3)
+
+
+def test_march_and_brick_resamplers_agree_at_full_size(dev):
+    """the two forward kernels (depth-marching with register-resident corners / brick gather) evaluate the same
+    weights and corners and differ only in the order of the 8-term sum."""
+    import os
+    from latentfusion_b200.modules.geometry import ObjectToCameraTransform, CameraToObjectTransform
+    S, C, N = 64, 32, 8
+    cams, _ = ph.synthetic_cameras(N, S, seed=5)
+    cam = cams.to(dev)
+    torch.manual_seed(1)
+    vol = torch.randn(1, C, S, S, S, device=dev)
+    vols = torch.randn(N, C, S, S, S, device=dev)
+    march = (ObjectToCameraTransform(1.0)(vol, cam), CameraToObjectTransform(1.0)(vols, cam))
+    os.environ['LFB200_RESAMPLE_BRICK'] = '1'
+    try:
+        brick = (ObjectToCameraTransform(1.0)(vol, cam), CameraToObjectTransform(1.0)(vols, cam))
+    finally:
+        del os.environ['LFB200_RESAMPLE_BRICK']
+    for a, b in zip(march, brick):
+        torch.testing.assert_close(a, b, atol=2e-6, rtol=1e-5)
 
 
 def test_o2c_bwd_cam_is_deterministic(dev):
