@@ -37,6 +37,17 @@ __device__ __forceinline__ float linspace_at(float a, float b, int n, int i) {
     return (i < n / 2) ? (a + step * (float)i) : (b - step * (float)(n - 1 - i));
 }
 
+// packed 2 x fp32 FMA (Blackwell FFMA2): d.xy = a * b.xy + c.xy with a scalar broadcast
+__device__ __forceinline__ void ffma2_bcast(float a, float bx, float by, float& cx, float& cy) {
+    unsigned long long ra, rb, rc, rd;
+    ra = ((unsigned long long)__float_as_uint(a) << 32) | __float_as_uint(a);
+    rb = ((unsigned long long)__float_as_uint(by) << 32) | __float_as_uint(bx);
+    rc = ((unsigned long long)__float_as_uint(cy) << 32) | __float_as_uint(cx);
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    cx = __uint_as_float((unsigned)rd);
+    cy = __uint_as_float((unsigned)(rd >> 32));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -14,6 +14,9 @@
 //   kind 2: depth-expand     x[N][H][W][Cin]    -> y[N][D][H][W][Cout], one 1x1 GEMM per depth slice,
 //           bias is [D][Cout]                                                  (FactorProjection2d3d)
 #include "common.cuh"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace lf {
 
@@ -264,6 +267,270 @@ conv_expand_kernel(const ConvGeom g, const float* __restrict__ x, const float* _
 }
 
 // ---------------------------------------------------------------------------------------------
+// The two depth projections of the render path (K5), as dedicated kernels.
+//
+// collapse (FactorProjection3d2d, geometry.py:744-749 + its conv): M = N*H*W positions, N = Cout <= 32,
+// K = D*Cin (2048 at config B).  One 128-position tile per CTA gives only M/128 = 256 CTAs of 4 warps for
+// 148 SMs, so the generic kernel above is latency-bound (12 TF/s).  Here a thread-block CLUSTER of KS CTAs
+// shares one tile and splits the depth axis; the KS partial 128x32 accumulator tiles are summed through
+// distributed shared memory in rank order (deterministic), each CTA finishing 128/KS rows of the tile
+// including the fused scale/bias/LeakyReLU/PixelNorm epilogue.  Global->register prefetch of the next K
+// chunk overlaps the FFMA loop (double-buffered shared tiles, one barrier per chunk).
+// ---------------------------------------------------------------------------------------------
+constexpr int RED_STRIDE = 36;     // floats per row of the partial-tile buffer (16-byte aligned rows)
+
+constexpr int CK = 32;             // K chunk of the collapse kernel (input channels per stage)
+constexpr int CMP = BM + 1;        // padded position pitch of its A tile (in float4 slots)
+
+__global__ void __launch_bounds__(128, 4)
+collapse_cluster_kernel(const ConvGeom g, const float* __restrict__ x, const float* __restrict__ wp,
+                        const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ rnorm, int KS) {
+    // A tile, k-blocked: sA[stage][k/4][position] = 4 consecutive channels of one position (one 128-bit slot).
+    // A quarter-warp stores the 8 slots (k/4 = 0..7) of ONE position: pitch 129 slots puts them in 8 different
+    // 16-byte bank groups; the FFMA loop reads, per k/4, the slots of positions ty, ty+16, ... (4 adjacent slots
+    // per warp, broadcast over the 8 cout lanes).  The partial-tile buffer of the cluster reduction aliases it.
+    __shared__ __align__(16) float4 sA4[2][CK / 4][CMP];
+    __shared__ __align__(16) float sB[2][CK][32];
+    float* red = reinterpret_cast<float*>(&sA4[0][0][0]);
+    static_assert(sizeof(float4) * 2 * (CK / 4) * CMP >= sizeof(float) * BM * RED_STRIDE, "partial tile must fit in the A buffer");
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();          // == blockIdx.z
+    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+    const int64_t hw = (int64_t)g.h * g.w;
+    const int64_t tstride = hw * g.cin;
+    const int tper = g.taps / KS, t0 = rank * tper;
+    const int kchunks = (g.cin + CK - 1) / CK;
+    const int nchunks = tper * kchunks;
+    // global->shared mapping of the A tile: float4 slot e = q*128 + tid -> position e/8, channel quad e%8
+    const int ak4 = tid & 7;
+    uint32_t abase[BM / 16];          // in float4 units (host checks the tensor is < 2^32 of them); ~0u = no position
+#pragma unroll
+    for (int q = 0; q < BM / 16; ++q) {
+        const int64_t P = (int64_t)blockIdx.x * BM + q * 16 + (tid >> 3);
+        abase[q] = 0xffffffffu;
+        if (P < g.out_positions) { const int64_t nb = P / hw; abase[q] = (uint32_t)((((nb * g.d) * hw + (P - nb * hw)) * g.cin) >> 2); }
+    }
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const uint32_t tstride4 = (uint32_t)(tstride >> 2);
+
+    float4 ra[BM / 16];
+    float4 rb[CK * 8 / 128];
+    auto load_chunk = [&](int c) {
+        const int tap = t0 + c / kchunks, kc = (c % kchunks) * CK;
+        const int k = kc + ak4 * 4;
+#pragma unroll
+        for (int q = 0; q < BM / 16; ++q)
+            ra[q] = (abase[q] != 0xffffffffu && k < g.cin) ? __ldg(x4 + (abase[q] + (uint32_t)tap * tstride4 + (uint32_t)(k >> 2))) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < CK * 8 / 128; ++q) {
+            const int e = tid + q * 128, kk = e >> 3, nn = (e & 7) * 4;
+            const float* wt = wp + ((int64_t)tap * g.cin + kc + kk) * g.cout + nn;
+            rb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kc + kk < g.cin) {
+                if ((g.cout & 3) == 0 && nn + 3 < g.cout) rb[q] = ldg4(wt);
+                else {
+                    if (nn + 0 < g.cout) rb[q].x = __ldg(wt + 0);
+                    if (nn + 1 < g.cout) rb[q].y = __ldg(wt + 1);
+                    if (nn + 2 < g.cout) rb[q].z = __ldg(wt + 2);
+                    if (nn + 3 < g.cout) rb[q].w = __ldg(wt + 3);
+                }
+            }
+        }
+    };
+    auto store_chunk = [&](int st) {
+#pragma unroll
+        for (int q = 0; q < BM / 16; ++q) sA4[st][ak4][q * 16 + (tid >> 3)] = ra[q];
+#pragma unroll
+        for (int q = 0; q < CK * 8 / 128; ++q) {
+            const int e = tid + q * 128;
+            *reinterpret_cast<float4*>(&sB[st][e >> 3][(e & 7) * 4]) = rb[q];
+        }
+    };
+
+    float acc[8][4];                 // rows ty + 16*i, couts tx*4 + j
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    load_chunk(0);
+    store_chunk(0);
+    __syncthreads();
+    for (int c = 0; c < nchunks; ++c) {
+        const int st = c & 1;
+        if (c + 1 < nchunks) load_chunk(c + 1);
+#pragma unroll
+        for (int k4 = 0; k4 < CK / 4; ++k4) {
+            float4 a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = sA4[st][k4][ty + 16 * i];
+#pragma unroll
+            for (int kq = 0; kq < 4; ++kq) {
+                const float4 bv = *reinterpret_cast<const float4*>(&sB[st][k4 * 4 + kq][tx * 4]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float av = kq == 0 ? a[i].x : kq == 1 ? a[i].y : kq == 2 ? a[i].z : a[i].w;
+                    ffma2_bcast(av, bv.x, bv.y, acc[i][0], acc[i][1]);
+                    ffma2_bcast(av, bv.z, bv.w, acc[i][2], acc[i][3]);
+                }
+            }
+        }
+        if (c + 1 < nchunks) store_chunk(st ^ 1);
+        __syncthreads();
+    }
+
+    // ---- cluster reduction through distributed shared memory (the A buffer is free now)
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(&red[(ty + 16 * i) * RED_STRIDE + tx * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    cluster.sync();
+    const int rows = BM / KS;
+    const float inv_c = 1.f / (float)g.cout;
+    for (int rr = ty; rr < rows; rr += 16) {
+        const int row = rank * rows + rr;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < KS; ++r) {                       // fixed rank order: bit-reproducible
+            const float* peer = cluster.map_shared_rank(red, r);
+            const float4 pv = *reinterpret_cast<const float4*>(peer + row * RED_STRIDE + tx * 4);
+            v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w;
+        }
+        const int64_t P = (int64_t)blockIdx.x * BM + row;
+        float o[4] = {v.x, v.y, v.z, v.w};
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int co = tx * 4 + j;
+            float t = o[j] * g.scale;
+            if (bias != nullptr && co < g.cout) t += __ldg(bias + co);
+            if (g.act) t = t > 0.f ? t : t * g.slope;
+            if (co >= g.cout) t = 0.f;
+            o[j] = t;
+            ss += t * t;
+        }
+        if (g.norm) {
+            ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+            const float r = sqrtf(ss * inv_c + 1e-8f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = o[j] / r;
+            if (rnorm != nullptr && tx == 0 && P < g.out_positions) rnorm[P] = r;
+        }
+        if (P < g.out_positions) {
+            float* yp = y + P * g.cout + tx * 4;
+            if ((g.cout & 3) == 0 && tx * 4 + 4 <= g.cout) *reinterpret_cast<float4*>(yp) = make_float4(o[0], o[1], o[2], o[3]);
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (tx * 4 + j < g.cout) yp[j] = o[j];
+            }
+        }
+    }
+    cluster.sync();          // nobody leaves while a peer may still read its partial tile
+}
+
+// expand (FactorProjection2d3d, geometry.py:724-728; and the backward of the collapse): per depth slice t a
+// 1x1 GEMM with its own weight slice, y[n][t][p][co] = act(scale * sum_ci x[n][p][ci] * w[t][ci][co] + b[t][co]).
+// The 128 x Cin input tile is staged in shared memory ONCE per CTA and reused for TS depth slices (the
+// generic kernel re-staged it per slice); weight slices are register-prefetched; 128-bit output stores.
+template <int CINMAX>
+__global__ void __launch_bounds__(128)
+expand_multi_kernel(const ConvGeom g, const float* __restrict__ x, const float* __restrict__ wp,
+                    const float* __restrict__ bias, float* __restrict__ y, int TS) {
+    __shared__ __align__(16) float sA[CINMAX][BM + 4];
+    __shared__ __align__(16) float sB[2][CINMAX][32];
+    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+    const int n0 = blockIdx.y * 32;
+    const int64_t hw = (int64_t)g.h * g.w;
+    const int64_t in_positions = (int64_t)g.n * hw;
+    const int64_t Pm = (int64_t)blockIdx.x * BM + tid;
+    const int t0 = blockIdx.z * TS, t1 = min(g.d, t0 + TS);
+    // stage the input tile: sA[ci][pos]
+    for (int kc = 0; kc < g.cin; kc += 4) {
+        const float4 v = (Pm < in_positions) ? ldg4(x + Pm * g.cin + kc) : make_float4(0.f, 0.f, 0.f, 0.f);
+        sA[kc + 0][tid] = v.x; sA[kc + 1][tid] = v.y; sA[kc + 2][tid] = v.z; sA[kc + 3][tid] = v.w;
+    }
+    const int nb_elems = g.cin * 8;                       // float4 slots of one weight slice tile [cin][32]
+    float4 rb[CINMAX * 8 / 128];
+    auto load_b = [&](int t) {
+#pragma unroll
+        for (int q = 0; q < CINMAX * 8 / 128; ++q) {
+            const int e = tid + q * 128;
+            rb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e < nb_elems) {
+                const int kk = e >> 3, nn = (e & 7) * 4;
+                const float* wt = wp + ((int64_t)t * g.cin + kk) * g.cout + n0 + nn;
+                if ((g.cout & 3) == 0 && n0 + nn + 3 < g.cout) rb[q] = ldg4(wt);
+                else {
+                    if (n0 + nn + 0 < g.cout) rb[q].x = __ldg(wt + 0);
+                    if (n0 + nn + 1 < g.cout) rb[q].y = __ldg(wt + 1);
+                    if (n0 + nn + 2 < g.cout) rb[q].z = __ldg(wt + 2);
+                    if (n0 + nn + 3 < g.cout) rb[q].w = __ldg(wt + 3);
+                }
+            }
+        }
+    };
+    auto store_b = [&](int st) {
+#pragma unroll
+        for (int q = 0; q < CINMAX * 8 / 128; ++q) {
+            const int e = tid + q * 128;
+            if (e < nb_elems) *reinterpret_cast<float4*>(&sB[st][e >> 3][(e & 7) * 4]) = rb[q];
+        }
+    };
+    load_b(t0);
+    store_b(0);
+    __syncthreads();
+    for (int t = t0; t < t1; ++t) {
+        const int st = (t - t0) & 1;
+        if (t + 1 < t1) load_b(t + 1);
+        float acc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int kk = 0; kk < g.cin; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&sA[kk][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&sA[kk][ty * 8 + 4]);
+            const float4 bv = *reinterpret_cast<const float4*>(&sB[st][kk][tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                ffma2_bcast(a[i], bv.x, bv.y, acc[i][0], acc[i][1]);
+                ffma2_bcast(a[i], bv.z, bv.w, acc[i][2], acc[i][3]);
+            }
+        }
+        float bj[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int co = n0 + tx * 4 + j;
+            if (bias != nullptr && co < g.cout) bj[j] = __ldg(bias + (int64_t)t * g.cout + co);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t P = (int64_t)blockIdx.x * BM + ty * 8 + i;
+            if (P >= in_positions) continue;
+            const int64_t nb = P / hw, p2 = P - nb * hw;
+            float* yp = y + (((nb * g.d + t) * hw) + p2) * g.cout + n0 + tx * 4;
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float u = acc[i][j] * g.scale + bj[j];
+                if (g.act) u = u > 0.f ? u : u * g.slope;
+                v[j] = u;
+            }
+            if ((g.cout & 3) == 0 && n0 + tx * 4 + 4 <= g.cout) st4_stream(yp, make_float4(v[0], v[1], v[2], v[3]));
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n0 + tx * 4 + j < g.cout) yp[j] = v[j];
+            }
+        }
+        if (t + 1 < t1) store_b(st ^ 1);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // PixelNorm over a (gd x C) group:  x[(o*gd + t)*inner + p][c], group = all (t, c) for fixed (o, p).
 // gd = 1 is the ordinary per-position PixelNorm (modules/__init__.py:14-15); gd = S is the
 // normalisation over the C*S channels of FactorProjection2d3d before its view() (geometry.py:724-728).
@@ -480,15 +747,42 @@ int conv_fp32_launch(const lf_conv_desc* d, const float* x, const float* w, cons
     if (g.kind == 2) {
         // expand: act fused; norm (over the whole (d,c) group) runs as a second pass in place
         ConvGeom ge = g; ge.norm = 0;
-        dim3 grid((unsigned)mblocks, (g.cout + 31) / 32, g.d);
-        if (vec) conv_expand_kernel<32, 4><<<grid, 128, 0, st>>>(ge, x, w, bias, y);
-        else conv_expand_kernel<32, 1><<<grid, 128, 0, st>>>(ge, x, w, bias, y);
+        if (vec && g.cin <= 32) {
+            // depth slices per CTA: amortise the staged input tile, keep >= ~8 CTAs per SM in the grid
+            int TS = 4;
+            while (TS > 1 && mblocks * ((g.cout + 31) / 32) * ((g.d + TS - 1) / TS) < 8ll * sm_count()) TS /= 2;
+            dim3 grid((unsigned)mblocks, (g.cout + 31) / 32, (g.d + TS - 1) / TS);
+            expand_multi_kernel<32><<<grid, 128, 0, st>>>(ge, x, w, bias, y, TS);
+        } else {
+            dim3 grid((unsigned)mblocks, (g.cout + 31) / 32, g.d);
+            if (vec) conv_expand_kernel<32, 4><<<grid, 128, 0, st>>>(ge, x, w, bias, y);
+            else conv_expand_kernel<32, 1><<<grid, 128, 0, st>>>(ge, x, w, bias, y);
+        }
         if (g.norm) {
             const int64_t groups = g.out_positions;
             const int64_t inner = (int64_t)g.h * g.w;
             pixelnorm_group_kernel<<<(unsigned)((groups * 32 + 255) / 256), 256, 0, st>>>(y, y, rnorm, g.n, g.d, inner, g.cout);
         }
         LF_RETURN_LAUNCH();
+    }
+    if (g.kind == 1 && vec && g.cout <= 32) {
+        // depth-collapse: split the depth axis over a cluster of KS CTAs per 128-position tile
+        int KS = 8;
+        while (KS > 1 && (g.taps % KS) != 0) KS /= 2;       // (a function of the depth only: batch-size independent bits)
+        if ((int64_t)g.n * g.d * g.h * g.w * (g.cin / 4) >= (1ll << 32)) KS = 1;
+        if (KS > 1) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)mblocks, 1, KS);
+            cfg.blockDim = dim3(128);
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = KS;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, collapse_cluster_kernel, g, x, w, bias, y, rnorm, KS);
+            if (e != cudaSuccess) { set_error("collapse: cluster launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+            LF_RETURN_LAUNCH();
+        }
     }
     const bool fuse_norm = g.norm && g.cout <= 64;
     ConvGeom gk = g; gk.norm = fuse_norm ? 1 : 0;

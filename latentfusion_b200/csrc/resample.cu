@@ -82,17 +82,6 @@ __device__ __forceinline__ void gen_grid(const float* __restrict__ cm, int S, in
     }
 }
 
-// packed 2 x fp32 FMA (Blackwell FFMA2): d.xy = a * b.xy + c.xy with a scalar broadcast
-__device__ __forceinline__ void ffma2_bcast(float a, float bx, float by, float& cx, float& cy) {
-    unsigned long long ra, rb, rc, rd;
-    ra = ((unsigned long long)__float_as_uint(a) << 32) | __float_as_uint(a);
-    rb = ((unsigned long long)__float_as_uint(by) << 32) | __float_as_uint(bx);
-    rc = ((unsigned long long)__float_as_uint(cy) << 32) | __float_as_uint(cx);
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-    cx = __uint_as_float((unsigned)rd);
-    cy = __uint_as_float((unsigned)(rd >> 32));
-}
-
 template <int VEC> struct Vec;
 template <> struct Vec<4> {
     typedef float4 T;

@@ -136,3 +136,42 @@ def test_gru_cell_channel_group_split_matches_oracle(precision):
     torch.testing.assert_close(xt.grad.double().cpu(), xr.grad, **tol)
     torch.testing.assert_close(ht.grad.double().cpu(), hr.grad, **tol)
 
+
+
+@pytest.mark.parametrize('n,c,cout,depth,hw', [(2, 8, 8, 16, 16), (1, 32, 32, 64, 64), (2, 12, 20, 12, 9), (1, 16, 32, 6, 20),
+                                                (3, 32, 16, 8, 7)])
+def test_depth_projections_vs_torch_fp64(n, c, cout, depth, hw):
+    """FactorProjection3d2d / 2d3d (geometry.py:724-749) as the dedicated kernels: the cluster split-depth collapse
+    (taps % 8 / 4 / 2 == 0 or the generic kernel otherwise) and the multi-slice expand, forward and backward, against
+    torch's fp64 1x1 convolution over the C*D channel view.  Exact-fp32 kernels -> the fp32 tolerance."""
+    dev = torch.device('cuda:0')
+    torch.manual_seed(n * 100 + c)
+    x = torch.randn(n, c, depth, hw, hw, device=dev)
+    w = torch.randn(cout, c * depth, 1, 1, device=dev)
+    b = torch.randn(cout, device=dev) * 0.1
+    y = ops.eq_conv(x, w, b, act=True, norm=True, kind=ops.KIND_COLLAPSE, depth=depth, precision=0)
+    torch.testing.assert_close(y.double(), ref_conv(x.reshape(n, c * depth, hw, hw), w, b, True, True), atol=1e-4, rtol=1e-3)
+    # backward on the linear layer (a LeakyReLU gate may legitimately flip for pre-activations within rounding of 0)
+    xt = x.clone().requires_grad_(True)
+    yl = ops.eq_conv(xt, w, b, kind=ops.KIND_COLLAPSE, depth=depth, precision=0)
+    xr = x.double().requires_grad_(True)
+    ref = ref_conv(xr.reshape(n, c * depth, hw, hw), w, b, False, False)
+    torch.testing.assert_close(yl.double(), ref, atol=1e-4, rtol=1e-3)
+    g = torch.randn_like(yl)
+    yl.backward(g)
+    ref.backward(g.double())
+    torch.testing.assert_close(xt.grad.double(), xr.grad, atol=1e-4, rtol=1e-3)
+    # expand: [n, cin, h, w] -> [n, c, depth, h, w]
+    x2 = torch.randn(n, cout, hw, hw, device=dev)
+    w2 = torch.randn(c * depth, cout, 1, 1, device=dev)
+    b2 = torch.randn(c * depth, device=dev) * 0.1
+    y2 = ops.eq_conv(x2, w2, b2, act=True, norm=False, kind=ops.KIND_EXPAND, depth=depth, precision=0)
+    torch.testing.assert_close(y2.double(), ref_conv(x2, w2, b2, True, False).reshape(n, c, depth, hw, hw), atol=1e-4, rtol=1e-3)
+    x2t = x2.clone().requires_grad_(True)
+    y2l = ops.eq_conv(x2t, w2, b2, kind=ops.KIND_EXPAND, depth=depth, precision=0)
+    x2r = x2.double().requires_grad_(True)
+    ref2 = ref_conv(x2r, w2, b2, False, False).reshape(n, c, depth, hw, hw)
+    g2 = torch.randn_like(y2l)
+    y2l.backward(g2)
+    ref2.backward(g2.double())
+    torch.testing.assert_close(x2t.grad.double(), x2r.grad, atol=1e-4, rtol=1e-3)
