@@ -226,6 +226,12 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const float* __re
                 float v[16];
                 __syncwarp();
                 tmem_ld16(taddr + cb, v);
+                if (p.dual) {
+                    float u[16];
+                    tmem_ld16(taddr + p.cout_pad + cb, u);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += u[i];
+                }
                 if (valid) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
@@ -244,17 +250,44 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const float* __re
             float v[16];
             __syncwarp();
             tmem_ld16(taddr + cb, v);
-            if (valid) {
+            if (p.dual) {
+                float u[16];
+                tmem_ld16(taddr + p.cout_pad + cb, u);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float a = v[i];
-                    if (cb + i < p.cout) {
-                        if (kAdd) a += yp[cb + i];
-                        if (!kRaw) {
-                            a = a * p.scale + bias_s[cb + i];
-                            a = fmaxf(a, a * slope) * inv;
+                for (int i = 0; i < 16; ++i) v[i] += u[i];
+            }
+            if (valid) {
+                if ((p.cout & 3) == 0) {                 // 128-bit read-modify-write of the row
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        if (cb + i < p.cout) {
+                            float a[4] = {v[i], v[i + 1], v[i + 2], v[i + 3]};
+                            if (kAdd) {
+                                const float4 o = *reinterpret_cast<const float4*>(yp + cb + i);
+                                a[0] += o.x; a[1] += o.y; a[2] += o.z; a[3] += o.w;
+                            }
+                            if (!kRaw) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    a[j] = a[j] * p.scale + bias_s[cb + i + j];
+                                    a[j] = fmaxf(a[j], a[j] * slope) * inv;
+                                }
+                            }
+                            *reinterpret_cast<float4*>(yp + cb + i) = make_float4(a[0], a[1], a[2], a[3]);
                         }
-                        yp[cb + i] = a;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float a = v[i];
+                        if (cb + i < p.cout) {
+                            if (kAdd) a += yp[cb + i];
+                            if (!kRaw) {
+                                a = a * p.scale + bias_s[cb + i];
+                                a = fmaxf(a, a * slope) * inv;
+                            }
+                            yp[cb + i] = a;
+                        }
                     }
                 }
             }
@@ -696,7 +729,7 @@ int conv_tc_launch_ex(const lf_conv_desc* d, const float* x, const float* w, con
     const size_t part = (size_t)pl.w_bytes / 2;
     if (d->precision == 2) return conv_tc_launch_pass(d, pl, x, wbase, bias, y, rnorm, pro, 0, tc::PASS_ONLY, 0, st);
     static const bool no_dual = getenv("LFB200_TC_NO_DUAL") != nullptr;
-    if (!no_dual && pro == nullptr && (d->cout & 3) == 0 && pl.cout_pad <= 32) {
+    if (!no_dual && pro == nullptr && (d->cout & 3) == 0 && pl.cout_pad <= 64) {
         // bf16x3 in TWO passes: x_hi * [W_hi | W_lo] (one N = 2*Cout MMA per tap: the A tile is fetched from shared
         // memory once for both products), then x_lo * W_hi accumulated in the epilogue
         tc::Plan pd;

@@ -271,8 +271,8 @@ def _tc_pack(wf, key):
 
 
 def _tc_passes(cout):
-    """kernel launches of one bf16x3 convolution: 2 when the dual-weight pass applies (Cout % 4 == 0, <= 32), else 3."""
-    return 2 if (cout % 4 == 0 and cout <= 32) else 3
+    """kernel launches of one bf16x3 convolution: 2 when the dual-weight pass applies (Cout % 4 == 0, <= 64), else 3."""
+    return 2 if (cout % 4 == 0 and cout <= 64) else 3
 
 
 def _tc_ok(desc):
