@@ -184,6 +184,27 @@ int lf_pose_loss_bwd(const lf_loss_desc* desc, const float* depth_logits, const 
                      float* grad_depth_logits, float* grad_mask_logits, float* grad_viewport /* [N][4] */,
                      float* grad_tz /* [N] */, void* stream);
 
+/* ---- IBR colour branch (forward only: the pose loop does not differentiate it) ---------------
+ * IBR camera block, LF_IBR_CAM_STRIDE floats per camera:
+ *   [0,12) cam_to_obj rows 0-2   [12,24) obj_to_cam rows 0-2   [24,36) obj_to_image = K * obj_to_cam (3x4)
+ *   [36,40) viewport x0, y0, width, height   [40,44) u0, v0, fu, fv   [44] znear - 0.01   [45] zfar + 0.01
+ * lf_ibr_reproject_fwd replaces latentfusion/ibr.py:11-93 (depth_to_warp_field + reproject_views: two batched
+ * matmuls, the [Vo*Vi,H,W,2] grid, the transformed-depth image and two F.grid_sample calls, bilinear / zeros /
+ * align_corners=False).  Images are planar (channel-first) like the reference's. */
+#define LF_IBR_CAM_STRIDE 48
+int lf_ibr_reproject_fwd(const float* image_in /* [Vi][C][H][W] */, const float* depth_in /* [Vi][H][W], used as given */,
+                         const float* depth_out /* [Vo][H][W], normalised */, const float* cam_out /* [Vo][48] */,
+                         const float* cam_in /* [Vi][48] */, float* image_reproj /* [Vo][Vi][C][H][W] */,
+                         float* depth_reproj /* [Vo][Vi][H][W] */, int vo, int vi, int c, int h, int w, void* stream);
+/* ibr.py:223-224, :231-234: out[b][c][p] = sum_i wts[b][i][per_pixel ? p : 0] * img[b][i][c][p] */
+int lf_ibr_blend_fwd(const float* img /* [B][Vi][C][HW] */, const float* wts /* [B][Vi] or [B][Vi][HW] */,
+                     float* out /* [B][C][HW] */, int b, int vi, int c, int hw, int per_pixel, void* stream);
+/* ibr.py:237-249 warp_blend_logits: logits [B][3*Vi][H][W] = (blend | flow x | flow y); C <= 8 */
+int lf_ibr_warp_blend_fwd(const float* logits, const float* image_reproj /* [B][Vi][C][H][W] */, float flow_size,
+                          float* image /* [B][C][H][W] */, float* weights /* [B][Vi][H][W] */,
+                          float* flow_dx /* [B][Vi][H][W] */, float* flow_dy /* [B][Vi][H][W] */,
+                          int b, int vi, int c, int h, int w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -262,6 +262,16 @@ class Camera(nn.Module):
         return torch.cat((m, vp, k, self.znear.unsqueeze(1), self.zfar.unsqueeze(1), cube, tail), dim=1)
 
     # ---- image <-> viewport crops (2-D; observation pre-processing and the loss head)
+    def ibr_block(self, eps=0.01):
+        """[n, 48] constant block of the IBR kernels (layout in include/lfb200.h): cam_to_obj, obj_to_cam,
+        obj_to_image (3x4 each), viewport origin/size, principal point/focal, depth normalisation bounds."""
+        n, dev = self.length, self.device
+        vp = torch.stack((self.viewport[:, 0], self.viewport[:, 1], self.viewport_width, self.viewport_height), dim=1)
+        k = torch.stack((self.u0, self.v0, self.fu, self.fv), dim=1)
+        zb = torch.stack((self.znear - eps, self.zfar + eps), dim=1)
+        return torch.cat((self.cam_to_obj[:, :3, :].reshape(n, 12), self.obj_to_cam[:, :3, :].reshape(n, 12),
+                          self.obj_to_image.reshape(n, 12), vp, k, zb, torch.zeros(n, 2, device=dev)), dim=1).float()
+
     def _full_viewport(self):
         z = torch.zeros(self.length, 1, device=self.device)
         return torch.cat((z, z, z + float(self.width), z + float(self.height)), dim=1)

@@ -660,3 +660,75 @@ def plateau_step_(rank_loss, lr, best, num_bad, threshold, patience, factor):
     _call('lf_plateau_step', L.lib().lf_plateau_step,
           (_p(rank_loss.contiguous()), _p(lr), _p(best), _p(num_bad), rank_loss.shape[0], float(threshold),
            float(patience), float(factor), _stream()))
+
+
+# ------------------------------------------------------------------------------------------------
+# IBR colour branch (forward only)
+# ------------------------------------------------------------------------------------------------
+IBR_CAM_STRIDE = 48
+
+
+def _no_grad_path(name, *tensors):
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise NotImplementedError(f"{name}: the IBR colour branch is forward-only in lfb200 (it is not on the pose "
+                                  f"loop's gradient path); call it under torch.no_grad() or detach its inputs")
+
+
+def ibr_reproject(image_in, depth_in, depth_out, cam_in_block, cam_out_block):
+    """latentfusion/ibr.py:55-93 for one object.  image_in [Vi,C,H,W], depth_in [Vi,1,H,W], depth_out [Vo,1,H,W],
+    camera blocks from Camera.ibr_block() -> (image_reproj [Vo,Vi,C,H,W], depth_reproj [Vo,Vi,1,H,W])."""
+    _need_cuda(image_in, depth_in, depth_out, cam_in_block, cam_out_block)
+    _no_grad_path('ibr_reproject', image_in, depth_in, depth_out, cam_in_block, cam_out_block)
+    vi, c, h, w = image_in.shape
+    vo = depth_out.shape[0]
+    if depth_in.shape[0] != vi or cam_in_block.shape != (vi, IBR_CAM_STRIDE) or cam_out_block.shape != (vo, IBR_CAM_STRIDE):
+        raise ValueError("ibr_reproject: view counts of images, depths and cameras do not match")
+    if tuple(depth_in.shape[-2:]) != (h, w) or tuple(depth_out.shape[-2:]) != (h, w):
+        raise ValueError("ibr_reproject: image and depth sizes must match")
+    img = image_in.detach().float().contiguous()
+    din = depth_in.detach().float().contiguous()
+    dout = depth_out.detach().float().contiguous()
+    ci, co = cam_in_block.detach().float().contiguous(), cam_out_block.detach().float().contiguous()
+    image_reproj = torch.empty(vo, vi, c, h, w, device=img.device)
+    depth_reproj = torch.empty(vo, vi, 1, h, w, device=img.device)
+    _call('lf_ibr_reproject_fwd', L.lib().lf_ibr_reproject_fwd,
+          (_p(img), _p(din), _p(dout), _p(co), _p(ci), _p(image_reproj), _p(depth_reproj), vo, vi, c, h, w, _stream()),
+          nbytes=4 * (image_reproj.numel() + depth_reproj.numel() + img.numel() + din.numel() + dout.numel()))
+    return image_reproj, depth_reproj
+
+
+def ibr_blend(image_reproj, weights):
+    """sum over views of weights * image_reproj.  image_reproj [B,Vi,C,H,W]; weights [B,Vi] (per view) or
+    [B,Vi,H,W] (per pixel).  latentfusion/ibr.py:223-224, :231-234."""
+    _need_cuda(image_reproj, weights)
+    _no_grad_path('ibr_blend', image_reproj, weights)
+    b, vi, c, h, w = image_reproj.shape
+    per_pixel = weights.dim() == 4
+    if tuple(weights.shape[:2]) != (b, vi) or (per_pixel and tuple(weights.shape[2:]) != (h, w)) or weights.dim() not in (2, 4):
+        raise ValueError("ibr_blend: weights must be [B,Vi] or [B,Vi,H,W]")
+    img = image_reproj.detach().float().contiguous()
+    wts = weights.detach().float().contiguous()
+    out = torch.empty(b, c, h, w, device=img.device)
+    _call('lf_ibr_blend_fwd', L.lib().lf_ibr_blend_fwd, (_p(img), _p(wts), _p(out), b, vi, c, h * w, int(per_pixel), _stream()),
+          nbytes=4 * (img.numel() + out.numel()))
+    return out
+
+
+def ibr_warp_blend(logits, image_reproj, flow_size):
+    """latentfusion/ibr.py:237-249 -> (image [B,C,H,W], blend_weights [B,Vi,1,H,W], flow_dx, flow_dy [B,Vi,H,W])."""
+    _need_cuda(logits, image_reproj)
+    _no_grad_path('ibr_warp_blend', logits, image_reproj)
+    b, vi, c, h, w = image_reproj.shape
+    if tuple(logits.shape) != (b, 3 * vi, h, w):
+        raise ValueError(f"ibr_warp_blend: logits must be [B, 3*Vi, H, W] = {(b, 3 * vi, h, w)}, got {tuple(logits.shape)}")
+    if c > 8:
+        raise ValueError("ibr_warp_blend: at most 8 colour channels")
+    lg = logits.detach().float().contiguous()
+    img = image_reproj.detach().float().contiguous()
+    image = torch.empty(b, c, h, w, device=img.device)
+    wts = torch.empty(b, vi, h, w, device=img.device)
+    dx, dy = torch.empty_like(wts), torch.empty_like(wts)
+    _call('lf_ibr_warp_blend_fwd', L.lib().lf_ibr_warp_blend_fwd,
+          (_p(lg), _p(img), float(flow_size), _p(image), _p(wts), _p(dx), _p(dy), b, vi, c, h, w, _stream()),
+          nbytes=4 * (lg.numel() + img.numel() + image.numel() + 3 * wts.numel()))
+    return image, wts.unsqueeze(2), dx, dy

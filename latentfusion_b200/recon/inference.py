@@ -1,12 +1,15 @@
 """LatentFusionModel façade.  API mirror of reference ``latentfusion/recon/inference.py``
 (from_checkpoint :17-29, build_latent_object :73-84, compute_latent_code :86-99, render_full :101-120,
-render_latent_object :122-128).  The IBR colour branch (:130-217) is outside this path."""
+render_latent_object :122-128, render_ibr_basic :130-149, render_ibr :151-192, _render_reprojections :194-217).
+The IBR colour branch runs on the forward-only kernels of ``latentfusion_b200/ibr.py``."""
 from pathlib import Path
 
 import torch
 
 from . import models
+from .. import ibr
 from ..observation import Observation
+from ..three.batchview import b2bv, bv2b
 
 
 class LatentFusionModel(object):
@@ -78,11 +81,12 @@ class LatentFusionModel(object):
         return feats
 
     def render_full(self, z_obj, camera, input_obs=None, p=0.5):
-        if input_obs is not None:
-            raise NotImplementedError("image-based colour rendering is outside the reconstruct->render path")
         # (argument order kept from the reference: the zoom box depends only on dist*size)
         camera_zoom = camera.zoom(None, self.camera_dist, self.input_size).to(self.device)
-        pred, _ = self.render_latent_object(z_obj, camera_zoom, apply_mask=True, return_latent=False)
+        if input_obs is None:
+            pred, _ = self.render_latent_object(z_obj, camera_zoom, apply_mask=True, return_latent=False)
+        else:
+            pred, _ = self.render_ibr_basic(z_obj, input_obs, camera_zoom, apply_mask=True, return_latent=False, p=p)
         mask = pred['mask']
         depth = camera_zoom.denormalize_depth(pred['depth']) * mask
         out = {'depth': camera_zoom.uncrop(depth)[0], 'mask': camera_zoom.uncrop(mask)[0]}
@@ -95,3 +99,44 @@ class LatentFusionModel(object):
         if return_latent:
             z = z.squeeze(0)       # one object
         return y, z
+
+    # ---- image-based colour rendering (reference inference.py:130-217); forward only
+    def render_ibr_basic(self, z_obj, input_obs, camera_out, return_latent=True, apply_mask=True, p=0.5):
+        input_obs = self.preprocess_observation(input_obs)
+        with torch.no_grad():
+            y_ibr, z_ibr = ibr.render_latent_ibr2(
+                self.photographer, z_obj, input_obs.camera.clone().to(self.device), camera_out.clone().to(self.device),
+                b2bv(input_obs.color, batch_size=1).to(self.device), p=p, weight_type='cam_dist',
+                return_latent=return_latent, apply_mask=apply_mask)
+        if return_latent:
+            z_ibr = z_ibr.squeeze(0)
+        return {k: v.squeeze(0) for k, v in y_ibr.items()}, z_ibr
+
+    def render_ibr(self, z_obj, input_obs, camera_out, return_latent=True):
+        if self.generator is None:
+            raise ValueError("render_ibr needs the IBR generator network (a checkpoint with a 'generator' entry)")
+        input_obs = self.preprocess_observation(input_obs)
+        with torch.no_grad():
+            (y_out, z_out, image_reproj, depth_reproj, _, depth_ibr_out, _, cam_dist_t) = self._render_reprojections(
+                z_obj, input_obs.color.to(self.device), input_obs.camera.to(self.device), camera_out.to(self.device))
+            if return_latent:
+                z_out = z_out.squeeze(0)
+            cam_sims = 1.0 - cam_dist_t * 2
+            x = torch.cat((image_reproj, depth_reproj,
+                           cam_sims[:, :, None, None, None].expand(-1, -1, -1, *image_reproj.shape[-2:])), dim=2)
+            x = x.view(-1, x.shape[1] * x.shape[2], x.shape[3], x.shape[4])      # views -> channels
+            x = torch.cat((depth_ibr_out, x), dim=1)
+            color_ibr, _, _, _ = ibr.warp_blend_logits(self.generator(x), image_reproj, 5)
+        y_out['color'] = color_ibr
+        return {k: v.squeeze(0) for k, v in y_out.items()}, z_out
+
+    def _render_reprojections(self, z_obj, color_in, camera_in, camera_out, return_latent=True):
+        y_in, _, _ = self.photographer.decode(z_obj, camera_in)
+        y_out, z_out, _ = self.photographer.decode(z_obj, camera_out, return_latent=return_latent)
+        mask_out, depth_out = y_out['mask'], y_out['depth']
+        image_reproj, depth_reproj, cam_dist_r, cam_dist_t = ibr.reproject_views_batch(
+            color_in.unsqueeze(0), y_in['depth'], y_out['depth'], camera_in, camera_out)
+        image_reproj = image_reproj * mask_out.unsqueeze(2)
+        depth_reproj = (depth_reproj + 1.0) * mask_out.unsqueeze(2) - 1.0
+        return (y_out, z_out, bv2b(image_reproj), bv2b(depth_reproj), bv2b(mask_out), bv2b(depth_out),
+                bv2b(cam_dist_r), bv2b(cam_dist_t))

@@ -415,3 +415,148 @@ def refine_iteration(sd, arch, z_obj, cam, target_depth, target_mask, weights):
     losses = pose_loss(target_depth, target_mask, z_depth, y['mask_logits'], cam)
     total = sum(weights.get(k, 0.0) * v for k, v in losses.items())
     return total, losses, y, latent
+
+
+# --------------------------------------------------------------------------------------
+# IBR colour branch                                     latentfusion/ibr.py
+# --------------------------------------------------------------------------------------
+
+
+def _cam_position(cam):
+    """geometry.py:219-224: C = -R^T t."""
+    R = quat_to_rot(qexp3(cam.log_quaternion))
+    return -(R.transpose(1, 2) @ cam.translation[:, :, None]).squeeze(-1)
+
+
+def _pixel_uv(cam, h, w):
+    """geometry.py:495-513 (pixel_coords_uv): viewport-spanning pixel grid, endpoints inclusive."""
+    n = len(cam)
+    tv, tu = torch.meshgrid(torch.linspace(0.0, 1.0, h), torch.linspace(0.0, 1.0, w), indexing='ij')
+    u = tu[None] * cam.vp_w().view(n, 1, 1) + cam.viewport[:, 0].view(n, 1, 1)
+    v = tv[None] * cam.vp_h().view(n, 1, 1) + cam.viewport[:, 1].view(n, 1, 1)
+    return u, v
+
+
+def _depth_camera_coords(cam, depth):
+    """geometry.py:533-545: back-project a depth map [n,1,H,W] to camera coordinates."""
+    n = len(cam)
+    u, v = _pixel_uv(cam, depth.shape[-2], depth.shape[-1])
+    z = depth.reshape(u.shape)
+    K = cam.intrinsic
+    x = (u - K[:, 0, 2].view(n, 1, 1)) / K[:, 0, 0].view(n, 1, 1) * z
+    y = (v - K[:, 1, 2].view(n, 1, 1)) / K[:, 1, 1].view(n, 1, 1) * z
+    return x, y, z
+
+
+def _apply(transform, pts):
+    """three/core.py:40-55: homogenise, multiply, de-homogenise (divide by the LAST output row)."""
+    ones = torch.ones_like(pts[..., :1])
+    out = torch.cat((pts, ones), dim=-1) @ transform.transpose(1, 2)
+    return out[..., :-1] / out[..., -1:]
+
+
+def _normalize_depth(cam, depth, eps=0.01):
+    """geometry.py:560-563."""
+    zn = (cam.znear() - eps).view(-1, 1, 1, 1)
+    zf = (cam.zfar() + eps).view(-1, 1, 1, 1)
+    return ((depth - zn) / (zf - zn)).clamp(0, 1) * 2.0 - 1.0
+
+
+def _repeat_interleave(cam, k):
+    return Cam(cam.intrinsic.repeat_interleave(k, 0), cam.log_quaternion.repeat_interleave(k, 0),
+               cam.translation.repeat_interleave(k, 0), cam.viewport.repeat_interleave(k, 0),
+               cam.z_span, cam.width, cam.height)
+
+
+def ibr_warp_field(cam_in, cam_out, depth_out):
+    """ibr.py:11-52 (depth_to_warp_field) -> grid [V_o, V_i, H, W, 2]."""
+    vo, vi = len(cam_out), len(cam_in)
+    h, w = depth_out.shape[-2:]
+    x, y, z = _depth_camera_coords(cam_out, cam_out.denormalize_depth(depth_out))
+    cam_pts = torch.stack((x, y, z), dim=-1).view(vo, -1, 3)
+    obj = _apply(cam_out.cam_to_obj(), cam_pts)                                     # [vo, HW, 3]
+    obj = obj[:, None].expand(-1, vi, -1, -1).reshape(vo * vi, -1, 3)
+    o2i = (cam_in.intrinsic @ cam_in.obj_to_cam())[None].expand(vo, -1, -1, -1).reshape(vo * vi, 3, 4)
+    pix = _apply(o2i, obj)                                                          # [vo*vi, HW, 2]
+    vp = cam_in.viewport.repeat(vo, 1)
+    gw, gh = vp[:, 2] - vp[:, 0], vp[:, 3] - vp[:, 1]
+    grid = torch.stack((((pix[..., 0] - vp[:, 0, None]) / gw[:, None]) * 2 - 1,
+                        ((pix[..., 1] - vp[:, 1, None]) / gh[:, None]) * 2 - 1), dim=-1)
+    return grid.view(vo, vi, h, w, 2)
+
+
+def ibr_reproject_views(image_in, depth_in, depth_out, cam_in, cam_out):
+    """ibr.py:55-93.  image_in [V_i,C,H,W], depth_in [V_i,1,H,W] (used as given — the reference passes the
+    NORMALISED depth here without denormalising it, kept), depth_out [V_o,1,H,W] ->
+    (image_reproj [V_o,V_i,C,H,W], depth_reproj [V_o,V_i,1,H,W])."""
+    vo, vi = len(cam_out), len(cam_in)
+    grid = ibr_warp_field(cam_in, cam_out, depth_out).reshape(vo * vi, *depth_out.shape[-2:], 2)
+    img = image_in[None].expand(vo, -1, -1, -1, -1).reshape(vo * vi, *image_in.shape[1:])
+    x, y, z = _depth_camera_coords(cam_in, depth_in)
+    obj_in = _apply(cam_in.cam_to_obj(), torch.stack((x, y, z), dim=-1).view(vi, -1, 3))        # [vi, HW, 3]
+    obj_in = obj_in[None].expand(vo, -1, -1, -1).reshape(vo * vi, -1, 3)
+    cam_o = _repeat_interleave(cam_out, vi)
+    z_tf = _apply(cam_o.obj_to_cam(), obj_in)[..., 2].view(vo * vi, 1, *depth_in.shape[-2:])
+    d_tf = _normalize_depth(cam_o, z_tf)
+    image_reproj = F.grid_sample(img, grid, mode='bilinear', align_corners=False)
+    depth_reproj = F.grid_sample(d_tf, grid, mode='bilinear', align_corners=False)
+    return (image_reproj.view(vo, vi, *image_reproj.shape[1:]), depth_reproj.view(vo, vi, *depth_reproj.shape[1:]))
+
+
+def outer_cosine_distance(x1, x2, eps=1e-8):
+    """distances.py:27-32."""
+    w1, w2 = x1.norm(dim=1, keepdim=True), x2.norm(dim=1, keepdim=True)
+    return 1.0 - (x1 @ x2.t()) / (w1 @ w2.t()).clamp(min=eps)
+
+
+def quat_angular_distance(q1, q2, eps=1e-7):
+    """three/quaternion.py:372-377."""
+    q1, q2 = F.normalize(q1, dim=-1, eps=1e-12), F.normalize(q2, dim=-1, eps=1e-12)
+    return 2 * torch.acos(torch.clamp((q1 @ q2.t()).abs(), min=-1.0 + eps, max=1.0 - eps))
+
+
+def ibr_view_weights(cam_in, cam_out, weight_type, p=0.5, eps=1e-2, depth_reproj=None, depth_out=None):
+    """ibr.py:196-222: softmax-normalised blending weights over the input views."""
+    if weight_type == 'cam_dist':
+        d = outer_cosine_distance(_cam_position(cam_out), _cam_position(cam_in), eps=eps) / 2.0
+    elif weight_type == 'cam_angle':
+        d = quat_angular_distance(qexp3(cam_out.log_quaternion), qexp3(cam_in.log_quaternion)) / math.pi
+    elif weight_type == 'cam_hybrid':
+        dt = outer_cosine_distance(_cam_position(cam_out), _cam_position(cam_in)) / 2.0
+        dr = (quat_angular_distance(qexp3(cam_out.log_quaternion), qexp3(cam_in.log_quaternion)) / (math.pi / 8)).clamp(0.0, 1.0)
+        d = 1.0 - (1.0 - dt) * (1.0 - dr)
+    elif weight_type == 'depth':
+        diff = (depth_reproj - depth_out.unsqueeze(1).expand_as(depth_reproj)).abs()
+        return torch.softmax(1.0 / ((diff / diff.max()) ** p + eps), dim=1).squeeze(2)
+    else:
+        raise ValueError(f'Unknown weight_type {weight_type}')
+    return torch.softmax(1.0 / (d.unsqueeze(-1).unsqueeze(-1) ** p).clamp(min=eps), dim=1)
+
+
+def ibr_render(cam_in, cam_out, image_in, depth_in, depth_out, p=0.5, weight_type='cam_dist', eps=1e-2):
+    """ibr.py:181-228 for one object: (image_ibr [V_o,C,H,W], image_reproj [V_o,V_i,C,H,W])."""
+    image_reproj, depth_reproj = ibr_reproject_views(image_in, depth_in, depth_out, cam_in, cam_out)
+    wts = ibr_view_weights(cam_in, cam_out, weight_type, p, eps, depth_reproj, depth_out)
+    return (wts.unsqueeze(2) * image_reproj).sum(dim=1), image_reproj
+
+
+def ibr_blend_logits(logits, image_reproj):
+    """ibr.py:231-234."""
+    wts = torch.softmax(logits, dim=1).unsqueeze(2)
+    return (wts * image_reproj).sum(dim=1), wts
+
+
+def ibr_warp_blend_logits(logits, image_reproj, flow_size):
+    """ibr.py:237-249: per-view softmax weights + a bounded flow refinement of each reprojection."""
+    b, vi = image_reproj.shape[:2]
+    h, w = image_reproj.shape[-2:]
+    bl, fxl, fyl = torch.split(logits, vi, dim=1)
+    wts = torch.softmax(bl, dim=1).unsqueeze(2)
+    dx = flow_size / w * torch.tanh(fxl)
+    dy = flow_size / h * torch.tanh(fyl)
+    gy, gx = torch.meshgrid(torch.linspace(-1, 1, h), torch.linspace(-1, 1, w), indexing='ij')
+    grid = torch.stack((gx[None, None].expand_as(dx) + dx, gy[None, None].expand_as(dy) + dy), dim=-1).clamp(-1, 1)
+    warped = F.grid_sample(image_reproj.reshape(b * vi, *image_reproj.shape[2:]), grid.reshape(b * vi, h, w, 2),
+                           mode='bilinear', align_corners=False)
+    warped = warped.view(b, vi, *warped.shape[1:])
+    return (wts * warped).sum(dim=1), wts, dx, dy

@@ -56,7 +56,10 @@ def _stub_module(name, **attrs):
 def install():
     """Install the stubs + shim and put the reference on sys.path. Idempotent."""
     import importlib.util
-    if importlib.util.find_spec('structlog') is None and 'structlog' not in sys.modules:
+    if getattr(install, '_done', False):
+        return
+    install._done = True
+    if 'structlog' not in sys.modules and importlib.util.find_spec('structlog') is None:
         sl = _stub_module('structlog', get_logger=lambda *a, **k: _Noop(),
                           configure=lambda **k: None)
         for sub in ('stdlib', 'processors', 'dev'):
