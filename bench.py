@@ -353,12 +353,13 @@ def run_ours(args):
         if conv_like:
             peak = peaks['bf16_tflops_sustained']
             ach = d['flops'] / d['calls'] / (d['ms_avg'] * 1e-3) / 1e12
-            tr = traffic.get('conv_tc_kernel') if (args.precision and 'conv3d' in name) else None
+            tr = (traffic.get('conv_tc_bf16x3_two_passes' if passes == 2 else 'conv_tc_kernel')
+                  if (args.precision and 'conv3d' in name) else None)
             roof = {"kernel": name, "bound": "tensor", "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s",
-                    "frac": round(ach / peak, 4), "traffic": None if tr is None else tr * passes,
+                    "frac": round(ach / peak, 4), "traffic": tr,
                     "peak_source": peaks['source'] + ' bf16 sustained',
                     "note": ("algorithmic flops 2*27*Cin*Cout*positions counted ONCE; the bf16x3 mode issues 3 tensor-core "
-                             "products per tap (in 2 kernel passes), so the MMA rate is 3x 'achieved'; traffic = 2 passes") if passes == 2 else
+                             "products per tap (in 2 kernel passes), so the MMA rate is 3x 'achieved'; traffic = both passes (the second re-reads x and read-modify-writes y)") if passes == 2 else
                             "algorithmic flops 2*27*Cin*Cout*positions"}
         else:
             peak = peaks['hbm_gbs']

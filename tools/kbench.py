@@ -94,6 +94,28 @@ def main():
         med, best = timeit(lambda: ops.eq_conv(x2, w2, b, act=True, norm=True, kind=ops.KIND_COLLAPSE, depth=S,
                                                precision=0), a.iters, flush)
         out['collapse_fwd'] = dict(ms=med, GBs=4 * x2.numel() / med / 1e6)
+    if a.only in ('all', 'ibr'):
+        # IBR colour branch at the configs[1] extents: 16 reference views -> N output views at (2S)^2
+        import torch.nn.functional as F
+        from latentfusion_b200 import ibr
+        P, VI, VO = 2 * S, 16, N
+        cin = ph.synthetic_cameras(VI, S, seed=41, perturb=False)[0].to(dev)
+        cout = ph.synthetic_cameras(VO, S, seed=42)[0].to(dev)
+        image = torch.rand(VI, 3, P, P, device=dev) * 2 - 1
+        din = (torch.rand(VI, 1, P, P, device=dev) - 0.5)
+        dout = (torch.rand(VO, 1, P, P, device=dev) - 0.5)
+        bi, bo = cin.ibr_block(), cout.ibr_block()
+        nbytes = 4 * (VO * VI * 4 * P * P + VI * 4 * P * P + VO * P * P)
+        with torch.no_grad():
+            med, best = timeit(lambda: ops.ibr_reproject(image, din, dout, bi, bo), a.iters, flush)
+
+            def torch_ops():          # the reference's formulation on the device: warp field + two grid_sample calls
+                grid = ibr.depth_to_warp_field(cin, cout, dout).reshape(VO * VI, P, P, 2)
+                return F.grid_sample(image[None].expand(VO, -1, -1, -1, -1).reshape(VO * VI, 3, P, P), grid,
+                                     mode='bilinear', align_corners=False)
+            med_t, _ = timeit(torch_ops, max(3, a.iters // 4), flush)
+        out['ibr_reproject'] = dict(ms=med, best_ms=best, GBs=nbytes / med / 1e6, frac=nbytes / med / 1e6 / peaks['hbm_gbs'],
+                                    torch_ops_colour_only_ms=med_t)
     if os.environ.get('LFB200_TC_DEBUG') and int(os.environ['LFB200_TC_DEBUG']) & 8:
         import ctypes, numpy as np
         from latentfusion_b200 import _lib as L
