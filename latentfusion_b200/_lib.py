@@ -45,6 +45,7 @@ _SIGNATURES = {
     'lf_conv_tc_weight_bytes': (c_i64, [c_int, c_int, c_int]),
     'lf_conv_tc_pack_weights': (c_int, [c_f32p, c_vp, c_int, c_int, c_int, c_vp]),
     'lf_conv_tc_supported': (c_int, [ctypes.POINTER(ConvDesc)]),
+    'lf_conv_tc_passes': (c_int, [ctypes.POINTER(ConvDesc)]),
     'lf_conv_bwd_data_fused': (c_int, [ctypes.POINTER(ConvDesc), c_f32p, c_f32p, c_f32p, c_int, c_float, c_int, c_f32p, c_f32p, c_vp]),
     'lf_actnorm_bwd': (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_int, c_i64, c_int, c_int, c_float, c_int, c_vp]),
     'lf_conv_bwd_weight': (c_int, [ctypes.POINTER(ConvDesc), c_f32p, c_f32p, c_f32p, c_f32p, c_vp]),

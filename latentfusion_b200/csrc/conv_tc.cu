@@ -787,6 +787,19 @@ extern "C" int lf_debug_tc_timeline(long long* host_out /* [3][64][2] */) {
     return (int)cudaMemcpyFromSymbol(host_out, tc::g_dbg, sizeof(long long) * 3 * 64 * 2);
 }
 
+// kernel launches lf_conv_fwd makes for this descriptor on the tcgen05 path: 1 (bf16), 2 (bf16x3 with the dual-weight
+// first pass) or 3 (bf16x3 as three single-product passes); 0 if the shape is not covered
+extern "C" int lf_conv_tc_passes(const lf_conv_desc* desc) {
+    tc::Plan pl;
+    if (desc == nullptr || desc->precision == 0 || !tc::make_plan(desc, pl)) return 0;
+    if (desc->precision == 2) return 1;
+    if (getenv("LFB200_TC_NO_DUAL") == nullptr && (desc->cout & 3) == 0 && pl.cout_pad <= 64) {
+        tc::Plan pd;
+        if (tc::make_plan(desc, pd, true)) return 2;
+    }
+    return 3;
+}
+
 extern "C" int lf_conv_tc_supported(const lf_conv_desc* desc) {
     if (desc == nullptr) return 0;
     return conv_tc_supported(desc);

@@ -270,9 +270,9 @@ def _tc_pack(wf, key):
     return out
 
 
-def _tc_passes(cout):
-    """kernel launches of one bf16x3 convolution: 2 when the dual-weight pass applies (Cout % 4 == 0, <= 64), else 3."""
-    return 2 if (cout % 4 == 0 and cout <= 64) else 3
+def _tc_passes(desc):
+    """kernel launches the library makes for this convolution on the tcgen05 path (1 bf16, 2|3 bf16x3)."""
+    return max(1, int(L.lib().lf_conv_tc_passes(ctypes.byref(desc))))
 
 
 def _tc_ok(desc):
@@ -349,7 +349,7 @@ class _EqConv(torch.autograd.Function):
             wf_arg = wf
         _call(_conv_name(kind, nd, k, 'fwd'), L.lib().lf_conv_fwd,
               (ctypes.byref(desc), _p(x), _p(wf_arg), _p(bpk), _p(y), _p(rnorm), _stream()),
-              kernels=(2 if (norm and (kind == KIND_EXPAND or gcout > 64)) else 1) if desc.precision != 1 else _tc_passes(gcout),
+              kernels=(2 if (norm and (kind == KIND_EXPAND or gcout > 64)) else 1) if desc.precision != 1 else _tc_passes(desc),
               nbytes=4 * (x.numel() + y.numel()), flops=2 * positions * taps * gcin * gcout)
         ctx.save_for_backward(x, y, rnorm, wb)
         ctx.wkey = wkey
@@ -410,7 +410,7 @@ class _EqConv(torch.autograd.Function):
                     wb_arg = wb
                 _call(_conv_name(kind, nd, k, 'bwd_data'), lib.lf_conv_fwd,
                       (ctypes.byref(bdesc), _p(du), _p(wb_arg), None, _p(gx), None, _stream()),
-                      kernels=_tc_passes(cin) if bdesc.precision == 1 else 1,
+                      kernels=_tc_passes(bdesc) if bdesc.precision == 1 else 1,
                       nbytes=4 * (du.numel() + gx.numel()), flops=bflops)
         if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
             taps = wb.shape[0]

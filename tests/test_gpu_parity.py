@@ -195,6 +195,35 @@ def test_gradient_estimator_three_iterations_vs_golden(g, dev):
     torch.testing.assert_close(best.translation, g['est.best_cam.translation'], atol=2e-4, rtol=1e-3)
 
 
+def test_cross_entropy_estimator_runs_on_the_cuda_path(g, dev):
+    """Coarse pose search (reference pose/estimation.py:300-470, configs/cross_entropy_latent.toml scaled down):
+    GMM proposals on the host, every render + the target's latent code on the lfb200 kernels, forward only."""
+    import numpy as np
+    from latentfusion_b200 import ops
+    from latentfusion_b200.pose import estimation, utils as pu
+    from latentfusion_b200.observation import Observation
+    from latentfusion_b200.recon.inference import LatentFusionModel
+    sculptor, fuser, photographer = ph.build_product_models(g, dev)
+    model = LatentFusionModel(sculptor, fuser, photographer, g.meta['camera_dist'], dev)
+    cfg = {'type': 'cross_entropy',
+           'args': dict(num_samples=8, num_iters=2, ranking_size=4, num_elites=4, num_gmm_components=2,
+                        learning_rate=0.3, sample_flipped=True, init_hemisphere=False, init_upright=False),
+           'loss_weights': dict(depth=0.0, ov_depth=0.0, iou=0.0, mask=0.0, latent=1.0)}
+    est = estimation.load_from_config(cfg, model, return_camera_history=True)
+    gt = ph.product_camera(g.cam('ref_cam_full'), 'cpu')[0:1]
+    torch.manual_seed(5)
+    np.random.seed(5)
+    target = Observation(torch.rand(1, 3, 480, 640), g['target.depth'], g['target.mask'], gt)
+    cams = pu.sample_cameras_with_estimate(n=16, camera_est=gt)
+    ops.KernelTrace.reset(False)
+    best, history = est.estimate(g['z_obj_gru'].to(dev), target, cameras=cams)
+    assert 1 <= len(best) <= 4
+    assert ops.KernelTrace.launches > 100            # the renders went through the C ABI
+    for losses, ranked in history:
+        assert torch.isfinite(losses).all()
+        assert torch.isfinite(ranked.translation).all() and torch.isfinite(ranked.log_quaternion).all()
+
+
 def test_config_a_render_vs_oracle(dev):
     """BASELINE config 1 shape (V=4, S=32, C=16, N=2): CUDA path vs the CPU oracle, fwd + camera grads."""
     from oracle import lf_oracle as O
