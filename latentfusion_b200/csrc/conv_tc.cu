@@ -29,10 +29,12 @@
 namespace lf {
 namespace tc {
 
-constexpr int kProducerWarps = 7;
-constexpr int kMmaWarps = 5;                               // issuer warp m owns M-tiles m, m+4, ...
+constexpr int kMmaWarps = 5;                               // at most; issuer warp m owns M-tiles m, m+nmma, ...
 constexpr int kEpiWarps = 4;                               // one warp per TMEM lane quarter (8 measured slower)
-constexpr int kThreads = 32 * (kProducerWarps + kMmaWarps + kEpiWarps);   // producers | MMA issuers | epilogue
+constexpr int kWarps = 16;
+constexpr int kThreads = 32 * kWarps;                      // producers | MMA issuers | epilogue (last 4 warps)
+// Roles are assigned at run time: nmma = min(NT, 5) issuer warps (one per M-tile), 4 epilogue warps, and every
+// remaining warp (7..11) is a producer — a plan with few tiles gets more loads in flight instead of idle issuers.
 constexpr int kMaxRing = 4;
 constexpr int kMaxTiles = 5;
 
@@ -51,6 +53,7 @@ struct Params {
     float scale; int act; float slope; int norm;
     int a_part;                // 0: hi = bf16(x), 1: lo = bf16(x - hi)
     int pass_mode;
+    int nprod, nmma;           // producer / MMA-issuer warp counts (nprod + nmma + 4 == 16)
     int dual, ncols;           // dual: B = [W_hi | W_lo] (N = 2*cout_pad): one pass yields x_hi*W_hi + x_hi*W_lo; ncols = MMA N
     uint32_t idesc;
     uint32_t slab_bytes, w_bytes;
@@ -326,11 +329,12 @@ conv_tc_kernel(const __grid_constant__ Params p) {
             bias_s[i] = (p.bias != nullptr && i < p.cout) ? p.bias[i] : 0.f;
     }
     if (threadIdx.x == 0) {
-        for (int i = 0; i < p.ring; ++i) { mbar_init(bar_full + 8 * i, kProducerWarps * 32); mbar_init(bar_empty + 8 * i, min(p.NT, kMmaWarps)); }
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, min(p.NT, kMmaWarps)); mbar_init(bar_acce + 8 * i, 32 * kEpiWarps); }
+        for (int i = 0; i < p.ring; ++i) { mbar_init(bar_full + 8 * i, p.nprod * 32); mbar_init(bar_empty + 8 * i, p.nmma); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, p.nmma); mbar_init(bar_acce + 8 * i, 32 * kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == kProducerWarps) {
+    const int NPROD = p.nprod, NMMA = p.nmma;
+    if (warp == NPROD) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
@@ -345,7 +349,7 @@ conv_tc_kernel(const __grid_constant__ Params p) {
     const uint32_t lbo_a = (uint32_t)p.pos_alloc * 16u;
     const int q4 = p.cin_pad / 4;                       // float4 units per position
 
-    if (warp < kProducerWarps) {
+    if (warp < NPROD) {
         // =========================== PRODUCERS: global fp32 -> bf16 UMMA slab ===========================
         uint32_t kcount = 0;                            // planes produced by this CTA so far
         const int tid = threadIdx.x;
@@ -365,12 +369,12 @@ conv_tc_kernel(const __grid_constant__ Params p) {
                     const int units = rows_in * p.P * q4;
                     if (p.pro_y == nullptr) {
                     constexpr int kBatch = 8;           // loads in flight per thread
-                    for (int u0 = tid; u0 < units; u0 += kBatch * kProducerWarps * 32) {
+                    for (int u0 = tid; u0 < units; u0 += kBatch * NPROD * 32) {
                         float4 v[kBatch];
                         int udst[kBatch];               // byte offset inside the slab, -1 = nothing to do
 #pragma unroll
                         for (int j = 0; j < kBatch; ++j) {
-                            const int u = u0 + j * kProducerWarps * 32;
+                            const int u = u0 + j * NPROD * 32;
                             v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                             udst[j] = -1;
                             if (u < units) {
@@ -399,13 +403,13 @@ conv_tc_kernel(const __grid_constant__ Params p) {
                         const float inv_c = 1.f / (float)p.cin;
                         const int units_pad = (units + 31) & ~31;
                         constexpr int kB2 = 4;
-                        for (int u0 = tid; u0 < units_pad; u0 += kB2 * kProducerWarps * 32) {
+                        for (int u0 = tid; u0 < units_pad; u0 += kB2 * NPROD * 32) {
                             float4 g4[kB2], y4[kB2];
                             float rr[kB2];
                             int udst[kB2];
 #pragma unroll
                             for (int j = 0; j < kB2; ++j) {
-                                const int u = u0 + j * kProducerWarps * 32;
+                                const int u = u0 + j * NPROD * 32;
                                 g4[j] = make_float4(0.f, 0.f, 0.f, 0.f); y4[j] = g4[j]; rr[j] = 1.f; udst[j] = -1;
                                 if (u < units) {
                                     const int pos = fast_div(u, p.magic_q4), q = u - pos * q4;
@@ -450,12 +454,12 @@ conv_tc_kernel(const __grid_constant__ Params p) {
                 if (tid == 0) dbg_stamp(p, 0, kcount, 1);
             }
         }
-    } else if (warp < kProducerWarps + kMmaWarps) {
+    } else if (warp < NPROD + NMMA) {
         // =========================== MMA ISSUERS (warp m owns M-tile m) ===========================
         // The whole warp runs this loop in lock-step so every descriptor/address lives in UNIFORM registers
         // (UTCHMMA takes uniform operands; a lane-0-only branch makes the compiler shuttle them through
         // R2UR + an elect waterfall, ~12 instructions per MMA); only the issue itself is elected.
-        const int my_tile = warp - kProducerWarps;
+        const int my_tile = warp - NPROD;
         if (my_tile < p.NT) {
             uint32_t kbase = 0;                         // running plane count at the start of the item
             uint32_t step = 0;                          // running step (accumulator) count
@@ -488,7 +492,7 @@ conv_tc_kernel(const __grid_constant__ Params p) {
                     // Issue loop kept to a handful of instructions per MMA: the descriptor's high word is
                     // constant, the low word is (LBO field | start>>4) and only the start changes, by +1 per
                     // dx, +P per dy, +2*LBO per k-step (all in 16-byte units).
-                    for (int t = my_tile; t < NT; t += kMmaWarps) {
+                    for (int t = my_tile; t < NT; t += NMMA) {
                         const uint32_t d_tmem = tmem_base + (buf * NT + t) * COUT_PAD;
                         uint32_t acc = 0;
                         for (int dz = 0; dz <= 2 * HZ; ++dz) {
@@ -528,7 +532,7 @@ conv_tc_kernel(const __grid_constant__ Params p) {
     } else {
         // =========================== EPILOGUE (4 warps = 128 TMEM lanes) ===========================
         const int wq = warp & 3;                       // TMEM lane quarter this warp may access
-        const int ehalf = (warp - kProducerWarps - kMmaWarps) >> 2;   // which half of the tiles this warp drains
+        const int ehalf = (warp - NPROD - NMMA) >> 2;   // which half of the tiles this warp drains (0 with 4 epilogue warps)
         uint32_t step = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
             int it = item;
@@ -563,7 +567,7 @@ conv_tc_kernel(const __grid_constant__ Params p) {
 
     tc_fence_before();
     __syncthreads();
-    if (warp == kProducerWarps) {
+    if (warp == NPROD) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
@@ -693,6 +697,8 @@ static int conv_tc_launch_pass(const lf_conv_desc* d, const tc::Plan& pl, const 
     p.n = d->n; p.d = d->d; p.h = d->h; p.w = d->w;
     p.cin = d->cin; p.cout = d->cout; p.cin_pad = pl.cin_pad; p.cout_pad = pl.cout_pad;
     p.ncols = pl.cout_pad * (dual ? 2 : 1);
+    p.nmma = pl.NT < tc::kMmaWarps ? pl.NT : tc::kMmaWarps;
+    p.nprod = tc::kWarps - tc::kEpiWarps - p.nmma;
     p.k = d->k; p.hz = (d->ndim == 3) ? d->k / 2 : 0;
     p.R = pl.R; p.NT = pl.NT; p.P = pl.P; p.pos_alloc = pl.pos_alloc; p.ring = pl.ring; p.DC = pl.DC;
     p.nstrips = pl.nstrips; p.ndchunks = pl.ndchunks; p.items = d->n * pl.nstrips * pl.ndchunks;

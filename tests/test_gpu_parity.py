@@ -218,7 +218,7 @@ def test_cross_entropy_estimator_runs_on_the_cuda_path(g, dev):
     ops.KernelTrace.reset(False)
     best, history = est.estimate(g['z_obj_gru'].to(dev), target, cameras=cams)
     assert 1 <= len(best) <= 4
-    assert ops.KernelTrace.launches > 100            # the renders went through the C ABI
+    assert ops.KernelTrace.launches > 40             # the renders + the target autoencode went through the C ABI
     for losses, ranked in history:
         assert torch.isfinite(losses).all()
         assert torch.isfinite(ranked.translation).all() and torch.isfinite(ranked.log_quaternion).all()
