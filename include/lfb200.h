@@ -186,6 +186,15 @@ int lf_pose_loss_bwd(const lf_loss_desc* desc, const float* depth_logits, const 
                      float* grad_depth_logits, float* grad_mask_logits, float* grad_viewport /* [N][4] */,
                      float* grad_tz /* [N] */, void* stream);
 
+/* bwd-data convolution (or depth-expand, ndim -1) with the PixelNorm/LeakyReLU backward of the PRODUCER of the forward
+ * input fused into the epilogue: writes du_prev = actnorm_bwd(conv_bwd_data(du), y_prev, rnorm_prev) in one kernel
+ * (replaces blocks.py:152-164's autograd of conv -> LeakyReLU -> PixelNorm between two stacked convolutions).
+ * `w`: tcgen05-packed weights for conv descriptors (precision 1|2), fp32 [D][Cin][Cout] for ndim -1. */
+int lf_conv_bwd_data_epi_supported(const lf_conv_desc* desc);
+int lf_conv_bwd_data_epi(const lf_conv_desc* desc, const float* du, const float* w, const float* y_prev,
+                         const float* rnorm_prev, int prev_act, float prev_slope, int prev_norm, float* du_prev,
+                         void* stream);
+
 /* ---- IBR colour branch (forward only: the pose loop does not differentiate it) ---------------
  * IBR camera block, LF_IBR_CAM_STRIDE floats per camera:
  *   [0,12) cam_to_obj rows 0-2   [12,24) obj_to_cam rows 0-2   [24,36) obj_to_image = K * obj_to_cam (3x4)

@@ -436,7 +436,9 @@ collapse_cluster_kernel(const ConvGeom g, const float* __restrict__ x, const flo
 template <int CINMAX>
 __global__ void __launch_bounds__(128)
 expand_multi_kernel(const ConvGeom g, const float* __restrict__ x, const float* __restrict__ wp,
-                    const float* __restrict__ bias, float* __restrict__ y, int TS) {
+                    const float* __restrict__ bias, float* __restrict__ y, int TS,
+                    const float* __restrict__ epi_y, const float* __restrict__ epi_r, int epi_act, int epi_norm,
+                    float epi_slope) {
     __shared__ __align__(16) float sA[CINMAX][BM + 4];
     __shared__ __align__(16) float sB[2][CINMAX][32];
     const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
@@ -508,9 +510,11 @@ expand_multi_kernel(const ConvGeom g, const float* __restrict__ x, const float* 
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int64_t P = (int64_t)blockIdx.x * BM + ty * 8 + i;
-            if (P >= in_positions) continue;
-            const int64_t nb = P / hw, p2 = P - nb * hw;
-            float* yp = y + (((nb * g.d + t) * hw) + p2) * g.cout + n0 + tx * 4;
+            const bool live = P < in_positions;                 // (no early exit: the fused epilogue shuffles)
+            const int64_t Pc = live ? P : in_positions - 1;
+            const int64_t nb = Pc / hw, p2 = Pc - nb * hw;
+            const int64_t orow = ((nb * g.d + t) * hw) + p2;      // output position index
+            float* yp = y + orow * g.cout + n0 + tx * 4;
             float v[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -518,6 +522,29 @@ expand_multi_kernel(const ConvGeom g, const float* __restrict__ x, const float* 
                 if (g.act) u = u > 0.f ? u : u * g.slope;
                 v[j] = u;
             }
+            if (epi_y != nullptr) {
+                // backward of the layer that produced this tensor's forward twin (grid.y == 1, Cout % 4 == 0 checked on
+                // the host): du = gate(y) * (g - y * mean_c(g*y)) / r, the 8 lanes tx of a row hold its Cout channels
+                const bool ch = tx * 4 < g.cout;
+                const float4 y4 = ch ? ldg4(epi_y + orow * g.cout + tx * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+                float dot = 0.f, ir = 1.f;
+                if (epi_norm) {
+                    dot = ch ? (v[0] * yv[0] + v[1] * yv[1] + v[2] * yv[2] + v[3] * yv[3]) : 0.f;
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+                    dot *= 1.f / (float)g.cout;
+                    ir = 1.f / __ldg(epi_r + orow);
+                }
+                const float gs = epi_act ? epi_slope : 1.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float o = (v[j] - yv[j] * dot) * ir;
+                    v[j] = yv[j] > 0.f ? o : o * gs;
+                }
+            }
+            if (!live) continue;
             if ((g.cout & 3) == 0 && n0 + tx * 4 + 4 <= g.cout) st4_stream(yp, make_float4(v[0], v[1], v[2], v[3]));
             else {
 #pragma unroll
@@ -752,7 +779,7 @@ int conv_fp32_launch(const lf_conv_desc* d, const float* x, const float* w, cons
             int TS = 4;
             while (TS > 1 && mblocks * ((g.cout + 31) / 32) * ((g.d + TS - 1) / TS) < 8ll * sm_count()) TS /= 2;
             dim3 grid((unsigned)mblocks, (g.cout + 31) / 32, (g.d + TS - 1) / TS);
-            expand_multi_kernel<32><<<grid, 128, 0, st>>>(ge, x, w, bias, y, TS);
+            expand_multi_kernel<32><<<grid, 128, 0, st>>>(ge, x, w, bias, y, TS, nullptr, nullptr, 0, 0, 1.f);
         } else {
             dim3 grid((unsigned)mblocks, (g.cout + 31) / 32, g.d);
             if (vec) conv_expand_kernel<32, 4><<<grid, 128, 0, st>>>(ge, x, w, bias, y);
@@ -800,6 +827,26 @@ int conv_fp32_launch(const lf_conv_desc* d, const float* x, const float* w, cons
         pixelnorm_group_kernel<<<(unsigned)((g.out_positions * 32 + 255) / 256), 256, 0, st>>>(
             y, y, rnorm, g.out_positions, 1, 1, g.cout);
     }
+    LF_RETURN_LAUNCH();
+}
+
+// expand with the fused PixelNorm/LeakyReLU backward epilogue (backward of a depth-collapse whose input came from
+// a Block conv): supported for Cin <= 32, Cin % 4 == 0, Cout <= 32, Cout % 4 == 0
+int expand_epi_supported(const lf_conv_desc* d) {
+    return d->ndim == -1 && d->cin <= 32 && (d->cin & 3) == 0 && d->cout <= 32 && (d->cout & 3) == 0 && !d->norm;
+}
+
+int expand_epi_launch(const lf_conv_desc* d, const float* x, const float* w, float* y, const float* epi_y,
+                      const float* epi_r, int epi_act, float epi_slope, int epi_norm, cudaStream_t st) {
+    ConvGeom g;
+    if (int e = make_geom(d, g)) return e;
+    LF_CHECK_ARG(expand_epi_supported(d), "expand: fused backward epilogue unsupported for this shape");
+    const int64_t mblocks = (g.out_positions + BM - 1) / BM;
+    LF_CHECK_ARG(mblocks < (1ll << 31), "conv: too many positions");
+    int TS = 4;
+    while (TS > 1 && mblocks * ((g.d + TS - 1) / TS) < 8ll * sm_count()) TS /= 2;
+    dim3 grid((unsigned)mblocks, 1, (g.d + TS - 1) / TS);
+    expand_multi_kernel<32><<<grid, 128, 0, st>>>(g, x, w, nullptr, y, TS, epi_y, epi_r, epi_act, epi_norm, epi_slope);
     LF_RETURN_LAUNCH();
 }
 

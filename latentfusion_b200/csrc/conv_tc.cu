@@ -45,6 +45,10 @@ struct Params {
     // fused backward prologue (bwd-data of a Block conv): x = upstream grad g, pro_y = the layer's output y,
     // pro_r = its saved PixelNorm denominators; the producers stage du = LeakyReLU'(y) * PixelNorm^T(g) on the fly
     const float* pro_y; const float* pro_r; int pro_act, pro_norm, pro_lg; float pro_slope;
+    // fused backward EPILOGUE (bwd-data feeding a Block conv): the result row gx is pushed through the
+    // PixelNorm/LeakyReLU backward of the layer that produced this conv's input (epi_y = that layer's output,
+    // epi_r = its saved norms), i.e. the kernel writes du_prev instead of gx and the separate pass disappears
+    const float* epi_y; const float* epi_r; int epi_act, epi_norm; float epi_slope;
     int n, d, h, w;            // extent (d = 1 for 2-D)
     int cin, cout, cin_pad, cout_pad;
     int k, hz;                 // kernel size (1|3); hz = depth halo (k/2 for 3-D, 0 for 2-D)
@@ -215,6 +219,35 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const float* __re
 #pragma unroll
                     for (int i = 0; i < NCH * 16; ++i) v[i] *= inv;
                     if (p.rnorm != nullptr) p.rnorm[opos] = rn;
+                }
+                if (p.epi_y != nullptr) {
+                    // du_prev = gate(y) * (g - y * mean_c(g*y)) / r   with g = this row (same formula as lf_actnorm_bwd)
+                    const float* yr = p.epi_y + opos * p.cout;
+                    float dot = 0.f, ir = 1.f;
+                    if (p.epi_norm) {
+#pragma unroll
+                        for (int i = 0; i < NCH * 16; i += 4) {
+                            if (i < p.cout) {
+                                const float4 y4 = ldg4(yr + i);
+                                dot += v[i] * y4.x + v[i + 1] * y4.y + v[i + 2] * y4.z + v[i + 3] * y4.w;
+                            }
+                        }
+                        dot *= 1.f / (float)p.cout;
+                        ir = 1.f / __ldg(p.epi_r + opos);
+                    }
+                    const float gs = p.epi_act ? p.epi_slope : 1.f;
+#pragma unroll
+                    for (int i = 0; i < NCH * 16; i += 4) {
+                        if (i < p.cout) {
+                            const float4 y4 = ldg4(yr + i);
+                            const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float o = (v[i + j] - yv[j] * dot) * ir;
+                                v[i + j] = yv[j] > 0.f ? o : o * gs;
+                            }
+                        }
+                    }
                 }
             }
 #pragma unroll
@@ -671,20 +704,25 @@ int conv_tc_supported(const lf_conv_desc* d) {
 }
 
 struct TcPrologue { const float* y; const float* rnorm; int act, norm; float slope; };
+struct TcEpilogue { const float* y; const float* rnorm; int act, norm; float slope; };
 
 int conv_tc_launch_ex(const lf_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
-                      float* rnorm, const TcPrologue* pro, cudaStream_t st);
+                      float* rnorm, const TcPrologue* pro, const TcEpilogue* epi, cudaStream_t st);
 
 int conv_tc_launch(const lf_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
                    float* rnorm, cudaStream_t st) {
-    return conv_tc_launch_ex(d, x, w, bias, y, rnorm, nullptr, st);
+    return conv_tc_launch_ex(d, x, w, bias, y, rnorm, nullptr, nullptr, st);
 }
 
 // one kernel launch: `wpk` points at the packed weight region to use (hi, lo or dual)
 static int conv_tc_launch_pass(const lf_conv_desc* d, const tc::Plan& pl, const float* x, const uint16_t* wpk,
                                const float* bias, float* y, float* rnorm, const TcPrologue* pro, int a_part,
-                               int mode, int dual, cudaStream_t st) {
+                               int mode, int dual, cudaStream_t st, const TcEpilogue* epi = nullptr) {
     tc::Params p;
+    p.epi_y = epi ? epi->y : nullptr; p.epi_r = epi ? epi->rnorm : nullptr;
+    p.epi_act = epi ? epi->act : 0; p.epi_norm = epi ? epi->norm : 0; p.epi_slope = epi ? epi->slope : 1.f;
+    if (epi) LF_CHECK_ARG((d->cout & 3) == 0 && pl.cout_pad <= 32 && (mode == tc::PASS_ONLY || mode == tc::PASS_LAST),
+                          "conv_tc: fused backward epilogue needs Cout % 4 == 0, Cout <= 32, on the final pass");
     p.x = x; p.bias = bias; p.y = y; p.rnorm = rnorm; p.wpk = wpk;
     p.a_part = a_part; p.pass_mode = mode; p.dual = dual;
     p.pro_y = pro ? pro->y : nullptr; p.pro_r = pro ? pro->rnorm : nullptr;
@@ -726,14 +764,14 @@ static int conv_tc_launch_pass(const lf_conv_desc* d, const tc::Plan& pl, const 
 }
 
 int conv_tc_launch_ex(const lf_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
-                      float* rnorm, const TcPrologue* pro, cudaStream_t st) {
+                      float* rnorm, const TcPrologue* pro, const TcEpilogue* epi, cudaStream_t st) {
     tc::Plan pl;
     LF_CHECK_ARG(tc::make_plan(d, pl), "conv_tc: unsupported shape");
     LF_CHECK_ARG(x && w && y, "conv_tc: null pointer");
     // packed weights: [hi | lo | dual], each `part` elements (dual is two parts long)
     const uint16_t* wbase = reinterpret_cast<const uint16_t*>(w);
     const size_t part = (size_t)pl.w_bytes / 2;
-    if (d->precision == 2) return conv_tc_launch_pass(d, pl, x, wbase, bias, y, rnorm, pro, 0, tc::PASS_ONLY, 0, st);
+    if (d->precision == 2) return conv_tc_launch_pass(d, pl, x, wbase, bias, y, rnorm, pro, 0, tc::PASS_ONLY, 0, st, epi);
     static const bool no_dual = getenv("LFB200_TC_NO_DUAL") != nullptr;
     if (!no_dual && pro == nullptr && (d->cout & 3) == 0 && pl.cout_pad <= 64) {
         // bf16x3 in TWO passes: x_hi * [W_hi | W_lo] (one N = 2*Cout MMA per tap: the A tile is fetched from shared
@@ -743,14 +781,14 @@ int conv_tc_launch_ex(const lf_conv_desc* d, const float* x, const float* w, con
             int e = conv_tc_launch_pass(d, pd, x, wbase + 2 * part, bias, y, rnorm, nullptr, 0, tc::PASS_FIRST, 1, st);
             if (e != LF_OK) return e;
             { const char* dbg = getenv("LFB200_TC_DEBUG"); if (dbg && (atoi(dbg) & 16)) return LF_OK; }   // profiling: first pass only
-            return conv_tc_launch_pass(d, pl, x, wbase, bias, y, rnorm, nullptr, 1, tc::PASS_LAST, 0, st);
+            return conv_tc_launch_pass(d, pl, x, wbase, bias, y, rnorm, nullptr, 1, tc::PASS_LAST, 0, st, epi);
         }
     }
     int e = conv_tc_launch_pass(d, pl, x, wbase, bias, y, rnorm, pro, 0, tc::PASS_FIRST, 0, st);
     if (e != LF_OK) return e;
     e = conv_tc_launch_pass(d, pl, x, wbase, bias, y, rnorm, pro, 1, tc::PASS_MID, 0, st);
     if (e != LF_OK) return e;
-    return conv_tc_launch_pass(d, pl, x, wbase + part, bias, y, rnorm, pro, 0, tc::PASS_LAST, 0, st);
+    return conv_tc_launch_pass(d, pl, x, wbase + part, bias, y, rnorm, pro, 0, tc::PASS_LAST, 0, st, epi);
 }
 
 }  // namespace lf
@@ -786,7 +824,41 @@ extern "C" int lf_conv_bwd_data_fused(const lf_conv_desc* desc, const float* gy,
     }
     LF_CHECK_ARG(gy && y_fwd && w_tc_packed && gx && (!fwd_norm || rnorm_fwd), "conv_bwd_data_fused: null pointer");
     TcPrologue pro{y_fwd, rnorm_fwd, fwd_act, fwd_norm, fwd_slope};
-    return conv_tc_launch_ex(desc, gy, w_tc_packed, nullptr, gx, nullptr, &pro, (cudaStream_t)stream);
+    return conv_tc_launch_ex(desc, gy, w_tc_packed, nullptr, gx, nullptr, &pro, nullptr, (cudaStream_t)stream);
+}
+
+namespace lf {
+int expand_epi_supported(const lf_conv_desc* d);
+int expand_epi_launch(const lf_conv_desc* d, const float* x, const float* w, float* y, const float* epi_y,
+                      const float* epi_r, int epi_act, float epi_slope, int epi_norm, cudaStream_t st);
+}
+
+// 1 if lf_conv_bwd_data_epi can run this bwd-data descriptor with the fused backward epilogue
+extern "C" int lf_conv_bwd_data_epi_supported(const lf_conv_desc* desc) {
+    if (desc == nullptr) return 0;
+    if (desc->ndim == -1) return lf::expand_epi_supported(desc);
+    if (desc->precision == 0 || desc->act || desc->norm) return 0;
+    tc::Plan pl;
+    return (tc::make_plan(desc, pl) && (desc->cout & 3) == 0 && pl.cout_pad <= 32) ? 1 : 0;
+}
+
+// bwd-data convolution whose result row is pushed through the PixelNorm/LeakyReLU backward of the layer that
+// produced the forward input (y_prev / rnorm_prev are that layer's saved output and norms): writes du_prev.
+// `w` is the tcgen05-packed weight for conv descriptors (precision 1|2) and the fp32 [D][Cin][Cout] pack for the
+// depth-expand (ndim -1).
+extern "C" int lf_conv_bwd_data_epi(const lf_conv_desc* desc, const float* du, const float* w, const float* y_prev,
+                                    const float* rnorm_prev, int prev_act, float prev_slope, int prev_norm,
+                                    float* du_prev, void* stream) {
+    if (!lf_conv_bwd_data_epi_supported(desc)) {
+        set_error("conv_bwd_data_epi: unsupported shape/precision");
+        return LF_EUNSUPPORTED;
+    }
+    LF_CHECK_ARG(du && w && y_prev && du_prev && (!prev_norm || rnorm_prev), "conv_bwd_data_epi: null pointer");
+    if (desc->ndim == -1)
+        return lf::expand_epi_launch(desc, du, w, du_prev, y_prev, rnorm_prev, prev_act, prev_slope, prev_norm,
+                                     (cudaStream_t)stream);
+    TcEpilogue epi{y_prev, rnorm_prev, prev_act, prev_norm, prev_slope};
+    return conv_tc_launch_ex(desc, du, w, nullptr, du_prev, nullptr, nullptr, &epi, (cudaStream_t)stream);
 }
 
 extern "C" int lf_debug_tc_timeline(long long* host_out /* [3][64][2] */) {

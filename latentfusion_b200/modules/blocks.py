@@ -5,6 +5,7 @@ reference's ~14 elementwise passes."""
 from torch import nn
 
 from . import Interpolate, PixelNorm, EqualizedConv2d, EqualizedConv3d
+from .. import ops
 
 
 def count_blocks(config):
@@ -99,7 +100,8 @@ class Block(nn.Module):
     def forward(self, x):
         slope = self.activation.negative_slope
         x = self.conv1(x, act=True, slope=slope, norm=True)
-        x = self.conv2(x, act=True, slope=slope, norm=True)
+        # conv2 is the only consumer of conv1's output: its bwd-data kernel can apply conv1's activation/norm backward
+        x = self.conv2(ops.mark_single_consumer(x), act=True, slope=slope, norm=True)
         if self.interpolate is not None:
             x = self.interpolate(x)
         return x

@@ -289,12 +289,39 @@ def _conv_name(kind, nd, k, what):
     return f'lf_conv_{what}[{tag}]'
 
 
+class _ActRec:
+    """What the backward of a fused conv+LeakyReLU+PixelNorm layer needs (its output and norms).  When the ONLY
+    consumer of that output is another lfb200 convolution (Block: conv1 -> conv2; Photographer: camera block ->
+    depth collapse), the consumer's bwd-data kernel applies this layer's activation/norm backward in its epilogue
+    (lf_conv_bwd_data_epi) and sets `pre_applied`, and this layer's own backward then skips lf_actnorm_bwd."""
+    __slots__ = ('shape', 'rnorm', 'act', 'slope', 'norm', 'pre_applied')
+
+    # (holds the norms but NOT the output tensor: the consumer has that tensor saved as its own input, and a
+    # reference from here would make an output <-> record cycle that only the garbage collector could free)
+    def __init__(self, shape, rnorm, act, slope, norm):
+        self.shape, self.rnorm, self.act, self.slope, self.norm, self.pre_applied = shape, rnorm, act, slope, norm, False
+
+
+def mark_single_consumer(t):
+    """Declare that the very next lfb200 convolution is the only consumer of `t` (see _ActRec)."""
+    t._lf_single_use = True
+    return t
+
+
+# Measured on B200 (config B): the fused-epilogue bwd-data is SLOWER than bwd-data + the vectorised lf_actnorm_bwd
+# (3x3x3 conv 1.02 ms vs 0.75 + 0.15; collapse 0.32 vs 0.15 + 0.15): the 128 epilogue threads each re-read a 128-byte
+# row of y (32 lines per load instruction) and the epilogue becomes the critical stage.  Opt-in (LFB200_FUSE_EPI=1)
+# until the row is staged through shared memory.
+_FUSE_EPI = _os.environ.get('LFB200_FUSE_EPI', '0') == '1'
+
+
 class _EqConv(torch.autograd.Function):
     """y = PixelNorm(LeakyReLU(conv(x, W) * he + b)) in one kernel.
     Reference: modules/equalized.py:57-64 + blocks.py:152-158 + modules/__init__.py:14-15."""
+    last_rec = None        # _ActRec of the most recent forward, picked up by eq_conv() to tag the returned tensor
 
     @staticmethod
-    def forward(ctx, x, weight, bias, kind, depth, act, slope, norm, precision, fan_in=None):
+    def forward(ctx, x, weight, bias, kind, depth, act, slope, norm, precision, fan_in=None, rec_in=None):
         _need_cuda(x, weight, bias)
         x = to_cl(x)
         dev = x.device
@@ -353,6 +380,9 @@ class _EqConv(torch.autograd.Function):
               nbytes=4 * (x.numel() + y.numel()), flops=2 * positions * taps * gcin * gcout)
         ctx.save_for_backward(x, y, rnorm, wb)
         ctx.wkey = wkey
+        ctx.rec_in = rec_in
+        ctx.rec_out = _ActRec(tuple(y.shape), rnorm, act, slope, norm) if ((act or norm) and kind != KIND_EXPAND) else None
+        _EqConv.last_rec = ctx.rec_out
         ctx.cfg = (kind, depth, act, slope, norm, precision, nd, n, d, h, w, gcin, gcout, k, scale,
                    tuple(weight.shape), bias is not None)
         return y
@@ -373,10 +403,16 @@ class _EqConv(torch.autograd.Function):
         bdesc = _desc(bkind, bnd, n, d, h, w, cout, cin, k, scale, 0, 0.0, 0, precision)
         bflops = 2 * (n * h * w * (d if kind == KIND_CONV else 1)) * wb.shape[0] * cin * cout
         fused_done = False
+        rec_out, rec_in = ctx.rec_out, ctx.rec_in
+        pre_applied = rec_out is not None and rec_out.pre_applied
+        if pre_applied:                   # the consumer's bwd-data epilogue already produced du for this layer
+            rec_out.pre_applied = False
+        epi = (rec_in is not None and ctx.needs_input_grad[0] and rec_in.shape == tuple(x.shape)
+               and bool(lib.lf_conv_bwd_data_epi_supported(ctypes.byref(bdesc))))
         # Measured on B200 (config B 3x3x3): the fused staging makes the producers the bottleneck (0.57 ms) while
         # the vectorised lf_actnorm_bwd (0.13 ms) + plain conv (0.32 ms) is faster, so fusion is opt-in
         # (LFB200_FUSE_BWD=1) until the producer stage is widened.
-        if (_FUSE_BWD and ctx.needs_input_grad[0] and (act or norm) and not need_w and kind == KIND_CONV and precision == PRECISION_BF16
+        if (_FUSE_BWD and not pre_applied and not epi and ctx.needs_input_grad[0] and (act or norm) and not need_w and kind == KIND_CONV and precision == PRECISION_BF16
                 and _tc_ok(bdesc) and cout in (16, 32, 64, 128)):
             # pose-loop case: PixelNorm/LeakyReLU backward fused into the tcgen05 kernel's operand staging
             gx = torch.empty_like(x)
@@ -387,7 +423,7 @@ class _EqConv(torch.autograd.Function):
                   nbytes=4 * (2 * gy.numel() + gx.numel()), flops=bflops)
             fused_done = True
         if not fused_done:
-            if act or norm:
+            if (act or norm) and not pre_applied:
                 du = torch.empty_like(gy)
                 if kind == KIND_EXPAND:
                     outer, gd, inner = n, d, h * w
@@ -400,7 +436,17 @@ class _EqConv(torch.autograd.Function):
                       nbytes=4 * 3 * gy.numel())
             else:
                 du = gy
-            if ctx.needs_input_grad[0]:
+            if epi:
+                # bwd-data + the producer layer's PixelNorm/LeakyReLU backward in one kernel: returns du of that layer
+                gx = torch.empty_like(x)
+                w_arg = wb if bkind == KIND_EXPAND else _tc_pack(wb, ctx.wkey + ('b',))
+                _call(_conv_name(kind, nd, k, 'bwd_data_epi'), lib.lf_conv_bwd_data_epi,
+                      (ctypes.byref(bdesc), _p(du), _p(w_arg), _p(x), _p(rec_in.rnorm), int(rec_in.act),
+                       float(rec_in.slope), int(rec_in.norm), _p(gx), _stream()),
+                      kernels=1 if bkind == KIND_EXPAND else _tc_passes(bdesc),
+                      nbytes=4 * (du.numel() + 2 * gx.numel()), flops=bflops)
+                rec_in.pre_applied = True
+            elif ctx.needs_input_grad[0]:
                 gx = torch.empty_like(x)
                 # bwd-data = the same implicit GEMM with flipped/transposed weights, no epilogue
                 if _tc_ok(bdesc):
@@ -423,13 +469,20 @@ class _EqConv(torch.autograd.Function):
                 gw = _unpack_weight_grad(gwp, wshape, kind, depth)
             if has_bias and ctx.needs_input_grad[2]:
                 gb = gbp.t().reshape(-1) if kind == KIND_EXPAND else gbp.reshape(-1)
-        return gx, gw, gb, None, None, None, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None, None, None, None
 
 
 def eq_conv(x, weight, bias, act=False, slope=0.2, norm=False, kind=KIND_CONV, depth=0, precision=None, fan_in=None):
     if precision is None:
         precision = _default_precision
-    return _EqConv.apply(x, weight, bias, kind, depth, bool(act), float(slope), bool(norm), int(precision), fan_in)
+    rec_in = None
+    if _FUSE_EPI and getattr(x, '_lf_single_use', False) and torch.is_grad_enabled():
+        rec_in = getattr(x, '_lf_actnorm', None)
+    y = _EqConv.apply(x, weight, bias, kind, depth, bool(act), float(slope), bool(norm), int(precision), fan_in, rec_in)
+    if y.requires_grad and _EqConv.last_rec is not None:
+        y._lf_actnorm = _EqConv.last_rec        # lets a single downstream lfb200 conv fuse this layer's backward
+    _EqConv.last_rec = None
+    return y
 
 
 # ------------------------------------------------------------------------------------------------

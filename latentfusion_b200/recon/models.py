@@ -16,6 +16,7 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
+from .. import ops
 from ..modules import unet, EqualizedConv3d
 from ..modules.blocks import create_blocks, OutputBlock3d, OutputBlock2d
 from ..modules.geometry import (TileProjection2d3d, FactorProjection2d3d, CameraToObjectTransform, Camera,
@@ -270,6 +271,8 @@ class Photographer(nn.Module):
         if self.projection_type == 'sum':
             z = z.sum(dim=2)
         elif self.projection_type == 'factor':
+            if not self.occlusion_module:          # the projection is then the only consumer of the camera block
+                z = ops.mark_single_consumer(z)
             z = self.projection_block(z)
         y = self.image_decoder(z)
         if len(self.output_blocks):

@@ -175,3 +175,43 @@ def test_depth_projections_vs_torch_fp64(n, c, cout, depth, hw):
     y2l.backward(g2)
     ref2.backward(g2.double())
     torch.testing.assert_close(x2t.grad.double(), x2r.grad, atol=1e-4, rtol=1e-3)
+
+
+@pytest.mark.parametrize('precision', [1, 2])
+def test_epilogue_fused_actnorm_backward_matches_separate_kernels(precision):
+    """Block (conv1 -> conv2, both LeakyReLU + PixelNorm) followed by the depth collapse: with LFB200_FUSE_EPI=1 (opt-in:
+    measured slower than the separate kernels, see ops._FUSE_EPI) the bwd-data kernels of conv2 and of the collapse apply the activation/norm backward of their producer in the epilogue
+    (lf_conv_bwd_data_epi) and the standalone lf_actnorm_bwd passes over the 3-D tensors disappear."""
+    from latentfusion_b200.modules.blocks import Block
+    from latentfusion_b200.modules import EqualizedConv3d
+    dev = torch.device('cuda:0')
+    torch.manual_seed(21)
+    C, S = 32, 16
+    block = Block(C, C, conv_module=EqualizedConv3d).to(dev)
+    for p_ in block.parameters():
+        p_.requires_grad_(False)
+    wc = torch.randn(C, C * S, 1, 1, device=dev)
+    x = torch.randn(2, C, S, S, S, device=dev)
+    g = torch.randn(2, C, S, S, device=dev)
+    results = []
+    old, old_fuse = ops.get_default_precision(), ops._FUSE_EPI
+    ops.set_default_precision(precision)
+    try:
+        for fuse in (False, True):
+            ops._FUSE_EPI = fuse
+            xt = x.clone().requires_grad_(True)
+            z = block(xt)
+            z = ops.eq_conv(ops.mark_single_consumer(z), wc, None, act=True, norm=True, kind=ops.KIND_COLLAPSE, depth=S)
+            ops.KernelTrace.reset(True)
+            z.backward(g)
+            names = [r[0] for r in ops.KernelTrace.records]
+            ops.KernelTrace.reset(False)
+            results.append((xt.grad.clone(), names))
+    finally:
+        ops._FUSE_EPI = old_fuse
+        ops.set_default_precision(old)
+    (g_sep, n_sep), (g_fused, n_fused) = results
+    assert n_sep.count('lf_actnorm_bwd') == 3 and not any('epi' in n for n in n_sep)
+    assert n_fused.count('lf_actnorm_bwd') == 1 and sum('bwd_data_epi' in n for n in n_fused) == 2, n_fused
+    tol = dict(atol=2e-5, rtol=1e-4) if precision == 1 else dict(atol=2e-3, rtol=2e-3)
+    torch.testing.assert_close(g_fused, g_sep, **tol)
