@@ -334,6 +334,20 @@ def fuse(kind, z_obj, sd=None):
         for i in range(1, z_obj.shape[1]):
             h = gru_cell(sd, 'gru', torch.cat((z_obj[:, i], coords), dim=1), h)
         return h.unsqueeze(1)
+    if kind == 'lstm':                      # fusion.py:234-246, modules/lstm.py:41-56
+        h = z_obj[:, 0]
+        c = torch.zeros_like(h)
+        coords = voxel_coords(*h.shape[-3:])[None].expand(h.shape[0], -1, -1, -1, -1).to(h.dtype)
+        nh = h.shape[1]
+        for i in range(1, z_obj.shape[1]):
+            gates = eq_conv(torch.cat((z_obj[:, i], coords, h), dim=1), sd, 'lstm.conv', 1)
+            gi, gf, go, gg = torch.split(gates, nh, dim=1)
+            c = torch.sigmoid(gf) * c + torch.sigmoid(gi) * torch.tanh(gg)
+            h = torch.sigmoid(go) * torch.tanh(c)
+        return h.unsqueeze(1)
+    if kind == 'concat':                    # fusion.py:87-92
+        n, v, ch, d, hh, w = z_obj.shape
+        return z_obj.reshape(n, 1, v * ch, d, hh, w)
     raise ValueError(kind)
 
 

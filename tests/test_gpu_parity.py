@@ -166,6 +166,37 @@ def test_sculptor_and_fusers_vs_golden(g, dev):
         torch.testing.assert_close(zg.cpu(), g['z_obj_gru'], atol=2e-4, rtol=2e-3)
 
 
+def test_lstm_and_concat_fusers_vs_golden(dev):
+    """recon/fusion.py:87-92 (ConcatFuser) and :204-246 (LSTMFuser, ConvLSTMCell) against the unmodified reference:
+    reference-format state_dict loads strictly; forward at the exact-fp32 and bf16x3 settings; backward to the
+    per-view cubes at exact fp32."""
+    import os
+    from latentfusion_b200 import ops
+    from latentfusion_b200.recon import fusion
+    gf = ph.Golden(os.path.join(ph.ROOT, 'tests', 'golden', 'fusers_c8_s10.npz'))
+    C = gf.meta['C']
+    lstm = fusion.get_fuser('lstm', in_channels=C, cube_size=1.0)
+    lstm.load_state_dict(gf.state_dict('lstm'), strict=True)
+    lstm = lstm.to(dev)
+    z = gf['z_obj'].to(dev)
+    old = ops.get_default_precision()
+    try:
+        for precision in (0, 1):
+            ops.set_default_precision(precision)
+            with torch.no_grad():
+                out, _ = lstm(z, None, None, None)
+            torch.testing.assert_close(out.cpu(), gf['fused.lstm'], **OUT_TOL)
+        ops.set_default_precision(0)
+        zt = z.clone().requires_grad_(True)
+        out, _ = lstm(zt, None, None, None)
+        (out * gf['lstm.w'].to(dev)).sum().backward()
+        torch.testing.assert_close(zt.grad.cpu(), gf['lstm.grad_z'], **GRAD_TOL)
+    finally:
+        ops.set_default_precision(old)
+    cat, _ = fusion.get_fuser('concat', in_channels=C, cube_size=1.0)(z, None, None, None)
+    assert torch.equal(cat.cpu(), gf['fused.concat'])
+
+
 def test_render_loss_and_camera_grads_vs_golden(g, dev):
     ph.smoke_check()
 
