@@ -197,6 +197,23 @@ def test_lstm_and_concat_fusers_vs_golden(dev):
     assert torch.equal(cat.cpu(), gf['fused.concat'])
 
 
+def test_blend_fuser_vs_golden(dev):
+    """recon/fusion.py:95-149 (BlendFuser: UNet3d on [z_cam, depth coordinate] -> camera->object resample -> softmax over
+    the views -> weighted sum) against the unmodified reference's output; strict state_dict load."""
+    import os
+    from latentfusion_b200.recon import fusion
+    from latentfusion_b200.utils import parse_block_config as pbc
+    gf = ph.Golden(os.path.join(ph.ROOT, 'tests', 'golden', 'fusers_c8_s10.npz'))
+    blend = fusion.get_fuser('blend', in_channels=gf.meta['C'], cube_size=1.0, block_config=pbc(gf.text('blend.cfg')))
+    blend.load_state_dict(gf.state_dict('blend'), strict=True)
+    blend = blend.to(dev)
+    cam = ph.product_camera(gf.cam('blend.cam'), dev)
+    with torch.no_grad():
+        fused, extra = blend(gf['blend.z_obj'].to(dev), [gf['blend.z_cam'].to(dev)], None, cam)
+    torch.testing.assert_close(extra['blend_weights'].cpu(), gf['blend.weights'], **OUT_TOL)
+    torch.testing.assert_close(fused.cpu(), gf['fused.blend'], **OUT_TOL)
+
+
 def test_render_loss_and_camera_grads_vs_golden(g, dev):
     ph.smoke_check()
 
