@@ -43,6 +43,8 @@ def create_blocks(config, conv_module, scale_factor, scale_mode='bilinear', kern
 
 
 class InputBlock(nn.Module):
+    """1x1 (by default) convolution + LeakyReLU in one kernel: lifts raw inputs to the first width of a config."""
+
     def __init__(self, in_channels, out_channels, conv_module, kernel_size=1, relu_slope=0.2, padding=0):
         super().__init__()
         self.conv = conv_module(in_channels, out_channels, kernel_size, padding=padding)
@@ -52,35 +54,31 @@ class InputBlock(nn.Module):
         return self.conv(x, act=True, slope=self.activation.negative_slope)
 
 
-class InputBlock2d(InputBlock):
-    def __init__(self, in_channels, out_channels, kernel_size=1, relu_slope=0.2, padding=0):
-        super().__init__(in_channels, out_channels, EqualizedConv2d, kernel_size, relu_slope, padding)
-
-
-class InputBlock3d(InputBlock):
-    def __init__(self, in_channels, out_channels, kernel_size=1, relu_slope=0.2, padding=0):
-        super().__init__(in_channels, out_channels, EqualizedConv3d, kernel_size, relu_slope, padding)
-
-
 class OutputBlock(nn.Module):
+    """Plain convolution head (logits), optionally followed by a caller-supplied activation module."""
+
     def __init__(self, in_channels, out_channels, conv_module, kernel_size=1, padding=0, activation=None):
         super().__init__()
         self.conv = conv_module(in_channels, out_channels, kernel_size, padding=padding)
         self.activation = activation
 
     def forward(self, x):
-        x = self.conv(x)
-        return self.activation(x) if self.activation else x
+        y = self.conv(x)
+        return y if not self.activation else self.activation(y)
 
 
-class OutputBlock2d(OutputBlock):
-    def __init__(self, in_channels, out_channels, kernel_size=1, padding=0, activation=None):
-        super().__init__(in_channels, out_channels, EqualizedConv2d, kernel_size, padding, activation)
+def _bind_conv(base, conv_module, name):
+    """`base` with its conv_module argument fixed (the reference spells these out as ...2d / ...3d classes)."""
+
+    def __init__(self, in_channels, out_channels, *args, **kwargs):
+        base.__init__(self, in_channels, out_channels, conv_module, *args, **kwargs)
+    return type(name, (base,), {'__init__': __init__, '__module__': __name__})
 
 
-class OutputBlock3d(OutputBlock):
-    def __init__(self, in_channels, out_channels, kernel_size=1, padding=0, activation=None):
-        super().__init__(in_channels, out_channels, EqualizedConv3d, kernel_size, padding, activation)
+InputBlock2d = _bind_conv(InputBlock, EqualizedConv2d, 'InputBlock2d')
+InputBlock3d = _bind_conv(InputBlock, EqualizedConv3d, 'InputBlock3d')
+OutputBlock2d = _bind_conv(OutputBlock, EqualizedConv2d, 'OutputBlock2d')
+OutputBlock3d = _bind_conv(OutputBlock, EqualizedConv3d, 'OutputBlock3d')
 
 
 class Block(nn.Module):

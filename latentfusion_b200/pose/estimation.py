@@ -60,29 +60,35 @@ def cosine_distance(x1, x2, dim=1, eps=1e-8):
 
 def default_pose_loss(target, z_pred_depth, z_pred_mask_logits, z_pred_camera, z_pred_latent=None,
                       z_target_latent=None):
-    """Fitness of a batch of rendered hypotheses against one target observation: every term is a
-    per-hypothesis scalar.  Crops are pasted back into the full frame (nearest for depth, bilinear
-    for mask logits) before comparing."""
-    pred_depth, _ = z_pred_camera.uncrop(z_pred_depth, scale_mode='nearest')
-    pred_mask_logits, _ = z_pred_camera.uncrop(z_pred_mask_logits, scale_mode='bilinear')
-    pred_mask = torch.sigmoid(pred_mask_logits)
-    pred_depth = pred_depth * pred_mask
-    invalid = (target.depth == 0) & (target.mask > 0.1)        # mask says object, sensor saw nothing
-    target = target.prepare()
+    """Per-hypothesis fitness terms of rendered crops against ONE full-frame target observation.
 
-    losses = {}
-    depth_l1 = pu.zero_invalid_pixels(
-        F.l1_loss(pred_depth, target.depth.expand_as(pred_depth), reduction='none'), invalid)
-    losses['ov_depth'] = pu.reduce_loss_mask(depth_l1, pred_mask * target.mask)
-    losses['depth'] = depth_l1.mean(dim=(1, 2, 3))
-    losses['iou'] = pu.iou_loss(pred_mask, pu.zero_invalid_pixels(target.mask, invalid))
-    losses['mask'] = F.binary_cross_entropy_with_logits(
-        pred_mask_logits, target.mask.expand_as(pred_mask), reduction='none').mean(dim=(1, 2, 3))
+    The crops are pasted back into the sensor frame first (depth: nearest, mask logits: bilinear; border-clamped).
+    Pixels the target mask claims but the depth sensor missed (depth == 0) are excluded from the depth and IoU terms.
+    Returns a dict of [N] tensors: 'depth' (mean L1 over the frame), 'ov_depth' (L1 averaged over the overlap of the
+    predicted and target masks), 'iou', 'mask' (BCE with logits) and, when both latents are given, 'latent'
+    (cosine distance of the flattened pre-decoder features).  Same arithmetic as reference estimation.py:70-118.
+    """
+    frame_depth = z_pred_camera.uncrop(z_pred_depth, scale_mode='nearest')[0]
+    frame_logits = z_pred_camera.uncrop(z_pred_mask_logits, scale_mode='bilinear')[0]
+    frame_mask = torch.sigmoid(frame_logits)
+    frame_depth = frame_depth * frame_mask
+    sensor_hole = (target.depth == 0) & (target.mask > 0.1)
+    target = target.prepare()
+    per_sample = (1, 2, 3)
+
+    abs_err = F.l1_loss(frame_depth, target.depth.expand_as(frame_depth), reduction='none')
+    abs_err = pu.zero_invalid_pixels(abs_err, sensor_hole)
+    terms = {
+        'ov_depth': pu.reduce_loss_mask(abs_err, frame_mask * target.mask),
+        'depth': abs_err.mean(dim=per_sample),
+        'iou': pu.iou_loss(frame_mask, pu.zero_invalid_pixels(target.mask, sensor_hole)),
+        'mask': F.binary_cross_entropy_with_logits(frame_logits, target.mask.expand_as(frame_mask),
+                                                   reduction='none').mean(dim=per_sample),
+    }
     if z_pred_latent is not None and z_target_latent is not None:
-        a = z_pred_latent.reshape(z_pred_latent.shape[0], -1)
-        b = z_target_latent.reshape(z_target_latent.shape[0], -1)
-        losses['latent'] = cosine_distance(a, b.expand_as(a))
-    return losses
+        rendered = z_pred_latent.flatten(1)
+        terms['latent'] = cosine_distance(rendered, z_target_latent.flatten(1).expand_as(rendered))
+    return terms
 
 
 def weigh_losses(loss_dict, weight_dict):
@@ -93,23 +99,19 @@ class PoseEstimator:
 
     def __init__(self, *, model, ranking_size, loss_weights, loss_func=None, return_camera_history=False,
                  verbose=False):
-        self.model = model
-        self.ranking_size = ranking_size
-        self.loss_func = default_pose_loss if loss_func is None else loss_func
-        self.loss_weights = defaultdict(float)
-        self.loss_weights.update(loss_weights)
-        self.return_camera_history = return_camera_history
-        self.verbose = verbose
+        self.model, self.ranking_size = model, ranking_size
+        self.loss_func = loss_func or default_pose_loss
+        self.loss_weights = defaultdict(float, loss_weights)          # unspecified terms weigh 0
+        self.return_camera_history, self.verbose = return_camera_history, verbose
 
-    @property
-    def device(self):
-        return self.model.device
+    device = property(lambda self: self.model.device)
 
     @classmethod
     def initial_pose(cls, target_obs):
-        return initialization.estimate_initial_pose(target_obs.depth, target_obs.mask,
-                                                    target_obs.camera.intrinsic, target_obs.camera.width,
-                                                    target_obs.camera.height)
+        """Centroid-of-the-masked-depth initial guess (pose/initialization.py)."""
+        cam = target_obs.camera
+        return initialization.estimate_initial_pose(target_obs.depth, target_obs.mask, cam.intrinsic, cam.width,
+                                                    cam.height)
 
     def estimate(self, z_obj, target_obs, **kwargs):
         if len(target_obs) > 1:
@@ -122,22 +124,21 @@ class PoseEstimator:
     def _track_best_items(self, ranking, step, items, loss):
         """Merge this step's (item, loss) pairs into the running top-`ranking_size` list; returns how
         much the best loss improved."""
-        loss = loss.detach().cpu()
-        prev_best = ranking[0][1] if ranking else float('inf')
-        ranking.extend((item, err.item(), step) for item, err in zip(items, loss))
-        ranking.sort(key=lambda r: r[1])
+        before = ranking[0][1] if ranking else float('inf')
+        for item, value in zip(items, loss.detach().cpu().tolist()):
+            ranking.append((item, value, step))
+        ranking.sort(key=lambda entry: entry[1])
         del ranking[self.ranking_size:]
-        best = ranking[0][1]
-        return prev_best - best if best < prev_best else 0.0
+        return max(before - ranking[0][1], 0.0)
 
     def _render_observation(self, z_obj, camera, **kwargs):
-        z_camera = camera.zoom(None, self.model.input_size, self.model.camera_dist)
-        with torch.set_grad_enabled(kwargs.get('grad_enabled', False)):
-            pred, z_latent = self.model.render_latent_object(z_obj, z_camera.to(self.device), return_latent=True)
-            z_mask = pred['mask'].squeeze(0)
-            z_mask_logits = pred['mask_logits'].squeeze(0)
-            z_depth = camera.denormalize_depth(pred['depth'].squeeze(0)) * z_mask
-        return z_depth, z_mask_logits, z_latent, z_camera
+        """Render full-frame cameras through their zoomed crops -> (masked metric depth, mask logits, latent, crop camera)."""
+        crop = camera.zoom(None, self.model.input_size, self.model.camera_dist)
+        with torch.set_grad_enabled(bool(kwargs.get('grad_enabled', False))):
+            out, latent = self.model.render_latent_object(z_obj, crop.to(self.device), return_latent=True)
+            mask, mask_logits, depth = (out[k].squeeze(0) for k in ('mask', 'mask_logits', 'depth'))
+            metric_depth = camera.denormalize_depth(depth) * mask
+        return metric_depth, mask_logits, latent, crop
 
 
 class CrossEntropyPoseEstimator(PoseEstimator):
@@ -154,54 +155,59 @@ class CrossEntropyPoseEstimator(PoseEstimator):
         self.translation_std, self.quaternion_std = translation_std, quaternion_std
         self.elite_sched = utils.ExponentialScheduler(num_samples, num_elites, num_iters)
 
+    _FLIP_AXES = ((0.0, 0.0, 1.0), (0.0, 1.0, 0.0), (1.0, 0.0, 0.0))
+
+    def _seed_population(self, target_obs, cameras):
+        """(reference camera for intrinsics/frame, initial population)"""
+        if cameras:
+            return cameras[0], cameras
+        guess = self.initial_pose(target_obs)
+        spread = pu.sample_cameras_with_estimate(n=self.num_gmm_components * self.num_samples, camera_est=guess,
+                                                 upright=self.init_upright, hemisphere=self.init_hemisphere)
+        return guess, spread
+
+    def _fit(self, cameras):
+        return self._create_gmm(self._camera_to_params(cameras).cpu())
+
     def _estimate(self, z_obj, target_obs, **kwargs):
-        if kwargs.get('cameras', None):
-            cameras = kwargs['cameras']
-            camera_init = cameras[0]
-        else:
-            camera_init = self.initial_pose(target_obs)
-            cameras = pu.sample_cameras_with_estimate(n=self.num_gmm_components * self.num_samples,
-                                                      camera_est=camera_init, upright=self.init_upright,
-                                                      hemisphere=self.init_hemisphere)
-        gmm = self._create_gmm(self._camera_to_params(cameras).cpu())
+        camera_init, population = self._seed_population(target_obs, kwargs.get('cameras'))
         target_obs = target_obs.to(self.device)
-        history, ranking, prev_gmm = [], [], None
+        proposal, previous = self._fit(population), None
+        ranking, history = [], []
         for step in utils.trange(self.num_iters):
-            elites = int(self.elite_sched.get(step))
-            cameras, losses = self._refine_pose(z_obj, target_obs, prev_gmm, gmm, num_elites=elites,
-                                                camera_init=camera_init)
-            prev_gmm = gmm
-            gmm = self._create_gmm(self._camera_to_params(cameras).cpu())
-            if self._track_best_items(ranking, step, cameras, losses) > 0:
-                history.append((losses, Camera.cat([c for c, _, _ in ranking])))
-        best = Camera.cat([c for c, _, _ in ranking])
-        return (best, history) if self.return_camera_history else best
+            keep = int(self.elite_sched.get(step))
+            elites, losses = self._refine_pose(z_obj, target_obs, previous, proposal, num_elites=keep,
+                                               camera_init=camera_init)
+            previous, proposal = proposal, self._fit(elites)
+            improved = self._track_best_items(ranking, step, elites, losses)
+            if improved > 0:
+                history.append((losses, Camera.cat([entry[0] for entry in ranking])))
+        winners = Camera.cat([entry[0] for entry in ranking])
+        return (winners, history) if self.return_camera_history else winners
 
     def _refine_pose(self, z_obj, target_obs, prev_gmm, gmm, num_elites, camera_init):
-        proposal = self._combined_gmm(prev_gmm, gmm, self.learning_rate) if prev_gmm is not None else gmm
-        n = self.num_samples // 4 if self.sample_flipped else self.num_samples
-        cameras = self._params_to_camera(self._sample_poses(proposal, n), camera_init=camera_init,
-                                         device=self.device)
-        if self.sample_flipped:
-            cameras = Camera.cat([cameras] + [pu.flip_camera(cameras, axis=a)
-                                              for a in ((0.0, 0.0, 1.0), (0.0, 1.0, 0.0), (1.0, 0.0, 0.0))])
-        z_target_latent = None
+        """One CE generation: sample from the (blended) proposal, score every sample with a forward render, keep the
+        `num_elites` best."""
+        mixture = gmm if prev_gmm is None else self._combined_gmm(prev_gmm, gmm, self.learning_rate)
+        draws = self.num_samples // (1 + len(self._FLIP_AXES)) if self.sample_flipped else self.num_samples
+        cameras = self._params_to_camera(self._sample_poses(mixture, draws), camera_init=camera_init, device=self.device)
+        if self.sample_flipped:                  # symmetric objects: also try each sample turned by pi about x, y, z
+            cameras = Camera.cat([cameras, *(pu.flip_camera(cameras, axis=axis) for axis in self._FLIP_AXES)])
+        target_code = None
         if self.loss_weights.get('latent', 0.0) > 0.0:
             with torch.no_grad():
-                z_target_latent = self.model.compute_latent_code(target_obs, cameras[0])
-        depth, mask_logits, latent, z_camera = self._render_observation(z_obj, cameras)
-        loss_dict = self.loss_func(target_obs, depth, mask_logits, z_camera, z_pred_latent=latent,
-                                   z_target_latent=z_target_latent)
-        loss = sum(weigh_losses(loss_dict, self.loss_weights).values())
-        elite = torch.argsort(loss)[:num_elites]
-        return cameras[elite], loss[elite]
+                target_code = self.model.compute_latent_code(target_obs, cameras[0])
+        depth, mask_logits, code, crop = self._render_observation(z_obj, cameras)
+        terms = self.loss_func(target_obs, depth, mask_logits, crop, z_pred_latent=code, z_target_latent=target_code)
+        score = sum(weigh_losses(terms, self.loss_weights).values())
+        best = torch.argsort(score)[:num_elites]
+        return cameras[best], score[best]
 
     def _sample_poses(self, gmm, n):
-        params, _ = gmm.sample(n)
-        params = torch.tensor(params, dtype=torch.float32, device=self.device)
-        params[:, :3] += torch.randn_like(params[:, :3]) * self.translation_std
-        params[:, 3:] += torch.randn_like(params[:, 3:]) * self.quaternion_std
-        return params
+        """n draws (translation | log-quaternion) from the proposal, jittered so elites never collapse to a point"""
+        drawn = torch.as_tensor(gmm.sample(n)[0], dtype=torch.float32, device=self.device)
+        jitter = torch.cat((torch.full((3,), float(self.translation_std)), torch.full((3,), float(self.quaternion_std))))
+        return drawn + torch.randn_like(drawn) * jitter.to(drawn.device)
 
     def _create_gmm(self, params=None):
         import sklearn.mixture
@@ -399,14 +405,12 @@ class GradientPoseEstimator(PoseEstimator):
             history[key] = torch.cat((history[key], value), dim=0) if key in history else value
 
     @classmethod
-    def _record_stat_dict(cls, history, d):
-        for key, value in d.items():
-            cls._record_stat(history, key, value)
+    def _record_stat_dict(cls, history, entries):
+        for name in entries:
+            cls._record_stat(history, name, entries[name])
 
     def _render_observation(self, z_obj, camera, **kwargs):
         """The optimised camera is already the zoomed one, so render it as is."""
-        pred, z_latent = self.model.render_latent_object(z_obj, camera.to(self.model.device), return_latent=True)
-        z_mask = pred['mask'].squeeze(0)
-        z_mask_logits = pred['mask_logits'].squeeze(0)
-        z_depth = camera.denormalize_depth(pred['depth'].squeeze(0))
-        return z_depth, z_mask, z_mask_logits, z_latent
+        out, latent = self.model.render_latent_object(z_obj, camera.to(self.model.device), return_latent=True)
+        mask, mask_logits, depth = (out[k].squeeze(0) for k in ('mask', 'mask_logits', 'depth'))
+        return camera.denormalize_depth(depth), mask, mask_logits, latent
