@@ -195,6 +195,13 @@ int lf_conv_bwd_data_epi(const lf_conv_desc* desc, const float* du, const float*
                          const float* rnorm_prev, int prev_act, float prev_slope, int prev_norm, float* du_prev,
                          void* stream);
 
+/* All output heads of the render decoder in one pass (recon/models.py:331-338, :448-452: several 1x1 Equalized convs
+ * with 1-3 output channels each, concatenated): y[pos][h] = scale * sum_c x[pos][c] * w[h][c] + bias[h], exact fp32.
+ * x [positions][C] channels-last, w [H][C], H <= 8, C = 4 * 2^k <= 128.  lf_heads_bwd: gx = scale * g . w. */
+int lf_heads_fwd(const float* x, const float* w, const float* bias, float* y, int64_t positions, int c, int h,
+                 float scale, void* stream);
+int lf_heads_bwd(const float* g, const float* w, float* gx, int64_t positions, int c, int h, float scale, void* stream);
+
 /* ---- IBR colour branch (forward only: the pose loop does not differentiate it) ---------------
  * IBR camera block, LF_IBR_CAM_STRIDE floats per camera:
  *   [0,12) cam_to_obj rows 0-2   [12,24) obj_to_cam rows 0-2   [24,36) obj_to_image = K * obj_to_cam (3x4)

@@ -63,6 +63,8 @@ _SIGNATURES = {
     'lf_pose_loss_bwd': (c_int, [ctypes.POINTER(LossDesc)] + [c_f32p] * 12 + [c_vp]),
     'lf_conv_bwd_data_epi_supported': (c_int, [ctypes.POINTER(ConvDesc)]),
     'lf_conv_bwd_data_epi': (c_int, [ctypes.POINTER(ConvDesc), c_f32p, c_f32p, c_f32p, c_f32p, c_int, ctypes.c_float, c_int, c_f32p, c_vp]),
+    'lf_heads_fwd': (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_int, c_int, ctypes.c_float, c_vp]),
+    'lf_heads_bwd': (c_int, [c_f32p, c_f32p, c_f32p, c_i64, c_int, c_int, ctypes.c_float, c_vp]),
     'lf_ibr_reproject_fwd': (c_int, [c_f32p] * 7 + [c_int] * 5 + [c_vp]),
     'lf_ibr_blend_fwd': (c_int, [c_f32p] * 3 + [c_int] * 5 + [c_vp]),
     'lf_ibr_warp_blend_fwd': (c_int, [c_f32p, c_f32p, ctypes.c_float] + [c_f32p] * 4 + [c_int] * 5 + [c_vp]),

@@ -233,3 +233,107 @@ extern "C" int lf_gru_gates2(const float* h, const float* update, const float* o
     gru_gates2_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(h, update, o, h_new, numel);
     LF_RETURN_LAUNCH();
 }
+
+// ------------------------------------------------------------------------------------------------
+// Output heads of the render decoder (recon/models.py:331-338, :448-452): several 1x1 Equalized convs with 1-3
+// output channels each, concatenated along channels.  As convolutions they are GEMMs with N = 1..3 — 52 us each on
+// the implicit-GEMM kernels for 17 MB of input.  Here: one pass over x for ALL heads, exact fp32.
+//   y[pos][h] = scale * sum_c x[pos][c] * w[h][c] + b[h]            h < H <= 8, C % 4 == 0, C <= 256
+// LPV = C/4 lanes share a position (128-bit coalesced loads), partial dot products are xor-shuffled together.
+// ------------------------------------------------------------------------------------------------
+namespace lf {
+
+constexpr int HEADS_MAX = 8;
+
+__global__ void __launch_bounds__(256)
+heads_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                 float* __restrict__ y, int64_t positions, int C, int H, int lg, float scale) {
+    extern __shared__ float sw[];                  // [H][C]
+    for (int i = threadIdx.x; i < H * C; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const int q4 = C >> 2;
+    const int64_t units = positions * q4, units_pad = (units + 31) & ~(int64_t)31;
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < units_pad; u += (int64_t)gridDim.x * blockDim.x) {
+        const bool live = u < units;
+        const int64_t uu = live ? u : units - 1;
+        const int64_t pos = uu >> lg;
+        const int q = (int)(uu & (q4 - 1));
+        const float4 xv = ldg4(x + uu * 4);
+        float acc[HEADS_MAX];
+#pragma unroll
+        for (int h = 0; h < HEADS_MAX; ++h) {
+            if (h < H) {
+                const float4 wv = *reinterpret_cast<const float4*>(sw + h * C + q * 4);
+                float d = xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+                for (int s = 1; s < q4; s <<= 1) d += __shfl_xor_sync(0xffffffffu, d, s);
+                acc[h] = d;
+            }
+        }
+        if (live && q == 0) {
+#pragma unroll
+            for (int h = 0; h < HEADS_MAX; ++h)
+                if (h < H) y[pos * H + h] = acc[h] * scale + (bias != nullptr ? bias[h] : 0.f);
+        }
+    }
+}
+
+// gx[pos][c] = scale * sum_h g[pos][h] * w[h][c]
+__global__ void __launch_bounds__(256)
+heads_bwd_kernel(const float* __restrict__ g, const float* __restrict__ w, float* __restrict__ gx,
+                 int64_t positions, int C, int H, int lg, float scale) {
+    extern __shared__ float sw[];
+    for (int i = threadIdx.x; i < H * C; i += blockDim.x) sw[i] = w[i] * scale;
+    __syncthreads();
+    const int q4 = C >> 2;
+    const int64_t units = positions * q4;
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pos = u >> lg;
+        const int q = (int)(u & (q4 - 1));
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int h = 0; h < H; ++h) {
+            const float gv = __ldg(g + pos * H + h);
+            const float4 wv = *reinterpret_cast<const float4*>(sw + h * C + q * 4);
+            o.x += gv * wv.x; o.y += gv * wv.y; o.z += gv * wv.z; o.w += gv * wv.w;
+        }
+        *reinterpret_cast<float4*>(gx + u * 4) = o;
+    }
+}
+
+static int heads_check(int64_t positions, int c, int h, int& lg) {
+    LF_CHECK_ARG(positions > 0 && h >= 1 && h <= HEADS_MAX, "heads: need 1..%d output channels", HEADS_MAX);
+    const int q4 = c >> 2;
+    LF_CHECK_ARG(c >= 4 && (c & 3) == 0 && (q4 & (q4 - 1)) == 0 && q4 <= 32, "heads: Cin must be 4 * 2^k <= 128");
+    lg = 0;
+    while ((1 << lg) < q4) ++lg;
+    return LF_OK;
+}
+
+}  // namespace lf
+
+extern "C" int lf_heads_fwd(const float* x, const float* w, const float* bias, float* y, int64_t positions, int c, int h,
+                            float scale, void* stream) {
+    LF_CHECK_ARG(x && w && y, "heads_fwd: null pointer");
+    int lg;
+    if (int e = lf::heads_check(positions, c, h, lg)) return e;
+    const int64_t units = positions * (c >> 2);
+    int64_t blocks = (units + 255) / 256;
+    const int64_t cap = (int64_t)lf::sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    lf::heads_fwd_kernel<<<(unsigned)blocks, 256, (size_t)h * c * sizeof(float), (cudaStream_t)stream>>>(
+        x, w, bias, y, positions, c, h, lg, scale);
+    LF_RETURN_LAUNCH();
+}
+
+extern "C" int lf_heads_bwd(const float* g, const float* w, float* gx, int64_t positions, int c, int h, float scale,
+                            void* stream) {
+    LF_CHECK_ARG(g && w && gx, "heads_bwd: null pointer");
+    int lg;
+    if (int e = lf::heads_check(positions, c, h, lg)) return e;
+    const int64_t units = positions * (c >> 2);
+    int64_t blocks = (units + 255) / 256;
+    const int64_t cap = (int64_t)lf::sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    lf::heads_bwd_kernel<<<(unsigned)blocks, 256, (size_t)h * c * sizeof(float), (cudaStream_t)stream>>>(
+        g, w, gx, positions, c, h, lg, scale);
+    LF_RETURN_LAUNCH();
+}

@@ -716,6 +716,65 @@ def plateau_step_(rank_loss, lr, best, num_bad, threshold, patience, factor):
 
 
 # ------------------------------------------------------------------------------------------------
+# fused 1x1 output heads
+# ------------------------------------------------------------------------------------------------
+class _Heads(torch.autograd.Function):
+    """All 1x1 output heads of a decoder in one pass over its feature map (exact fp32).  weight [H, C] is the
+    row-stack of the heads' [Cout_i, C, 1, 1] weights; every head has fan-in C, hence one He constant."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _need_cuda(x, weight, bias)
+        x = to_cl(x)
+        n, c, hh, ww = x.shape
+        h = weight.shape[0]
+        scale = math.sqrt(2.0 / c)
+        wf = weight.detach().float().contiguous()
+        y = empty_cl((n, h, hh, ww), x.device)
+        _call('lf_heads_fwd', L.lib().lf_heads_fwd,
+              (_p(x), _p(wf), _p(None if bias is None else bias.detach().float().contiguous()), _p(y), n * hh * ww, c, h,
+               scale, _stream()), nbytes=4 * (x.numel() + y.numel()), flops=2 * n * hh * ww * c * h)
+        ctx.save_for_backward(x, wf)
+        ctx.scale = scale
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, wf = ctx.saved_tensors
+        gy = to_cl(gy)
+        n, c, hh, ww = x.shape
+        h = wf.shape[0]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            _call('lf_heads_bwd', L.lib().lf_heads_bwd, (_p(gy), _p(wf), _p(gx), n * hh * ww, c, h, ctx.scale, _stream()),
+                  nbytes=4 * (x.numel() + gy.numel()), flops=2 * n * hh * ww * c * h)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:       # training: tiny [H, C] reductions in torch
+            g2 = gy.permute(0, 2, 3, 1).reshape(-1, h)
+            if ctx.needs_input_grad[1]:
+                gw = (g2.t() @ x.permute(0, 2, 3, 1).reshape(-1, c)) * ctx.scale
+            if ctx.needs_input_grad[2]:
+                gb = g2.sum(dim=0)
+        return gx, gw, gb
+
+
+def heads_supported(c, h):
+    q4 = c // 4
+    return c % 4 == 0 and c >= 4 and (q4 & (q4 - 1)) == 0 and q4 <= 32 and 1 <= h <= 8
+
+
+def fused_heads(x, weights, biases):
+    """x [N,C,H,W]; weights: list of [Cout_i, C, 1, 1]; biases: list of [Cout_i] or None -> [N, sum Cout_i, H, W]."""
+    c = x.shape[1]
+    w = torch.cat([wi.reshape(wi.shape[0], c) for wi in weights], dim=0)
+    if all(b is None for b in biases):
+        b = None
+    else:
+        b = torch.cat([bi if bi is not None else wi.new_zeros(wi.shape[0]) for wi, bi in zip(weights, biases)], dim=0)
+    return _Heads.apply(x, w, b)
+
+
+# ------------------------------------------------------------------------------------------------
 # IBR colour branch (forward only)
 # ------------------------------------------------------------------------------------------------
 IBR_CAM_STRIDE = 48

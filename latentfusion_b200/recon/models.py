@@ -256,8 +256,18 @@ class Photographer(_Checkpointable, nn.Module):
             z = z.sum(dim=2)
         y = self.image_decoder(z)
         if len(self.output_blocks):
-            y = torch.cat([head(y) for head in self.output_blocks], dim=1)
+            y = self._heads(y)
         return y, (z if return_latent else None), z_depth
+
+    def _heads(self, features):
+        """depth / mask / colour logits: one pass for all heads when they are plain 1x1 convolutions"""
+        convs = [head.conv for head in self.output_blocks]
+        plain = all(head.activation is None and conv.module.kernel_size == (1, 1)
+                    for head, conv in zip(self.output_blocks, convs))
+        if (plain and features.is_cuda
+                and ops.heads_supported(features.shape[1], sum(conv.module.out_channels for conv in convs))):
+            return ops.fused_heads(features, [conv.module.weight for conv in convs], [conv.bias for conv in convs])
+        return torch.cat([head(features) for head in self.output_blocks], dim=1)
 
     def interpret_logits(self, logits, apply_mask=False):
         """split the head channels and squash them: colour/depth tanh, mask sigmoid; without a mask head the mask is

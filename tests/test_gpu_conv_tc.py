@@ -215,3 +215,24 @@ def test_epilogue_fused_actnorm_backward_matches_separate_kernels(precision):
     assert n_fused.count('lf_actnorm_bwd') == 1 and sum('bwd_data_epi' in n for n in n_fused) == 2, n_fused
     tol = dict(atol=2e-5, rtol=1e-4) if precision == 1 else dict(atol=2e-3, rtol=2e-3)
     torch.testing.assert_close(g_fused, g_sep, **tol)
+
+
+@pytest.mark.parametrize('c,heads', [(32, (1, 1)), (64, (3, 1, 1)), (8, (1,)), (128, (1, 1))])
+def test_fused_output_heads_match_separate_1x1_convs(c, heads):
+    """lf_heads_fwd/bwd (all 1x1 output heads of the decoder in one pass) against the per-head exact-fp32 convolutions
+    concatenated along channels, forward, backward to the features and the training gradients of weights and biases."""
+    dev = torch.device('cuda:0')
+    torch.manual_seed(c + len(heads))
+    x = torch.randn(3, c, 20, 17, device=dev)
+    ws = [torch.randn(h, c, 1, 1, device=dev, requires_grad=True) for h in heads]
+    bs = [(torch.randn(h, device=dev) * 0.1).requires_grad_(True) for h in heads]
+    xa = x.clone().requires_grad_(True)
+    ya = ops.fused_heads(xa, ws, bs)
+    xb = x.clone().requires_grad_(True)
+    yb = torch.cat([ops.eq_conv(xb, w, b, precision=0) for w, b in zip(ws, bs)], dim=1)
+    torch.testing.assert_close(ya, yb, atol=1e-5, rtol=1e-5)
+    g = torch.randn_like(ya)
+    ga = torch.autograd.grad(ya, [xa] + ws + bs, g)
+    gb = torch.autograd.grad(yb, [xb] + ws + bs, g)
+    for a, b in zip(ga, gb):
+        torch.testing.assert_close(a, b, atol=2e-4, rtol=1e-4)
