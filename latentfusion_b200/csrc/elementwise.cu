@@ -36,13 +36,15 @@ struct InterpGeom {
     int mode;
 };
 
-template <bool BWD>
+template <bool BWD, int VEC>
 __global__ void interp_kernel(const InterpGeom g, const float* __restrict__ src, float* __restrict__ dst) {
-    // forward: src = x, dst = y (gather).  backward: src = gy, dst = gx (scatter with atomics; gx zeroed).
-    const int64_t total = (int64_t)g.n * g.od * g.oh * g.ow * g.c;
+    // forward: src = x, dst = y (gather).  backward: src = gy, dst = gx (scatter with reductions; gx zeroed).
+    // VEC = 4 when C % 4 == 0: one thread moves 4 channels with 128-bit loads/stores/reductions.
+    const int cv = g.c / VEC;
+    const int64_t total = (int64_t)g.n * g.od * g.oh * g.ow * cv;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = e;
-        const int c = (int)(r % g.c); r /= g.c;
+        const int c = (int)(r % cv) * VEC; r /= cv;
         const int ox = (int)(r % g.ow); r /= g.ow;
         const int oy = (int)(r % g.oh); r /= g.oh;
         const int oz = (int)(r % g.od); r /= g.od;
@@ -51,8 +53,13 @@ __global__ void interp_kernel(const InterpGeom g, const float* __restrict__ src,
         const Tap ty = axis_tap(oy, g.h, g.mode, g.fh);
         const Tap tx = axis_tap(ox, g.w, g.mode, g.fw);
         const int64_t base = (int64_t)n * g.d;
-        float accv = 0.f;
-        const float gyv = BWD ? src[e] : 0.f;
+        float acc[VEC], gv[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { acc[j] = 0.f; gv[j] = 0.f; }
+        if (BWD) {
+            if (VEC == 4) { const float4 t = ldg4(src + e * 4); gv[0] = t.x; gv[1] = t.y; gv[2] = t.z; gv[3] = t.w; }
+            else gv[0] = src[e];
+        }
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
             const float wz = a ? tz.w1 : tz.w0; const int iz = a ? tz.i1 : tz.i0;
@@ -65,13 +72,25 @@ __global__ void interp_kernel(const InterpGeom g, const float* __restrict__ src,
                 for (int q = 0; q < 2; ++q) {
                     const float wx = q ? tx.w1 : tx.w0; const int ix = q ? tx.i1 : tx.i0;
                     if (wx == 0.f) continue;
+                    const float wgt = wz * wy * wx;
                     const int64_t idx = (((base + iz) * g.h + iy) * g.w + ix) * g.c + c;
-                    if (BWD) atomicAdd(dst + idx, gyv * (wz * wy * wx));
-                    else accv += (wz * wy * wx) * src[idx];
+                    if (BWD) {
+                        if (VEC == 4) atomicAdd(reinterpret_cast<float4*>(dst + idx),
+                                                make_float4(gv[0] * wgt, gv[1] * wgt, gv[2] * wgt, gv[3] * wgt));
+                        else atomicAdd(dst + idx, gv[0] * wgt);
+                    } else if (VEC == 4) {
+                        const float4 t = ldg4(src + idx);
+                        acc[0] += wgt * t.x; acc[1] += wgt * t.y; acc[2] += wgt * t.z; acc[3] += wgt * t.w;
+                    } else {
+                        acc[0] += wgt * src[idx];
+                    }
                 }
             }
         }
-        if (!BWD) dst[e] = accv;
+        if (!BWD) {
+            if (VEC == 4) *reinterpret_cast<float4*>(dst + e * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            else dst[e] = acc[0];
+        }
     }
 }
 
@@ -190,7 +209,8 @@ extern "C" int lf_interp_fwd(const float* x, float* y, int ndim, int n, int d, i
     if (int e = interp_geom(g, ndim, n, d, h, w, c, mode, factor)) return e;
     LF_CHECK_ARG(x && y, "interp: null pointer");
     const int64_t total = (int64_t)g.n * g.od * g.oh * g.ow * g.c;
-    interp_kernel<false><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(g, x, y);
+    if ((g.c & 3) == 0) interp_kernel<false, 4><<<ew_grid(total / 4), 256, 0, (cudaStream_t)stream>>>(g, x, y);
+    else interp_kernel<false, 1><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(g, x, y);
     LF_RETURN_LAUNCH();
 }
 
@@ -201,7 +221,8 @@ extern "C" int lf_interp_bwd(const float* gy, float* gx, int ndim, int n, int d,
     LF_CHECK_ARG(gy && gx, "interp: null pointer");
     const int64_t total = (int64_t)g.n * g.od * g.oh * g.ow * g.c;
     cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)g.n * g.d * g.h * g.w * g.c, (cudaStream_t)stream);
-    interp_kernel<true><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(g, gy, gx);
+    if ((g.c & 3) == 0) interp_kernel<true, 4><<<ew_grid(total / 4), 256, 0, (cudaStream_t)stream>>>(g, gy, gx);
+    else interp_kernel<true, 1><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(g, gy, gx);
     LF_RETURN_LAUNCH();
 }
 
