@@ -250,6 +250,7 @@ def _unpack_weight_grad(gw, weight_shape, kind, depth):
     return gw.permute(2, 0, 1).reshape(-1, cin, 1, 1).contiguous()            # [c][d][ci]
 
 
+_bwd_precision_override = None     # dev/experiments: force the precision of every bwd-data convolution
 _FUSE_BWD = _os.environ.get('LFB200_FUSE_BWD', '0') == '1'
 _TC_PACK_CACHE = {}
 
@@ -395,6 +396,8 @@ class _EqConv(torch.autograd.Function):
         lib = L.lib()
         if precision == PRECISION_MIXED:
             precision = PRECISION_BF16
+        if _bwd_precision_override is not None:
+            precision = _bwd_precision_override
         need_w = ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2])
         gx = gw = gb = None
         du = None

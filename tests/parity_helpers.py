@@ -119,9 +119,18 @@ def cam_to_dict(cam):
     return {k: getattr(cam, k).detach().cpu().clone() for k in ('intrinsic', 'log_quaternion', 'translation', 'viewport')}
 
 
-def smoke_check():
+def smoke_check(precision=None):
     """Tiny render fwd + loss + bwd-to-camera on cuda:0 against (a) the golden vectors produced by the
-    unmodified reference and (b) the CPU oracle."""
+    unmodified reference and (b) the CPU oracle.  `precision` selects the convolution path for the duration of the
+    check (1 = the tcgen05 bf16x3 kernels bench.py times; None = leave the process default alone)."""
+    from latentfusion_b200 import ops
+    if precision is not None:
+        old = ops.get_default_precision()
+        ops.set_default_precision(precision)
+        try:
+            return smoke_check(None)
+        finally:
+            ops.set_default_precision(old)
     from oracle import lf_oracle as O
     from latentfusion_b200.pose import estimation
     from latentfusion_b200.observation import Observation
@@ -181,3 +190,47 @@ def assert_grad_close_to_fp64(ours, g32, g64, what=''):
     err = (ours.double() - g64).abs().max()
     bound = max(3.0 * float(err32), 2e-3 * float(scale))
     assert float(err) <= bound, f'{what}: |ours - fp64| = {float(err):.4g} > {bound:.4g} (fp32 reference error {float(err32):.4g}, scale {float(scale):.4g})'
+
+
+GOLDEN_B = os.path.join(ROOT, 'tests', 'golden', 'configB_s64_c32.npz')
+
+
+GOLDEN_B_SMOOTH = os.path.join(ROOT, 'tests', 'golden', 'configB_s64_c32_smooth.npz')
+
+
+def config_b_cube(C, S, smooth):
+    """oracle/make_golden_configB.py:make_cube — white noise, or the same noise low-pass filtered (5^3 box)."""
+    import torch.nn.functional as F
+    torch.manual_seed(5)
+    z = torch.randn(1, C, S, S, S)
+    if smooth:
+        z = F.avg_pool3d(F.pad(z, (2, 2, 2, 2, 2, 2), mode='replicate'), 5, stride=1)
+        z = z / z.std()
+    return z * 0.5
+
+
+def config_b_case(dev, smooth=False):
+    """The benchmarked configuration (BASELINE configs[1]: LF-synth(64, 32), 128^2 render) as pinned by
+    oracle/make_golden_configB.py from the unmodified reference: (golden, model, z_obj, target observation)."""
+    from latentfusion_b200.observation import Observation
+    from latentfusion_b200.recon import fusion, models
+    from latentfusion_b200.recon.inference import LatentFusionModel
+    from latentfusion_b200.utils import parse_block_config as pbc
+    g = Golden(GOLDEN_B_SMOOTH if smooth else GOLDEN_B)
+    S, C = g.meta['S'], g.meta['C']
+    photographer = models.Photographer(**g.meta['arch_photographer'])
+    photographer.load_state_dict(g.state_dict('photographer'), strict=True)
+    sculptor = models.Sculptor(in_size=2 * S, image_config=pbc(f"{C},D,{2*C}:{2*C},{2*C}"), camera_config=pbc(f"{C},{C}"),
+                               object_config=pbc(f"{C},{C}"), projection_type='factor', input_color=True,
+                               input_depth=False, input_mask=True, scale_mode='nearest')
+    fuser = fusion.get_fuser('pool:mean', C, 1.0)
+    model = LatentFusionModel(sculptor.to(dev), fuser.to(dev), photographer.to(dev), g.meta['camera_dist'], dev)
+    z_obj = config_b_cube(C, S, smooth).unsqueeze(0)
+    chk = g['z_obj.checksum']
+    assert abs(float(z_obj.double().sum()) - float(chk[0])) < 1e-6 * float(chk[1]), 'torch CPU generator drifted'
+    t = g.meta['target']
+    yy, xx = torch.meshgrid(torch.arange(480, dtype=torch.float32), torch.arange(640, dtype=torch.float32), indexing='ij')
+    tmask = (((yy - t['cy']) ** 2 + (xx - t['cx']) ** 2) <= t['radius'] ** 2).float().view(1, 1, 480, 640)
+    gt = product_camera(g.cam('gt_cam'), dev)
+    target = Observation(torch.zeros(1, 3, 480, 640, device=dev), (tmask * g.meta['camera_dist']).to(dev), tmask.to(dev), gt)
+    return g, model, z_obj.to(dev), target
