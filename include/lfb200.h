@@ -99,6 +99,29 @@ typedef struct {
 
 int lf_conv_fwd(const lf_conv_desc* desc, const float* x, const float* w, const float* bias,
                 float* y, float* rnorm, void* stream);
+/* ---- depth-batched tcgen05 3x3x3 convolution on split-planar activations (csrc/conv3d_dz.cu) ----
+ * Same reference op as lf_conv_fwd with ndim = 3, k = 3 (modules/equalized.py:57-64 + blocks.py:152-158), for
+ * Cout <= 32 (Cout % 4 == 0), precision 1 (bf16x3 in ONE pass) or 2 (bf16).  Activations travel between
+ * convolutions in the library's internal "split-planar" layout
+ *     [part: hi | lo][N][D][C_pad/8][H+2][W+2][8] bf16      (x ~ hi + lo; zero halo; C_pad = C rounded up to 16)
+ * which a kernel stages with 1-D bulk TMA copies (cp.async.bulk).  lf_split_bytes gives the buffer size in bytes,
+ * lf_split_pack converts a dense channels-last fp32 tensor [N][D][H][W][C] into it (halo and padding channels zeroed).
+ * lf_conv3d_dz reads x_split and writes y32 (fp32 channels-last [N][D][H][W][Cout], nullable) and/or y_split
+ * (split-planar with Cout channels, nullable; the kernel writes its whole halo) and rnorm (nullable).
+ * `w_packed` comes from lf_conv3d_dz_pack_weights applied to the [27][Cin][Cout] fp32 pack (tap = (dz*3+dy)*3+dx).
+ * Error contract of every tcgen05 kernel: all mbarrier waits are bounded; a pipeline fault prints one line and
+ * traps (cudaErrorLaunchFailure at the next synchronisation) instead of hanging the device. */
+int lf_conv3d_dz_supported(const lf_conv_desc* desc);
+int64_t lf_split_bytes(int n, int d, int h, int w, int c);
+int lf_split_pack(const float* x, void* out_split, int n, int d, int h, int w, int c, void* stream);
+int64_t lf_conv3d_dz_weight_bytes(int cin, int cout);
+int lf_conv3d_dz_pack_weights(const float* w27, void* out, int cin, int cout, void* stream);
+int lf_conv3d_dz(const lf_conv_desc* desc, const void* x_split, const void* w_packed, const float* bias,
+                 float* y32, void* y_split, float* rnorm, void* stream);
+/* diagnostic: same launch, plus SM-clock stamps of CTA 0's pipeline roles in `stamps` (device, 4*64*2 int64) */
+int lf_conv3d_dz_timeline(const lf_conv_desc* desc, const void* x_split, const void* w_packed, const float* bias,
+                          float* y32, void* y_split, float* rnorm, void* stamps, void* stream);
+
 /* tcgen05 path (precision 1|2): `w` passed to lf_conv_fwd must point to weights pre-packed by
  * lf_conv_tc_pack_weights (bf16 hi part followed by the bf16 lo part, UMMA no-swizzle K-major layout
  * [part][tap][Cin_pad/8][Cout_pad][8]); lf_conv_tc_weight_bytes gives the buffer size.  Shapes the

@@ -42,6 +42,13 @@ _SIGNATURES = {
     'lf_resample_c2o_fwd': (c_int, [c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_vp]),
     'lf_resample_c2o_bwd_vol': (c_int, [c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_vp]),
     'lf_conv_fwd': (c_int, [ctypes.POINTER(ConvDesc), c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_vp]),
+    'lf_conv3d_dz_supported': (c_int, [ctypes.POINTER(ConvDesc)]),
+    'lf_split_bytes': (c_i64, [c_int] * 5),
+    'lf_split_pack': (c_int, [c_f32p, c_vp] + [c_int] * 5 + [c_vp]),
+    'lf_conv3d_dz_weight_bytes': (c_i64, [c_int, c_int]),
+    'lf_conv3d_dz_pack_weights': (c_int, [c_f32p, c_vp, c_int, c_int, c_vp]),
+    'lf_conv3d_dz': (c_int, [ctypes.POINTER(ConvDesc), c_vp, c_vp, c_f32p, c_f32p, c_vp, c_f32p, c_vp]),
+    'lf_conv3d_dz_timeline': (c_int, [ctypes.POINTER(ConvDesc), c_vp, c_vp, c_f32p, c_f32p, c_vp, c_f32p, c_vp, c_vp]),
     'lf_conv_tc_weight_bytes': (c_i64, [c_int, c_int, c_int]),
     'lf_conv_tc_pack_weights': (c_int, [c_f32p, c_vp, c_int, c_int, c_int, c_vp]),
     'lf_conv_tc_supported': (c_int, [ctypes.POINTER(ConvDesc)]),

@@ -97,7 +97,8 @@ class Block(nn.Module):
 
     def forward(self, x):
         slope = self.activation.negative_slope
-        x = self.conv1(x, act=True, slope=slope, norm=True)
+        # (3-D: conv1's epilogue also leaves the split-planar form conv2's TMA staging reads)
+        x = self.conv1(x, act=True, slope=slope, norm=True, emit_split=isinstance(self.conv1, EqualizedConv3d))
         # conv2 is the only consumer of conv1's output: its bwd-data kernel can apply conv1's activation/norm backward
         x = self.conv2(ops.mark_single_consumer(x), act=True, slope=slope, norm=True)
         if self.interpolate is not None:

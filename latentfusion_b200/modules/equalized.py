@@ -43,6 +43,10 @@ class Equalized(nn.Module):
             raise ValueError(f"lfb200 convolutions support k=1/pad=0 and k=3/pad=1, got k={kernel_size} pad={padding}")
         if not equalized:
             raise ValueError("only the equalised form is used on the path")
+        if lr_scale != 1.0:
+            # reference equalized.py:44-47 rescales the stored weights by 1/lr_scale and the run-time constant by
+            # lr_scale; nothing on the path passes it, and the fused kernels recompute sqrt(2/fan_in) themselves
+            raise ValueError("lfb200 convolutions support lr_scale=1.0 only")
         self.module = _ConvParams(in_channels, out_channels, kernel_size, self.ndim, padding)
         self.equalized = equalized
         if bias:
@@ -57,9 +61,9 @@ class Equalized(nn.Module):
     def get_he_constant(self):
         return math.sqrt(2.0 / math.prod(self.module.weight.shape[1:]))
 
-    def forward(self, x, act=False, slope=0.2, norm=False):
+    def forward(self, x, act=False, slope=0.2, norm=False, emit_split=False):
         return ops.eq_conv(x, self.module.weight, self.bias, act=act, slope=slope, norm=norm,
-                           precision=self.precision)
+                           precision=self.precision, emit_split=emit_split)
 
 
 class EqualizedConv2d(Equalized):

@@ -32,8 +32,11 @@ def get_default_precision():
     return _default_precision
 
 
+_active_device = None      # device of the tensors of the op being issued (set by _need_cuda)
+
+
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch.cuda.current_stream(_active_device).cuda_stream)
 
 
 class KernelTrace:
@@ -63,7 +66,12 @@ class KernelTrace:
 
 
 def _call(name, fn, args, kernels=1, nbytes=0, flops=0):
-    """Invoke one C-ABI entry point, optionally bracketed by CUDA events on the current stream."""
+    """Invoke one C-ABI entry point, optionally bracketed by CUDA events on the current stream.  The library launches
+    on the CUDA runtime's current device: when the tensors live elsewhere (model on cuda:1 without set_device), the
+    call is issued under a device guard, like a PyTorch op would."""
+    if _active_device is not None and _active_device.index != torch.cuda.current_device():
+        with torch.cuda.device(_active_device):
+            return _call(name, fn, args, kernels, nbytes, flops)
     KernelTrace.launches += kernels
     if KernelTrace.enabled:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -81,10 +89,21 @@ def _p(t):
 
 
 def _need_cuda(*tensors):
+    """every tensor argument must be on ONE CUDA device; remembers it for the launches that follow"""
+    global _active_device
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("latentfusion_b200: tensors must live on a CUDA device "
                                "(the hot path is sm_100a CUDA only; there is no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"latentfusion_b200: tensors of one op live on different devices ({dev} and {t.device})")
+    if dev is not None:
+        _active_device = dev
 
 
 def _mf(ndim):
@@ -128,6 +147,7 @@ class _ResampleO2C(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         vol, cam = ctx.saved_tensors
+        _need_cuda(gout, vol)
         gout = to_cl(gout)
         B, C, S = vol.shape[0], vol.shape[1], vol.shape[-1]
         N = cam.shape[0]
@@ -172,6 +192,7 @@ class _ResampleC2O(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         (cam,) = ctx.saved_tensors
+        _need_cuda(gout, cam)
         V, C, S = ctx.shape
         gvol = None
         if ctx.needs_input_grad[0]:
@@ -200,6 +221,15 @@ KIND_CONV, KIND_COLLAPSE, KIND_EXPAND = 0, 1, 2
 _PACK_CACHE = {}
 
 
+def _cache_put(cache, key, value, limit):
+    """insert; when the cache is over its limit, drop the entries whose parameter object is dead (never a live
+    entry: captured CUDA graphs and saved-for-backward tensors hold raw pointers into live packs)."""
+    if len(cache) >= limit:
+        for k in [k for k, v in cache.items() if v[0]() is None]:
+            del cache[k]
+    cache[key] = value
+
+
 def _pack_weight_cached(weight, kind, depth):
     """_pack_weight memoised per live parameter object and version (weights are frozen in the pose loop, so the
     flip/permute kernels run once, not once per convolution call)."""
@@ -208,9 +238,7 @@ def _pack_weight_cached(weight, kind, depth):
     if hit is not None and hit[0]() is weight:
         return hit[1], hit[2]
     wf, wb = _pack_weight(weight.detach(), kind, depth)
-    if len(_PACK_CACHE) > 512:
-        _PACK_CACHE.clear()
-    _PACK_CACHE[key] = (weakref.ref(weight), wf, wb)
+    _cache_put(_PACK_CACHE, key, (weakref.ref(weight), wf, wb), 512)
     return wf, wb
 
 
@@ -255,6 +283,15 @@ _FUSE_BWD = _os.environ.get('LFB200_FUSE_BWD', '0') == '1'
 _TC_PACK_CACHE = {}
 
 
+def _cache_put(cache, key, value, limit):
+    """insert; when the cache is over its limit, drop the entries whose parameter object is dead (never a live
+    entry: captured CUDA graphs and saved-for-backward tensors hold raw pointers into live packs)."""
+    if len(cache) >= limit:
+        for k in [k for k, v in cache.items() if v[0]() is None]:
+            del cache[k]
+    cache[key] = value
+
+
 def _tc_pack(wf, key):
     """fp32 packed weights [taps][Cin][Cout] -> bf16 hi|lo UMMA layout for the tcgen05 kernel (cached per
     parameter version; the pack itself is one small kernel)."""
@@ -265,9 +302,7 @@ def _tc_pack(wf, key):
     nbytes = L.lib().lf_conv_tc_weight_bytes(taps, cin, cout)
     out = torch.empty(nbytes // 2, device=wf.device, dtype=torch.int16)
     _call('lf_conv_tc_pack_weights', L.lib().lf_conv_tc_pack_weights, (_p(wf), _p(out), taps, cin, cout, _stream()))
-    if len(_TC_PACK_CACHE) > 256:
-        _TC_PACK_CACHE.clear()
-    _TC_PACK_CACHE[key[1:]] = (weakref.ref(key[0]), out)
+    _cache_put(_TC_PACK_CACHE, key[1:], (weakref.ref(key[0]), out), 256)
     return out
 
 
@@ -288,6 +323,73 @@ def _desc(kind, nd, n, d, h, w, cin, cout, k, scale, act, slope, norm, precision
 def _conv_name(kind, nd, k, what):
     tag = {KIND_CONV: f'conv{nd}d_k{k}', KIND_COLLAPSE: 'collapse', KIND_EXPAND: 'expand'}[kind]
     return f'lf_conv_{what}[{tag}]'
+
+
+# ------------------------------------------------------------------------------------------------
+# depth-batched tcgen05 3x3x3 convolution on split-planar activations (csrc/conv3d_dz.cu)
+# ------------------------------------------------------------------------------------------------
+class SplitVol:
+    """A feature volume in the library's internal split-planar layout ([hi|lo][N][D][C_pad/8][H+2][W+2][8] bf16,
+    zero halo): what the depth-batched convolution stages with bulk TMA copies.  `buf` is an int16 device tensor."""
+    __slots__ = ('buf', 'n', 'c', 'd', 'h', 'w')
+
+    def __init__(self, buf, n, c, d, h, w):
+        self.buf, self.n, self.c, self.d, self.h, self.w = buf, n, c, d, h, w
+
+    @staticmethod
+    def empty(n, c, d, h, w, device):
+        nbytes = L.lib().lf_split_bytes(n, d, h, w, c)
+        return SplitVol(torch.empty(nbytes // 2, device=device, dtype=torch.int16), n, c, d, h, w)
+
+    def to_dense(self):
+        """fp32 [N,C,D,H,W] (tests / debugging): hi + lo of the interior."""
+        cp = (self.c + 15) // 16 * 16
+        v = self.buf.view(torch.bfloat16).view(2, self.n, self.d, cp // 8, self.h + 2, self.w + 2, 8).float()
+        v = (v[0] + v[1])[:, :, :, 1:-1, 1:-1, :]                       # [n, d, kc, h, w, 8]
+        return v.permute(0, 2, 5, 1, 3, 4).reshape(self.n, cp, self.d, self.h, self.w)[:, :self.c]
+
+
+def split_pack(x):
+    """dense fp32 [N,C,D,H,W] (any memory format) -> SplitVol."""
+    _need_cuda(x)
+    x = to_cl(x)
+    n, c, d, h, w = x.shape
+    out = SplitVol.empty(n, c, d, h, w, x.device)
+    _call('lf_split_pack', L.lib().lf_split_pack, (_p(x), _p(out.buf), n, d, h, w, c, _stream()),
+          nbytes=4 * x.numel() + out.buf.numel() * 2)
+    return out
+
+
+def _dz_pack(wf, key):
+    """[27][Cin][Cout] fp32 -> the depth-batched kernel's bf16 hi|lo weight layout (cached like _tc_pack)."""
+    hit = _TC_PACK_CACHE.get(key[1:])
+    if hit is not None and hit[0]() is key[0]:
+        return hit[1]
+    taps, cin, cout = wf.shape
+    out = torch.empty(L.lib().lf_conv3d_dz_weight_bytes(cin, cout) // 2, device=wf.device, dtype=torch.int16)
+    _call('lf_conv3d_dz_pack_weights', L.lib().lf_conv3d_dz_pack_weights, (_p(wf), _p(out), cin, cout, _stream()))
+    _cache_put(_TC_PACK_CACHE, key[1:], (weakref.ref(key[0]), out), 256)
+    return out
+
+
+def _dz_ok(desc):
+    return desc.precision in (1, 2) and bool(L.lib().lf_conv3d_dz_supported(ctypes.byref(desc)))
+
+
+def conv3d_dz(xs, wpk, bias, cout, scale, act, slope, norm, precision, want_dense=True, want_split=False,
+              name='lf_conv3d_dz'):
+    """one launch of the depth-batched kernel: SplitVol -> (dense fp32 channels-last | None, SplitVol | None, rnorm | None)"""
+    desc = _desc(KIND_CONV, 3, xs.n, xs.d, xs.h, xs.w, xs.c, cout, 3, scale, act, slope, norm, precision)
+    dev = xs.buf.device
+    y = empty_cl((xs.n, cout, xs.d, xs.h, xs.w), dev) if want_dense else None
+    ys = SplitVol.empty(xs.n, cout, xs.d, xs.h, xs.w, dev) if want_split else None
+    rnorm = torch.empty(xs.n * xs.d * xs.h * xs.w, device=dev, dtype=torch.float32) if norm else None
+    positions = xs.n * xs.d * xs.h * xs.w
+    _call(name, L.lib().lf_conv3d_dz,
+          (ctypes.byref(desc), _p(xs.buf), _p(wpk), _p(bias), _p(y), _p(None if ys is None else ys.buf), _p(rnorm), _stream()),
+          nbytes=xs.buf.numel() * 2 + (4 * y.numel() if y is not None else 0) + (ys.buf.numel() * 2 if ys is not None else 0),
+          flops=2 * positions * 27 * xs.c * cout)
+    return y, ys, rnorm
 
 
 class _ActRec:
@@ -320,9 +422,11 @@ class _EqConv(torch.autograd.Function):
     """y = PixelNorm(LeakyReLU(conv(x, W) * he + b)) in one kernel.
     Reference: modules/equalized.py:57-64 + blocks.py:152-158 + modules/__init__.py:14-15."""
     last_rec = None        # _ActRec of the most recent forward, picked up by eq_conv() to tag the returned tensor
+    last_split = None      # split-planar twin of the most recent forward's output (when asked for), tagged likewise
 
     @staticmethod
-    def forward(ctx, x, weight, bias, kind, depth, act, slope, norm, precision, fan_in=None, rec_in=None):
+    def forward(ctx, x, weight, bias, kind, depth, act, slope, norm, precision, fan_in=None, rec_in=None,
+                x_split=None, emit_split=False):
         _need_cuda(x, weight, bias)
         x = to_cl(x)
         dev = x.device
@@ -364,21 +468,31 @@ class _EqConv(torch.autograd.Function):
             bpk = bias.detach().float().reshape(cout, d).t().contiguous()
         else:
             bpk = bias.detach().float().contiguous()
-        y = empty_cl(out_shape, dev)
-        rnorm = torch.empty(positions, device=dev, dtype=torch.float32) if norm else None
         desc = _desc(kind, nd, n, d, h, w, gcin, gcout, k, scale, act, slope, norm,
                      PRECISION_BF16X3 if precision == PRECISION_MIXED else precision)
+        use_dz = kind == KIND_CONV and nd == 3 and k == 3 and _dz_ok(desc)
+        y = None if use_dz else empty_cl(out_shape, dev)
+        rnorm = torch.empty(positions, device=dev, dtype=torch.float32) if (norm and not use_dz) else None
         taps = wf.shape[0]
         wkey = (weight, id(weight), weight._version, kind)
-        if _tc_ok(desc):
-            wf_arg = _tc_pack(wf, wkey + ('f',))
-        else:                      # shapes the tensor-core kernel does not cover run on the exact fp32 path
-            desc.precision = 0
-            wf_arg = wf
-        _call(_conv_name(kind, nd, k, 'fwd'), L.lib().lf_conv_fwd,
-              (ctypes.byref(desc), _p(x), _p(wf_arg), _p(bpk), _p(y), _p(rnorm), _stream()),
-              kernels=(2 if (norm and (kind == KIND_EXPAND or gcout > 64)) else 1) if desc.precision != 1 else _tc_passes(desc),
-              nbytes=4 * (x.numel() + y.numel()), flops=2 * positions * taps * gcin * gcout)
+        _EqConv.last_split = None
+        if use_dz:
+            # depth-batched tcgen05 kernel on split-planar activations (one launch for bf16x3); the producer may have
+            # left the split-planar form of x next to it (x_split), otherwise it is packed here
+            xs = x_split if x_split is not None else split_pack(x)
+            y, ys, rnorm = conv3d_dz(xs, _dz_pack(wf, wkey + ('dzf',)), bpk, gcout, scale, act, slope, norm, desc.precision,
+                                     want_dense=True, want_split=emit_split, name=_conv_name(kind, nd, k, 'fwd'))
+            _EqConv.last_split = ys
+        else:
+            if _tc_ok(desc):
+                wf_arg = _tc_pack(wf, wkey + ('f',))
+            else:                      # shapes the tensor-core kernel does not cover run on the exact fp32 path
+                desc.precision = 0
+                wf_arg = wf
+            _call(_conv_name(kind, nd, k, 'fwd'), L.lib().lf_conv_fwd,
+                  (ctypes.byref(desc), _p(x), _p(wf_arg), _p(bpk), _p(y), _p(rnorm), _stream()),
+                  kernels=(2 if (norm and (kind == KIND_EXPAND or gcout > 64)) else 1) if desc.precision != 1 else _tc_passes(desc),
+                  nbytes=4 * (x.numel() + y.numel()), flops=2 * positions * taps * gcin * gcout)
         ctx.save_for_backward(x, y, rnorm, wb)
         ctx.wkey = wkey
         ctx.rec_in = rec_in
@@ -391,6 +505,7 @@ class _EqConv(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x, y, rnorm, wb = ctx.saved_tensors
+        _need_cuda(gy, x)
         (kind, depth, act, slope, norm, precision, nd, n, d, h, w, cin, cout, k, scale, wshape, has_bias) = ctx.cfg
         gy = to_cl(gy)
         lib = L.lib()
@@ -400,7 +515,7 @@ class _EqConv(torch.autograd.Function):
             precision = _bwd_precision_override
         need_w = ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2])
         gx = gw = gb = None
-        du = None
+        du = du_split = None
         bkind = {KIND_CONV: KIND_CONV, KIND_COLLAPSE: KIND_EXPAND, KIND_EXPAND: KIND_COLLAPSE}[kind]
         bnd = {KIND_CONV: nd, KIND_COLLAPSE: 2, KIND_EXPAND: 3}[kind]
         bdesc = _desc(bkind, bnd, n, d, h, w, cout, cin, k, scale, 0, 0.0, 0, precision)
@@ -449,6 +564,11 @@ class _EqConv(torch.autograd.Function):
                       kernels=1 if bkind == KIND_EXPAND else _tc_passes(bdesc),
                       nbytes=4 * (du.numel() + 2 * gx.numel()), flops=bflops)
                 rec_in.pre_applied = True
+            elif ctx.needs_input_grad[0] and kind == KIND_CONV and nd == 3 and k == 3 and _dz_ok(bdesc):
+                # bwd-data on the depth-batched kernel: flipped/transposed weights, no epilogue
+                dus = du_split if du_split is not None else split_pack(du)
+                gx, _, _ = conv3d_dz(dus, _dz_pack(wb, ctx.wkey + ('dzb',)), None, cin, scale, False, 0.0, False, bdesc.precision,
+                                     name=_conv_name(kind, nd, k, 'bwd_data'))
             elif ctx.needs_input_grad[0]:
                 gx = torch.empty_like(x)
                 # bwd-data = the same implicit GEMM with flipped/transposed weights, no epilogue
@@ -472,19 +592,26 @@ class _EqConv(torch.autograd.Function):
                 gw = _unpack_weight_grad(gwp, wshape, kind, depth)
             if has_bias and ctx.needs_input_grad[2]:
                 gb = gbp.t().reshape(-1) if kind == KIND_EXPAND else gbp.reshape(-1)
-        return gx, gw, gb, None, None, None, None, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None, None, None, None, None, None
 
 
-def eq_conv(x, weight, bias, act=False, slope=0.2, norm=False, kind=KIND_CONV, depth=0, precision=None, fan_in=None):
+def eq_conv(x, weight, bias, act=False, slope=0.2, norm=False, kind=KIND_CONV, depth=0, precision=None, fan_in=None,
+            emit_split=False):
+    """emit_split: also leave the split-planar twin of the output on the returned tensor (`_lf_split`), for a following
+    3x3x3 convolution to stage with TMA instead of re-packing (the epilogue writes it for free: the kernel is
+    tensor-bound)."""
     if precision is None:
         precision = _default_precision
     rec_in = None
     if _FUSE_EPI and getattr(x, '_lf_single_use', False) and torch.is_grad_enabled():
         rec_in = getattr(x, '_lf_actnorm', None)
-    y = _EqConv.apply(x, weight, bias, kind, depth, bool(act), float(slope), bool(norm), int(precision), fan_in, rec_in)
+    y = _EqConv.apply(x, weight, bias, kind, depth, bool(act), float(slope), bool(norm), int(precision), fan_in, rec_in,
+                      getattr(x, '_lf_split', None), bool(emit_split))
     if y.requires_grad and _EqConv.last_rec is not None:
         y._lf_actnorm = _EqConv.last_rec        # lets a single downstream lfb200 conv fuse this layer's backward
-    _EqConv.last_rec = None
+    if _EqConv.last_split is not None:
+        y._lf_split = _EqConv.last_split
+    _EqConv.last_rec = _EqConv.last_split = None
     return y
 
 
@@ -513,6 +640,7 @@ class _Interp(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         nd, n, d, h, w, c, mode, factor, xshape = ctx.cfg
+        _need_cuda(gy)
         gy = to_cl(gy)
         gx = empty_cl(xshape, gy.device)
         _call('lf_interp_bwd', L.lib().lf_interp_bwd, (_p(gy), _p(gx), nd, n, d, h, w, c, mode, factor, _stream()),
@@ -562,6 +690,7 @@ class _FusePool(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         (zf,) = ctx.saved_tensors
+        _need_cuda(gout, zf)
         B, V, P, C, kind, zshape = ctx.cfg
         g = to_cl(gout.reshape(B, *zshape[2:]))
         gz = torch.empty_like(zf)
@@ -652,6 +781,7 @@ class _PoseLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gterms):
         dl, ml, vp, tzc, td, tm, sums = ctx.saved_tensors
+        _need_cuda(gterms, dl)
         n, p, width, height, z_span, eps, dshape, mshape = ctx.cfg
         desc = L.LossDesc(n, p, width, height, z_span, eps)
         g_dl, g_ml = torch.empty_like(dl), torch.empty_like(ml)
@@ -689,6 +819,7 @@ class _CameraO2CBlock(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gblock):
         lqc, trc = ctx.saved_tensors
+        _need_cuda(gblock, lqc)
         n = lqc.shape[0]
         gb = gblock.float().contiguous()
         g_lq, g_tr = torch.empty_like(lqc), torch.empty_like(trc)
@@ -744,6 +875,7 @@ class _Heads(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x, wf = ctx.saved_tensors
+        _need_cuda(gy, x)
         gy = to_cl(gy)
         n, c, hh, ww = x.shape
         h = wf.shape[0]
