@@ -118,6 +118,16 @@ int64_t lf_conv3d_dz_weight_bytes(int cin, int cout);
 int lf_conv3d_dz_pack_weights(const float* w27, void* out, int cin, int cout, void* stream);
 int lf_conv3d_dz(const lf_conv_desc* desc, const void* x_split, const void* w_packed, const float* bias,
                  float* y32, void* y_split, float* rnorm, void* stream);
+/* bwd-data (desc: cin = forward Cout, cout = forward Cin, act = norm = 0) with the PixelNorm/LeakyReLU backward of the
+ * layer that produced the forward input fused into the epilogue (replaces lf_actnorm_bwd of that layer: its output
+ * y_prev arrives in split-planar form, rnorm_prev are its saved norms); writes du_prev dense and/or split-planar. */
+int lf_conv3d_dz_bwd_epi(const lf_conv_desc* desc, const void* du_split, const void* w_packed,
+                         const void* y_prev_split, const float* rnorm_prev, int prev_act, float prev_slope,
+                         int prev_norm, float* du_prev32, void* du_prev_split, void* stream);
+/* lf_actnorm_bwd for a 3-D layer with C in {16, 32} that writes du in split-planar form (du_split, with its zero halo)
+ * for the layer's bwd-data convolution, and dense fp32 too when `du` is non-null. */
+int lf_actnorm_bwd_split(const float* gy, const float* y, const float* rnorm, float* du, void* du_split,
+                         int n, int d, int h, int w, int c, int act, float slope, int norm, void* stream);
 /* diagnostic: same launch, plus SM-clock stamps of CTA 0's pipeline roles in `stamps` (device, 4*64*2 int64) */
 int lf_conv3d_dz_timeline(const lf_conv_desc* desc, const void* x_split, const void* w_packed, const float* bias,
                           float* y32, void* y_split, float* rnorm, void* stamps, void* stream);

@@ -53,6 +53,10 @@ struct Params {
     uint32_t slab_bytes, w_bytes;
     int nprod;                    // 3: bf16x3, 1: bf16
     float scale; int act; float slope; int norm;
+    // fused backward epilogue (bwd-data feeding a Block conv): the result row g is pushed through the PixelNorm /
+    // LeakyReLU backward of the layer that produced this conv's forward input: epi_y = that layer's output in
+    // split-planar form (lo part at + epi_part_elems), epi_r = its saved norms; the kernel then writes du_prev
+    const uint16_t* epi_y; int64_t epi_part_elems; const float* epi_r; int epi_act, epi_norm; float epi_slope;
     uint64_t magic_Wp;
     long long* dbg;               // diagnostic timeline of CTA 0 (nullable): [role 0..3][event 0..63][2] SM clock stamps
 };
@@ -317,6 +321,36 @@ conv3d_dz_kernel(const __grid_constant__ Params p) {
                         if (valid && p.rnorm != nullptr)
                             p.rnorm[(((int64_t)n * p.d + pl) * p.h + (yp - 1)) * p.w + (xp - 1)] = rn;
                     }
+                    if (p.epi_y != nullptr && valid) {
+                        // du_prev = gate(y) * (g - y * mean_c(g*y)) / r   with g = this row   (same formula as lf_actnorm_bwd)
+                        const uint16_t* yh = p.epi_y + ((((int64_t)n * p.d + pl) * p.KCo) * p.PP + q) * 8;
+                        const uint16_t* yl = yh + p.epi_part_elems;
+                        float yv[NCH * 16];
+#pragma unroll
+                        for (int kc = 0; kc < NCH * 2; ++kc) {
+                            const uint4 h4 = __ldg(reinterpret_cast<const uint4*>(yh + (int64_t)kc * p.PP * 8));
+                            const uint4 l4 = __ldg(reinterpret_cast<const uint4*>(yl + (int64_t)kc * p.PP * 8));
+                            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                yv[kc * 8 + 2 * u] = __uint_as_float(hw[u] << 16) + __uint_as_float(lw[u] << 16);
+                                yv[kc * 8 + 2 * u + 1] = __uint_as_float(hw[u] & 0xffff0000u) + __uint_as_float(lw[u] & 0xffff0000u);
+                            }
+                        }
+                        float dot = 0.f, ir = 1.f;
+                        if (p.epi_norm) {
+#pragma unroll
+                            for (int i = 0; i < NCH * 16; ++i) dot += v[i] * yv[i];
+                            dot *= 1.f / (float)p.cout;
+                            ir = 1.f / __ldg(p.epi_r + (((int64_t)n * p.d + pl) * p.h + (yp - 1)) * p.w + (xp - 1));
+                        }
+                        const float gs = p.epi_act ? p.epi_slope : 1.f;
+#pragma unroll
+                        for (int i = 0; i < NCH * 16; ++i) {
+                            const float o = (v[i] - yv[i] * dot) * ir;
+                            v[i] = yv[i] > 0.f ? o : o * gs;
+                        }
+                    }
                     if (p.y32 != nullptr && valid) {
                         float* yo = p.y32 + ((((int64_t)n * p.d + pl) * p.h + (yp - 1)) * p.w + (xp - 1)) * p.cout;
 #pragma unroll
@@ -411,6 +445,55 @@ __global__ void split_pack_kernel(const float* __restrict__ x, uint16_t* __restr
         }
     }
     (void)magic_PP;
+}
+
+// PixelNorm/LeakyReLU backward of a 3-D layer (lf_actnorm_bwd's formula: du = gate(y) * (g - y*mean_c(g*y)) / r) that
+// writes its result in split-planar form — what the layer's bwd-data convolution stages with TMA — and, optionally,
+// dense fp32 as well (the weight-gradient kernel reads that).  C/4 lanes per position (C in {16, 32}), every lane
+// owns 4 channels = 8 bytes of a 16-byte split-planar row; the grid walks PADDED positions so the halo gets its zeros.
+__global__ void __launch_bounds__(256)
+actnorm_bwd_split_kernel(const float* __restrict__ gy, const float* __restrict__ y, const float* __restrict__ rnorm,
+                         float* __restrict__ du, uint16_t* __restrict__ dus, int64_t part_elems, int nd, int h, int w,
+                         int c, int lg, int act, float slope, int norm, uint64_t magic_Wp) {
+    const int Wp = w + 2, PP = (h + 2) * Wp, q4 = c >> 2, KC = c >> 3;
+    const int64_t units = (int64_t)nd * PP * q4;           // multiple of 32? not necessarily: pad for the shuffles
+    const int64_t units_pad = (units + 31) & ~(int64_t)31;
+    const float inv_c = 1.f / (float)c;
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < units_pad; u += (int64_t)gridDim.x * blockDim.x) {
+        const bool live = u < units;
+        const int64_t uu = live ? u : units - 1;
+        const int l = (int)(uu & (q4 - 1));
+        const int64_t pidx = uu >> lg;                      // padded position index over all planes
+        const int plane = (int)(pidx / PP);
+        const int q = (int)(pidx - (int64_t)plane * PP);
+        const int yp = fast_div(q, magic_Wp), xp = q - yp * Wp;
+        const bool valid = yp >= 1 && yp <= h && xp >= 1 && xp <= w;
+        const int64_t pos = valid ? (((int64_t)plane * h + (yp - 1)) * w + (xp - 1)) : 0;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f), yv = g;
+        if (valid) { g = ldg4(gy + pos * c + l * 4); yv = ldg4(y + pos * c + l * 4); }
+        float4 o = g;
+        if (norm) {
+            float dot = g.x * yv.x + g.y * yv.y + g.z * yv.z + g.w * yv.w;
+            for (int sft = 1; sft < q4; sft <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, sft);
+            dot *= inv_c;
+            const float ir = valid ? 1.f / __ldg(rnorm + pos) : 0.f;
+            o.x = (g.x - yv.x * dot) * ir; o.y = (g.y - yv.y * dot) * ir;
+            o.z = (g.z - yv.z * dot) * ir; o.w = (g.w - yv.w * dot) * ir;
+        }
+        if (act) {
+            o.x = yv.x > 0.f ? o.x : o.x * slope; o.y = yv.y > 0.f ? o.y : o.y * slope;
+            o.z = yv.z > 0.f ? o.z : o.z * slope; o.w = yv.w > 0.f ? o.w : o.w * slope;
+        }
+        if (!live) continue;
+        if (valid && du != nullptr) *reinterpret_cast<float4*>(du + pos * c + l * 4) = o;
+        uint2 hi2, lo2;
+        split_bf16x2(o.x, o.y, hi2.x, lo2.x);
+        split_bf16x2(o.z, o.w, hi2.y, lo2.y);
+        if (!valid) { hi2 = make_uint2(0u, 0u); lo2 = hi2; }
+        uint16_t* dst = dus + (((int64_t)plane * KC + (l >> 1)) * PP + q) * 8 + (l & 1) * 4;
+        *reinterpret_cast<uint2*>(dst) = hi2;
+        *reinterpret_cast<uint2*>(dst + part_elems) = lo2;
+    }
 }
 
 // fp32 packed weights [27 = (dz,dy,dx)][cin][cout] -> [j = dy*3+dx][part][kc][(2-dz)*cout_pad + co][8 ci] bf16
@@ -531,8 +614,11 @@ extern "C" int lf_conv3d_dz_pack_weights(const float* w27, void* out, int cin, i
     LF_RETURN_LAUNCH();
 }
 
+struct DzEpi { const void* y_split; const float* rnorm; int act, norm; float slope; };
+
 static int conv3d_dz_launch(const lf_conv_desc* desc, const void* x_split, const void* w_packed, const float* bias,
-                            float* y32, void* y_split, float* rnorm, long long* dbg, void* stream) {
+                            float* y32, void* y_split, float* rnorm, long long* dbg, void* stream,
+                            const DzEpi* epi = nullptr) {
     dz::Plan pl;
     if (desc == nullptr || !dz::make_plan(desc, pl)) {
         set_error("conv3d_dz: unsupported shape/precision (needs 3-D k=3, Cout in {4..32, %%4}, precision 1|2)");
@@ -554,6 +640,10 @@ static int conv3d_dz_launch(const lf_conv_desc* desc, const void* x_split, const
     p.scale = desc->scale; p.act = desc->act; p.slope = desc->slope; p.norm = desc->norm;
     p.magic_Wp = tcx::make_magic(pl.Wp);
     p.dbg = dbg;
+    p.epi_y = epi ? reinterpret_cast<const uint16_t*>(epi->y_split) : nullptr;
+    p.epi_part_elems = p.ypart_elems;
+    p.epi_r = epi ? epi->rnorm : nullptr; p.epi_act = epi ? epi->act : 0; p.epi_norm = epi ? epi->norm : 0;
+    p.epi_slope = epi ? epi->slope : 1.f;
     void (*kern)(dz::Params) = pl.cout_pad == 16 ? dz::conv3d_dz_kernel<1> : dz::conv3d_dz_kernel<2>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dz::kSmemBudget);
     if (e != cudaSuccess) { set_error("conv3d_dz: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return (int)e; }
@@ -574,4 +664,34 @@ extern "C" int lf_conv3d_dz_timeline(const lf_conv_desc* desc, const void* x_spl
                                      void* stream) {
     LF_CHECK_ARG(stamps, "conv3d_dz_timeline: null stamp buffer");
     return conv3d_dz_launch(desc, x_split, w_packed, bias, y32, y_split, rnorm, reinterpret_cast<long long*>(stamps), stream);
+}
+
+// bwd-data convolution (desc: cin = forward Cout, cout = forward Cin, act = norm = 0, no bias) whose result row is pushed
+// through the PixelNorm/LeakyReLU backward of the layer that produced the forward input: writes du_prev (dense fp32
+// and/or split-planar).  y_prev_split is that layer's output in split-planar form, rnorm_prev its saved norms.
+extern "C" int lf_conv3d_dz_bwd_epi(const lf_conv_desc* desc, const void* du_split, const void* w_packed,
+                                    const void* y_prev_split, const float* rnorm_prev, int prev_act, float prev_slope,
+                                    int prev_norm, float* du_prev32, void* du_prev_split, void* stream) {
+    LF_CHECK_ARG(desc && !desc->act && !desc->norm, "conv3d_dz_bwd_epi: the bwd-data descriptor has no activation/norm of its own");
+    LF_CHECK_ARG(y_prev_split && (!prev_norm || rnorm_prev), "conv3d_dz_bwd_epi: null pointer");
+    DzEpi epi{y_prev_split, rnorm_prev, prev_act, prev_norm, prev_slope};
+    return conv3d_dz_launch(desc, du_split, w_packed, nullptr, du_prev32, du_prev_split, nullptr, nullptr, stream, &epi);
+}
+
+extern "C" int lf_actnorm_bwd_split(const float* gy, const float* y, const float* rnorm, float* du, void* du_split,
+                                    int n, int d, int h, int w, int c, int act, float slope, int norm, void* stream) {
+    LF_CHECK_ARG(gy && y && du_split && (!norm || rnorm), "actnorm_bwd_split: null pointer");
+    LF_CHECK_ARG(n > 0 && d > 0 && h > 0 && w > 0 && (c == 16 || c == 32), "actnorm_bwd_split: C must be 16 or 32");
+    const int Wp = w + 2;
+    const int64_t PP = (int64_t)(h + 2) * Wp;
+    LF_CHECK_ARG(PP < (1 << 20) && Wp < 4096, "actnorm_bwd_split: plane too large");
+    const int lg = (c == 32) ? 3 : 2;
+    const int64_t units = (int64_t)n * d * PP * (c >> 2);
+    int64_t blocks = (units + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    dz::actnorm_bwd_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        gy, y, rnorm, du, reinterpret_cast<uint16_t*>(du_split), (int64_t)n * d * c * PP, n * d, h, w, c, lg, act, slope,
+        norm, tcx::make_magic(Wp));
+    LF_RETURN_LAUNCH();
 }

@@ -372,6 +372,30 @@ def _dz_pack(wf, key):
     return out
 
 
+_GRAD_SPLIT = [None]       # (data_ptr, numel, SplitVol) of the most recent fused bwd-data result: its single consumer is
+#                            the very next backward node (the producer layer's), which takes it instead of re-packing
+
+
+def _put_grad_split(g, gs):
+    _GRAD_SPLIT[0] = (g.data_ptr(), g.numel(), gs)
+
+
+def _take_grad_split(g):
+    rec, _GRAD_SPLIT[0] = _GRAD_SPLIT[0], None
+    if rec is not None and rec[0] == g.data_ptr() and rec[1] == g.numel():
+        return rec[2]
+    return None
+
+
+def _dz_shape(x, weight, kind, precision):
+    """cheap test: would eq_conv run this convolution on the depth-batched kernel?"""
+    if kind != KIND_CONV or x.dim() != 5 or weight.dim() != 5 or weight.shape[-1] != 3 or precision not in (1, 2, 3):
+        return False
+    n, cin, d, h, w = x.shape
+    desc = _desc(KIND_CONV, 3, n, d, h, w, cin, weight.shape[0], 3, 1.0, False, 0.0, False, 1 if precision == 3 else precision)
+    return _dz_ok(desc)
+
+
 def _dz_ok(desc):
     return desc.precision in (1, 2) and bool(L.lib().lf_conv3d_dz_supported(ctypes.byref(desc)))
 
@@ -476,10 +500,12 @@ class _EqConv(torch.autograd.Function):
         taps = wf.shape[0]
         wkey = (weight, id(weight), weight._version, kind)
         _EqConv.last_split = None
+        ctx.xs = None
         if use_dz:
             # depth-batched tcgen05 kernel on split-planar activations (one launch for bf16x3); the producer may have
             # left the split-planar form of x next to it (x_split), otherwise it is packed here
             xs = x_split if x_split is not None else split_pack(x)
+            ctx.xs = xs if rec_in is not None else None      # the producer layer's output, for the fused backward epilogue
             y, ys, rnorm = conv3d_dz(xs, _dz_pack(wf, wkey + ('dzf',)), bpk, gcout, scale, act, slope, norm, desc.precision,
                                      want_dense=True, want_split=emit_split, name=_conv_name(kind, nd, k, 'fwd'))
             _EqConv.last_split = ys
@@ -540,6 +566,41 @@ class _EqConv(torch.autograd.Function):
                    _stream()), kernels=3 if precision == 1 else 1,
                   nbytes=4 * (2 * gy.numel() + gx.numel()), flops=bflops)
             fused_done = True
+        use_dz_b = ctx.needs_input_grad[0] and kind == KIND_CONV and nd == 3 and k == 3 and _dz_ok(bdesc)
+        if use_dz_b and not fused_done:
+            # ---- depth-batched path: split-planar du straight out of the activation backward, and (when the producer
+            # of x is a Block conv whose only consumer this is) that producer's activation backward in the epilogue
+            if (act or norm) and not pre_applied:
+                du_split = SplitVol.empty(n, cout, d, h, w, x.device)
+                if cout in (16, 32):
+                    du = torch.empty_like(gy) if need_w else None
+                    _call('lf_actnorm_bwd', lib.lf_actnorm_bwd_split,
+                          (_p(gy), _p(y), _p(rnorm), _p(du), _p(du_split.buf), n, d, h, w, cout, int(act), slope, int(norm),
+                           _stream()), nbytes=4 * 2 * gy.numel() + 2 * du_split.buf.numel())
+                else:
+                    du = torch.empty_like(gy)
+                    _call('lf_actnorm_bwd', lib.lf_actnorm_bwd, (_p(gy), _p(y), _p(rnorm), _p(du), n * d * h * w, 1, 1, cout,
+                                                                int(act), slope, int(norm), _stream()), nbytes=4 * 3 * gy.numel())
+                    du_split = split_pack(du)
+            else:
+                du = gy
+                du_split = _take_grad_split(gy) or split_pack(gy)
+            wpk_b = _dz_pack(wb, ctx.wkey + ('dzb',))
+            if rec_in is not None and ctx.xs is not None and rec_in.shape == tuple(x.shape):
+                gx = empty_cl(tuple(x.shape), x.device)
+                gxs = SplitVol.empty(n, cin, d, h, w, x.device)
+                _call(_conv_name(kind, nd, k, 'bwd_data'), lib.lf_conv3d_dz_bwd_epi,
+                      (ctypes.byref(bdesc), _p(du_split.buf), _p(wpk_b), _p(ctx.xs.buf), _p(rec_in.rnorm), int(rec_in.act),
+                       float(rec_in.slope), int(rec_in.norm), _p(gx), _p(gxs.buf), _stream()),
+                      nbytes=2 * du_split.buf.numel() + 2 * ctx.xs.buf.numel() + 4 * gx.numel() + 2 * gxs.buf.numel(), flops=bflops)
+                rec_in.pre_applied = True
+                _put_grad_split(gx, gxs)
+            else:
+                gx, _, _ = conv3d_dz(du_split, wpk_b, None, cin, scale, False, 0.0, False, bdesc.precision,
+                                     name=_conv_name(kind, nd, k, 'bwd_data'))
+            fused_done = True
+            if need_w and du is None:
+                du = du_split.to_dense()
         if not fused_done:
             if (act or norm) and not pre_applied:
                 du = torch.empty_like(gy)
@@ -564,11 +625,6 @@ class _EqConv(torch.autograd.Function):
                       kernels=1 if bkind == KIND_EXPAND else _tc_passes(bdesc),
                       nbytes=4 * (du.numel() + 2 * gx.numel()), flops=bflops)
                 rec_in.pre_applied = True
-            elif ctx.needs_input_grad[0] and kind == KIND_CONV and nd == 3 and k == 3 and _dz_ok(bdesc):
-                # bwd-data on the depth-batched kernel: flipped/transposed weights, no epilogue
-                dus = du_split if du_split is not None else split_pack(du)
-                gx, _, _ = conv3d_dz(dus, _dz_pack(wb, ctx.wkey + ('dzb',)), None, cin, scale, False, 0.0, False, bdesc.precision,
-                                     name=_conv_name(kind, nd, k, 'bwd_data'))
             elif ctx.needs_input_grad[0]:
                 gx = torch.empty_like(x)
                 # bwd-data = the same implicit GEMM with flipped/transposed weights, no epilogue
@@ -603,7 +659,7 @@ def eq_conv(x, weight, bias, act=False, slope=0.2, norm=False, kind=KIND_CONV, d
     if precision is None:
         precision = _default_precision
     rec_in = None
-    if _FUSE_EPI and getattr(x, '_lf_single_use', False) and torch.is_grad_enabled():
+    if getattr(x, '_lf_single_use', False) and torch.is_grad_enabled() and (_FUSE_EPI or _dz_shape(x, weight, kind, precision)):
         rec_in = getattr(x, '_lf_actnorm', None)
     y = _EqConv.apply(x, weight, bias, kind, depth, bool(act), float(slope), bool(norm), int(precision), fan_in, rec_in,
                       getattr(x, '_lf_split', None), bool(emit_split))

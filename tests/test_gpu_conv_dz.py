@@ -78,3 +78,58 @@ def test_conv3d_dz_vs_fp64(dev, n, cin, cout, d, h, w, precision):
         _, ys1, _ = ops.conv3d_dz(xs, wpk, b, cout, he, True, 0.2, True, precision, want_dense=False, want_split=True)
         y2, _, _ = ops.conv3d_dz(ys1, wpk, b, cout, he, True, 0.2, True, precision)
         torch.testing.assert_close(y2.double(), ref2, atol=tol['atol'] * 3, rtol=tol['rtol'] * 3)
+
+
+@pytest.mark.parametrize('c,size', [(32, (2, 9, 12, 10)), (16, (1, 6, 7, 8))])
+@pytest.mark.parametrize('train', [False, True])
+def test_block_forward_backward_through_dz_path(dev, c, size, train):
+    """Block(C, C) (reference modules/blocks.py:152-164) at precision 1: conv1 hands conv2 its split-planar output,
+    conv2's bwd-data applies conv1's PixelNorm/LeakyReLU backward in its epilogue and hands conv1 the split-planar du.
+    Checked against fp64 autograd of the same composition: output, d/dx and (train) the weight/bias gradients."""
+    from latentfusion_b200 import ops
+    from latentfusion_b200.modules import EqualizedConv3d
+    from latentfusion_b200.modules.blocks import Block
+    n, d, h, w = size
+    torch.manual_seed(c + d)
+    blk = Block(c, c, conv_module=EqualizedConv3d, scale_factor=1.0).to(dev)
+    for k, p in blk.named_parameters():
+        if k.endswith('bias'):
+            p.data.normal_(0, 0.1)
+        p.requires_grad_(train)
+    x = torch.randn(n, c, d, h, w, device=dev, requires_grad=True)
+    g = torch.randn(n, c, d, h, w, device=dev)
+    old = ops.get_default_precision()
+    ops.set_default_precision(1)
+    try:
+        ops.KernelTrace.reset(True)
+        y = blk(x)
+        y.backward(g)
+        names = [r[0] for r in ops.KernelTrace.records]
+    finally:
+        ops.KernelTrace.reset(False)
+        ops.set_default_precision(old)
+    assert names.count('lf_split_pack') == 1, names            # only the block's input is packed
+    assert 'lf_conv_bwd_data[conv3d_k3]' in names
+    xr = x.detach().double().requires_grad_(True)
+    ws = {k: v.detach().double().requires_grad_(True) for k, v in blk.named_parameters()}
+    t = xr
+    fragile = torch.zeros(n, 1, d, h, w, device=dev)
+    for i in (1, 2):
+        he = math.sqrt(2.0 / (c * 27))
+        t = F.conv3d(t, ws[f'conv{i}.module.weight'], None, padding=1) * he + ws[f'conv{i}.bias'].view(1, -1, 1, 1, 1)
+        # a pre-activation within rounding of zero may take the other LeakyReLU branch in fp32: its gradient then differs
+        # by 0.8x on that channel, which the bwd-data convolutions spread over a 3^3 (layer 1) / 5^3 (layer 2) stencil
+        near0 = (t.detach().abs() < 2e-4).any(dim=1, keepdim=True).float()
+        fragile = torch.maximum(fragile, F.max_pool3d(near0, 2 * i + 1, stride=1, padding=i))
+        t = F.leaky_relu(t, 0.2)
+        t = t / torch.sqrt((t * t).mean(dim=1, keepdim=True) + 1e-8)
+    t.backward(g.double())
+    torch.testing.assert_close(y.detach().double(), t.detach(), atol=2e-4, rtol=2e-3)
+    keep = (fragile == 0).expand_as(x)
+    assert keep.float().mean() > 0.5
+    torch.testing.assert_close(x.grad.double()[keep], xr.grad[keep], atol=2e-4, rtol=2e-3)
+    if train:
+        # (sums over all positions: a flipped LeakyReLU branch at a near-zero pre-activation moves them by one term)
+        for k, p in blk.named_parameters():
+            rel = float((p.grad.double() - ws[k].grad).norm() / ws[k].grad.norm())
+            assert rel < 2e-2, f'{k}: relative L2 error {rel:.3g}'
