@@ -148,12 +148,54 @@ def pick_threads(O, sds, arch, z_obj, cam_dict, tdepth, tmask):
 
 
 def run_reference(args):
-    from oracle import lf_oracle as O
-    from tests import parity_helpers as ph
+    """Reference arm: the reference's OWN estimator loop (GradientPoseEstimator.estimate, adam_quick.toml) on the host
+    cores — the unmodified reference staged under oracle/_ref (kind "reference"), or, when that copy is absent, the
+    oracle port of the render+loss+backward part (kind "port").  One step = one full iteration over all N hypotheses
+    (render fwd, loss, backward, N Adam + plateau steps, ranking); no extrapolation."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    import warnings
+    warnings.filterwarnings('ignore')
+    os.environ.setdefault('TQDM_DISABLE', '1')
+    from oracle import ref_bench
     device = torch.device(args.ref_device)
+    cores = os.cpu_count() or 1
+    if ref_bench.available():
+        kind = 'reference'
+        threads = cores
+        if device.type == 'cpu':
+            # PyTorch CPU ops do not scale to every core of a large host: keep the fastest of a few thread counts
+            best = float('inf')
+            for nt in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16), min(cores, 8)}, reverse=True):
+                dt = ref_bench.time_iterations('cpu', 2, 0, 1, threads=nt)
+                if dt < best:
+                    best, threads = dt, nt
+        sec_per_iter = ref_bench.time_iterations(str(device), N_HYP, args.warmup, args.steps, tf32=False,
+                                                 threads=threads if device.type == 'cpu' else None)
+        sample = (f"{args.steps} full iterations of the unmodified reference's GradientPoseEstimator.estimate() "
+                  f"(adam_quick.toml) over all {N_HYP} hypotheses after {args.warmup} warm-up iterations; "
+                  f"{'host CPU, ' + str(threads) + ' threads' if device.type == 'cpu' else 'stock PyTorch CUDA ops, TF32 off'}")
+        cores_used = threads
+    else:
+        kind = 'port'
+        sec_per_iter, cores_used, sample = _reference_port(args, device)
+    value = 1.0 / sec_per_iter
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_iter * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"configs[1]: LF-synth(S={S},C={C}), V={V}, N={N_HYP} hypotheses, 128^2 render, fp32",
+                       "device": str(device)},
+            "cpu_baseline": {"value": value, "unit": "iters/s", "cores": cores_used if device.type == 'cpu' else 0,
+                             "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def _reference_port(args, device):
+    """fallback when oracle/_ref is absent: the oracle port (plain PyTorch ops restating the reference), full N"""
+    from oracle import lf_oracle as O
+    from tests import parity_helpers as ph
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     cores = os.cpu_count() or 1
@@ -164,12 +206,10 @@ def run_reference(args):
     for k in sds['photographer']:
         sds['photographer'][k] = sds['photographer'][k].to(device).requires_grad_(True)
     torch.manual_seed(5)
-    z_obj = torch.randn(1, C, S, S, S, device=device) * 0.5      # the cube's values do not change the cost
+    z_obj = torch.randn(1, C, S, S, S, device=device) * 0.5
     hyp = hypothesis_cameras(inp['gt'].uncrop(), N_HYP, seed=7).zoom(None, 2 * S, inp['dist'])
     cam_dict = {k: v.to(device) for k, v in ph.cam_to_dict(hyp).items()}
     tdepth, tmask = inp['tdepth'].to(device), inp['tmask'].to(device)
-    n_sample = args.ref_hyp
-    scale = N_HYP / n_sample
     if device.type == 'cpu':
         cores = pick_threads(O, sds, arch, z_obj, cam_dict, tdepth, tmask)
 
@@ -177,7 +217,7 @@ def run_reference(args):
         if device.type == 'cuda':
             torch.cuda.synchronize()
         t0 = time.perf_counter()
-        reference_iteration(_dev(O, device), sds, arch, z_obj, cam_dict, tdepth, tmask, n_sample)
+        reference_iteration(_dev(O, device), sds, arch, z_obj, cam_dict, tdepth, tmask, N_HYP)
         if device.type == 'cuda':
             torch.cuda.synchronize()
         return time.perf_counter() - t0
@@ -185,19 +225,8 @@ def run_reference(args):
     for _ in range(args.warmup):
         one()
     times = [one() for _ in range(args.steps)]
-    sec_per_iter = statistics.mean(times) * scale
-    value = 1.0 / sec_per_iter
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_iter * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"configs[1]: LF-synth(S={S},C={C}), V={V}, N={N_HYP} hypotheses, 128^2 render, fp32",
-                       "device": str(device)},
-            "cpu_baseline": {"value": value, "unit": "iters/s", "cores": cores if device.type == 'cpu' else 0,
-                             "kind": "port",
-                             "sample": f"fwd+bwd of {n_sample} of {N_HYP} hypotheses per step (cost is linear in N: "
-                                       f"time x{scale:g}); plain PyTorch {device.type} ops, all host threads"},
-            "e2e": {"value": value, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    return statistics.mean(times), cores, (f"fwd+bwd of all {N_HYP} hypotheses per step; oracle port (plain PyTorch "
+                                           f"{device.type} ops restating the reference), no optimiser step")
 
 
 def _dev(O, device):
@@ -238,7 +267,7 @@ def run_ours(args):
     # per-view cubes are all-gathered (NCCL), the GRU recurrence runs replicated.
     from latentfusion_b200 import dist as lfdist
     recon_times = []
-    for _ in range(2):                      # first call is cold (allocator, weight packing); report the second
+    for _ in range(3):                      # first call is cold (allocator, weight packing); report the last
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); t0.record()
         with torch.no_grad():
@@ -302,6 +331,27 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     value = world * 1000.0 / ms_per_step
 
+    # ---------------- strong scaling of configs[2] (64 hypotheses in total, split over the ranks) ----------------
+    strong = None
+    if not args.no_strong and N_HYP == 8 and 64 % world == 0:
+        n_loc = 64 // world
+        cfg_s = {'type': 'gradient', 'args': dict(EST_ARGS, num_iters=3, num_samples=n_loc, ranking_size=n_loc),
+                 'loss_weights': LOSS_WEIGHTS}
+        est_s = estimation.load_from_config(cfg_s, model)
+        hyp_s = hypothesis_cameras(gt_full, 64, seed=11)[rank * n_loc:(rank + 1) * n_loc].to(dev)
+        est_s.estimate(z_obj, target_dev, camera=hyp_s)          # warm-up (captures this shape's graph)
+        est_s.num_iters = 5
+        barrier()
+        e0.record()
+        est_s.estimate(z_obj, target_dev, camera=hyp_s)
+        e1.record()
+        barrier()
+        ms_s = max_over_ranks(e0.elapsed_time(e1)) / 5
+        strong = {"workload": "configs[2]: adam_quick.toml at num_samples=64 (64 hypotheses in total, strong scaling)",
+                  "hypotheses_total": 64, "hypotheses_per_gpu": n_loc, "ms_per_step": ms_s, "iters_per_s": 1000.0 / ms_s,
+                  "hypothesis_renders_per_s": 64 * 1000.0 / ms_s, "steps": 5}
+        del est_s
+
     # ---------------- end-to-end through the public API with HOST buffers ----------------
     # One user-level call: estimator.estimate(z_obj, HOST target observation, HOST hypothesis cameras) for K
     # iterations.  Inside the timed region: the H2D copy of the target (colour+depth+mask, pinned) and of the
@@ -341,10 +391,9 @@ def run_ours(args):
                          "achieved_GBs": None if gbs is None else round(gbs, 1),
                          "achieved_TFs": None if tfs is None else round(tfs, 2)}
     traffic = {}
-    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    tpath = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))        # dram bytes per launch from the committed ncu --set full captures
-    passes = 2 if args.precision in (1, 3) else 1        # bf16x3 = 3 tensor-core products issued in 2 kernel passes
     roof = None
     if ktrace:
         top = max(ktrace.items(), key=lambda kv: kv[1]['ms_total'])
@@ -353,14 +402,13 @@ def run_ours(args):
         if conv_like:
             peak = peaks['bf16_tflops_sustained']
             ach = d['flops'] / d['calls'] / (d['ms_avg'] * 1e-3) / 1e12
-            tr = (traffic.get('conv_tc_bf16x3_two_passes' if passes == 2 else 'conv_tc_kernel')
-                  if (args.precision and 'conv3d' in name) else None)
+            tr = traffic.get('conv3d_dz_kernel') if (args.precision and 'conv3d' in name) else None
             roof = {"kernel": name, "bound": "tensor", "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s",
                     "frac": round(ach / peak, 4), "traffic": tr,
                     "peak_source": peaks['source'] + ' bf16 sustained',
-                    "note": ("algorithmic flops 2*27*Cin*Cout*positions counted ONCE; the bf16x3 mode issues 3 tensor-core "
-                             "products per tap (in 2 kernel passes), so the MMA rate is 3x 'achieved'; traffic = both passes (the second re-reads x and read-modify-writes y)") if passes == 2 else
-                            "algorithmic flops 2*27*Cin*Cout*positions"}
+                    "note": ("algorithmic flops 2*27*Cin*Cout*positions counted ONCE; precision 1 (bf16x3) issues 3 tensor-core "
+                             "products per tap in one kernel pass (depth-batched N=3*Cout MMAs), so the MMA rate is 3x 'achieved'")
+                            if args.precision in (1, 3) else "algorithmic flops 2*27*Cin*Cout*positions"}
         else:
             peak = peaks['hbm_gbs']
             ach = d['bytes'] / d['calls'] / (d['ms_avg'] * 1e-3) / 1e9
@@ -374,10 +422,14 @@ def run_ours(args):
                          "algorithmic_bytes": 4 * C * S ** 3 * (1 + N_HYP), "traffic": traffic.get('resample_fwd_kernel'),
                          "peak_source": peaks['source']}
 
-    # ---------------- CPU baseline (oracle port, bounded sample, rank 0, N=1 only) ----------------
+    # ---------------- CPU baseline (bounded sample, rank 0, N=1 only) + the stock-PyTorch-CUDA context number ----------
     cpu = None
+    ref_cuda = None
     if world == 1 and not args.no_cpu_baseline:
+        del est, est_e
+        torch.cuda.empty_cache()
         cpu = cpu_baseline(sds, arch, inp)
+        ref_cuda = reference_cuda_block(dev)
 
     line = {"metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -394,30 +446,64 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h,
                     "note": "one estimator.estimate(z_obj, host target obs, host cameras) call of K iterations / K: includes H2D of target+cameras (graph captured once, during warm-up), per-iteration D2H of losses and camera snapshots"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_resample": resample_roof,
-            "kernels": kernels, "cpu_baseline": cpu}
+            "kernels": kernels, "cpu_baseline": cpu, "reference_cuda": ref_cuda, "strong_scaling": strong,
+            "recon": {"ms": round(recon_ms, 2), "ms_first_call": round(recon_times[0], 2), "views": V,
+                      "views_per_gpu": (V + world - 1) // world, "fuser": "gru",
+                      "note": "LatentFusionModel.build_latent_object, views sharded over the ranks (dist.py), max over ranks"}}
     print(json.dumps(line), flush=True)
 
 
 def cpu_baseline(sds, arch, inp):
+    """The reference timed beside the GPU number, on the box's host cores, bounded (one warm + two timed full
+    iterations over all N hypotheses): the unmodified reference's estimator when oracle/_ref is staged, else the port."""
+    import warnings
+    warnings.filterwarnings('ignore')
+    os.environ.setdefault('TQDM_DISABLE', '1')
+    from oracle import ref_bench
+    cores = os.cpu_count() or 1
+    if ref_bench.available():
+        best, threads = float('inf'), cores
+        for nt in sorted({min(cores, 64), min(cores, 32), min(cores, 16), min(cores, 8)}, reverse=True):
+            dt = ref_bench.time_iterations('cpu', 2, 0, 1, threads=nt)
+            if dt < best:
+                best, threads = dt, nt
+        sec = ref_bench.time_iterations('cpu', N_HYP, 1, 2, threads=threads)
+        return {"value": 1.0 / sec, "unit": "iters/s", "cores": threads, "kind": "reference",
+                "sample": f"2 full iterations (after 1 warm-up) of the unmodified reference's GradientPoseEstimator over all "
+                          f"{N_HYP} hypotheses, host CPU, {threads} threads (fastest of 64/32/16/8)"}
     from oracle import lf_oracle as O
     from tests import parity_helpers as ph
-    cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in sds['photographer'].items()}
     torch.manual_seed(5)
     z_obj = torch.randn(1, C, S, S, S) * 0.5
     hyp = hypothesis_cameras(inp['gt'].uncrop(), N_HYP, seed=7).zoom(None, 2 * S, inp['dist'])
     cam_dict = ph.cam_to_dict(hyp)
-    n_sample = 2
     cores = pick_threads(O, {'photographer': sd}, arch, z_obj, cam_dict, inp['tdepth'], inp['tmask'])
     t0 = time.perf_counter()
     reps = 2
     for _ in range(reps):
-        reference_iteration(O, {'photographer': sd}, arch, z_obj, cam_dict, inp['tdepth'], inp['tmask'], n_sample)
-    sec = (time.perf_counter() - t0) / reps * (N_HYP / n_sample)
+        reference_iteration(O, {'photographer': sd}, arch, z_obj, cam_dict, inp['tdepth'], inp['tmask'], N_HYP)
+    sec = (time.perf_counter() - t0) / reps
     return {"value": 1.0 / sec, "unit": "iters/s", "cores": cores, "kind": "port",
-            "sample": f"{reps} x (fwd+bwd of {n_sample} of {N_HYP} hypotheses), time scaled x{N_HYP // n_sample}; "
-                      f"plain PyTorch CPU ops restating the reference (oracle/lf_oracle.py), {cores} threads"}
+            "sample": f"{reps} x (fwd+bwd of all {N_HYP} hypotheses); plain PyTorch CPU ops restating the reference "
+                      f"(oracle/lf_oracle.py), {cores} threads"}
+
+
+def reference_cuda_block(dev):
+    """Context (north_star's ">= 10x the reference PyTorch render loop"): the unmodified reference's estimator on this
+    same GPU through stock PyTorch CUDA ops, TF32 off (the fp32-parity setting) and on (PyTorch's cuDNN default)."""
+    from oracle import ref_bench
+    if not ref_bench.available():
+        return None
+    out = {"kind": "reference", "steps": 20, "warmup": 2, "unit": "iters/s"}
+    for name, tf32 in (("tf32_off", False), ("tf32_on", True)):
+        sec = ref_bench.time_iterations(str(dev), N_HYP, 2, 20, tf32=tf32)
+        out[name] = 1.0 / sec
+        torch.cuda.empty_cache()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return out
 
 
 def main():
@@ -434,6 +520,7 @@ def main():
                     help='hypotheses per GPU (default 8 = BASELINE configs[1]; 64 = configs[2], adam_quick.toml at num_samples=64)')
     ap.add_argument('--no-kernel-events', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-strong', action='store_true', help='skip the configs[2] strong-scaling extra')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.hypotheses != N_HYP:

@@ -41,12 +41,23 @@ def bbox_to_grid(bbox, in_size, out_size):
 
 
 def bboxes_to_grid(boxes, in_size, out_size):
+    """Crop grids of reference geometry.py:20-43.  As the reference executes (its TorchScript `bbox[i].item()` becomes
+    an implicit int), the box edges are TRUNCATED toward zero before the grid is laid out — the crops of an
+    Observation are taken on whole-pixel boxes while the camera keeps the exact viewport (quirks are
+    reproduced, not fixed; pinned by tests/golden/facade_s16_c8.npz)."""
+    boxes = torch.trunc(boxes.float())
     h, w = float(in_size[0]), float(in_size[1])
     oh, ow = int(out_size[0]), int(out_size[1])
-    ty = torch.linspace(0.0, 1.0, oh, device=boxes.device)
-    tx = torch.linspace(0.0, 1.0, ow, device=boxes.device)
-    gx = (boxes[:, 0, None] / w + tx[None] * ((boxes[:, 2, None] - boxes[:, 0, None]) / w)) * 2 - 1
-    gy = (boxes[:, 1, None] / h + ty[None] * ((boxes[:, 3, None] - boxes[:, 1, None]) / h)) * 2 - 1
+
+    def rows(lo, hi, steps):
+        # torch.linspace(lo_i, hi_i, steps) for every box i, with ATen's symmetric evaluation (start + i*step in the
+        # first half, end - (steps-1-i)*step in the second), so the crops match the reference bit for bit
+        i = torch.arange(steps, device=boxes.device, dtype=torch.float32)[None]
+        step = (hi - lo)[:, None] / max(steps - 1, 1)
+        return torch.where(i < steps // 2, lo[:, None] + i * step, hi[:, None] - (steps - 1 - i) * step)
+
+    gx = rows(boxes[:, 0] / w, boxes[:, 2] / w, ow) * 2 - 1
+    gy = rows(boxes[:, 1] / h, boxes[:, 3] / h, oh) * 2 - 1
     n = boxes.shape[0]
     return torch.stack((gx[:, None, :].expand(n, oh, ow), gy[:, :, None].expand(n, oh, ow)), dim=-1)
 

@@ -137,6 +137,7 @@ def crop_boxes(image, boxes, in_hw, out_size, mode):
     geometry.py:20-43, :349-352."""
     h, w = in_hw
     n = boxes.shape[0]
+    boxes = torch.trunc(boxes)      # geometry.py:24-27: `.item()` under torch.jit.script is an implicit int (truncation)
     lin = torch.linspace(0.0, 1.0, out_size)
     gx = (boxes[:, 0, None] / w + lin[None] * ((boxes[:, 2, None] - boxes[:, 0, None]) / w)) * 2 - 1
     gy = (boxes[:, 1, None] / h + lin[None] * ((boxes[:, 3, None] - boxes[:, 1, None]) / h)) * 2 - 1

@@ -20,7 +20,11 @@ removed from torch.
 import sys
 import types
 
-REFERENCE_ROOT = '/root/reference'
+import os as _os
+
+# the reference as it lies in the authoring container, else the verbatim copy staged for the GPU box (oracle/stage_ref.py)
+_STAGED = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), '_ref')
+REFERENCE_ROOT = '/root/reference' if _os.path.isdir('/root/reference/latentfusion') else _STAGED
 
 
 class _Noop:
@@ -66,6 +70,14 @@ def install():
             setattr(sl, sub, _stub_module(f'structlog.{sub}'))
     if 'IPython' not in sys.modules and importlib.util.find_spec('IPython') is None:
         _stub_module('IPython', get_ipython=lambda: None)
+    if 'toml' not in sys.modules and importlib.util.find_spec('toml') is None:
+        # latentfusion/pose/estimation.py:10 imports toml only to read config FILES; the harness passes dicts
+        import tomllib
+
+        def _toml_load(path):
+            with open(path, 'rb') as fh:
+                return tomllib.load(fh)
+        _stub_module('toml', load=_toml_load)
     for name in ('imageio', 'plyfile'):
         if name not in sys.modules and importlib.util.find_spec(name) is None:
             _stub_module(name)
