@@ -213,6 +213,11 @@ typedef struct {
 int lf_pose_loss_fwd(const lf_loss_desc* desc, const float* depth_logits, const float* mask_logits,
                      const float* viewport, const float* tz, const float* target_depth, const float* target_mask,
                      float* sums, float* terms, void* stream);
+/* forward-only variant for the coarse search (CrossEntropyPoseEstimator: estimation.py:187-197 multiplies the crop's
+ * metric depth by the crop's sigmoid(mask) before the loss pastes it into the frame); same outputs as lf_pose_loss_fwd */
+int lf_pose_loss_search_fwd(const lf_loss_desc* desc, const float* depth_logits, const float* mask_logits,
+                            const float* viewport, const float* tz, const float* target_depth,
+                            const float* target_mask, float* sums, float* terms, void* stream);
 int lf_pose_loss_bwd(const lf_loss_desc* desc, const float* depth_logits, const float* mask_logits,
                      const float* viewport, const float* tz, const float* target_depth, const float* target_mask,
                      const float* sums, const float* grad_terms /* [N][4] */,

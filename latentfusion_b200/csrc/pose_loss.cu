@@ -20,6 +20,8 @@ constexpr int kSums = 6;   // A=sum dl1, B=sum dl1*pm*tm, C=sum pm*tm, D=sum pm,
 struct LossGeom {
     int n, p, width, height;
     float range, base_off;    // z = (tanh(dl)+1)/2 * gate * range + (tz + base_off)
+    int premask;              // coarse search (PoseEstimator._render_observation, estimation.py:187-197): the crop's metric
+                              // depth is multiplied by the crop's own sigmoid(mask) before it is pasted into the frame
 };
 
 struct PixelSample {
@@ -47,7 +49,10 @@ __device__ __forceinline__ PixelSample make_sample(float X, float Y, const float
     const float vw = vp[2] - vp[0], vh = vp[3] - vp[1];
     const float gx = (X - vp[0]) / vw * 2.f - 1.f;       // geometry.py:281-282
     const float gy = (Y - vp[1]) / vh * 2.f - 1.f;
-    const float ix = clip_coord(gx, P, s.mx), iy = clip_coord(gy, P, s.my);
+    float ix = clip_coord(gx, P, s.mx), iy = clip_coord(gy, P, s.my);
+    // degenerate optimised viewport (zero width / NaN): the reference only propagates NaNs; keep the indices in range
+    if (!isfinite(ix)) { ix = 0.f; s.mx = 0.f; }
+    if (!isfinite(iy)) { iy = 0.f; s.my = 0.f; }
     const int xn = (int)nearbyintf(ix), yn = (int)nearbyintf(iy);
     s.near_idx = yn * P + xn;
     const float fx0 = floorf(ix), fy0 = floorf(iy);
@@ -68,11 +73,12 @@ struct PixelTerms { float z, pm, pd, dl1, td, tm, valid, ml, gate, th; };
 
 __device__ __forceinline__ PixelTerms eval_pixel(const PixelSample& s, const float* __restrict__ dl,
                                                  const float* __restrict__ ml, float tdepth, float tmask,
-                                                 float range, float base) {
+                                                 float range, float base, int premask = 0) {
     PixelTerms t;
     t.th = tanhf(dl[s.near_idx]);
     t.gate = sigmoid_(ml[s.near_idx]) > 0.5f ? 1.f : 0.f;          // apply_mask (models.py:478-481)
     t.z = (t.th + 1.f) * 0.5f * t.gate * range + base;
+    if (premask) t.z *= sigmoid_(ml[s.near_idx]);
     t.ml = s.w00 * ml[s.i00] + s.w01 * ml[s.i01] + s.w10 * ml[s.i10] + s.w11 * ml[s.i11];
     t.pm = sigmoid_(t.ml);
     t.pd = t.z * t.pm;
@@ -96,7 +102,7 @@ pose_loss_sums_kernel(const LossGeom g, const float* __restrict__ dlog, const fl
     for (int px = blockIdx.x * blockDim.x + threadIdx.x; px < HW; px += gridDim.x * blockDim.x) {
         const int Y = px / g.width, X = px - Y * g.width;
         const PixelSample s = make_sample((float)X, (float)Y, vp + 4 * n, g.p);
-        const PixelTerms t = eval_pixel(s, dl, ml, tdepth[px], tmask[px], g.range, base);
+        const PixelTerms t = eval_pixel(s, dl, ml, tdepth[px], tmask[px], g.range, base, g.premask);
         acc[0] += t.dl1;
         acc[1] += t.dl1 * t.pm * t.tm;
         acc[2] += t.pm * t.tm;
@@ -256,6 +262,7 @@ static int loss_geom(const lf_loss_desc* d, LossGeom& g) {
     g.n = d->n; g.p = d->p; g.width = d->width; g.height = d->height;
     g.range = 2.f * d->z_span + 2.f * d->eps;          // (zfar + eps) - (znear - eps)
     g.base_off = -d->z_span - d->eps;                  // znear - eps = tz - z_span - eps
+    g.premask = 0;
     return LF_OK;
 }
 
@@ -270,6 +277,26 @@ extern "C" int lf_pose_loss_fwd(const lf_loss_desc* desc, const float* depth_log
     if (int e = loss_geom(desc, g)) return e;
     LF_CHECK_ARG(depth_logits && mask_logits && viewport && tz && target_depth && target_mask && sums && terms,
                  "pose_loss_fwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(sums, 0, sizeof(float) * 8 * g.n, st);
+    const int HW = g.width * g.height;
+    const int bx = min((HW + 255) / 256, 4 * sm_count() / max(1, min(g.n, 8)) + 1);
+    target_sum_kernel<<<min(64, (HW + 255) / 256), 256, 0, st>>>(g, target_depth, target_mask, sums);
+    pose_loss_sums_kernel<<<dim3(bx, g.n), 256, 0, st>>>(g, depth_logits, mask_logits, viewport, tz, target_depth, target_mask, sums);
+    pose_loss_terms_kernel<<<(g.n + 63) / 64, 64, 0, st>>>(g, sums, terms);
+    LF_RETURN_LAUNCH();
+}
+
+// Forward-only scoring for the coarse pose search (CrossEntropyPoseEstimator, reference estimation.py:187-197 +
+// :70-118): same four terms, with the search's extra crop-space mask factor on the rendered depth.
+extern "C" int lf_pose_loss_search_fwd(const lf_loss_desc* desc, const float* depth_logits, const float* mask_logits,
+                                       const float* viewport, const float* tz, const float* target_depth,
+                                       const float* target_mask, float* sums, float* terms, void* stream) {
+    LossGeom g;
+    if (int e = loss_geom(desc, g)) return e;
+    g.premask = 1;
+    LF_CHECK_ARG(depth_logits && mask_logits && viewport && tz && target_depth && target_mask && sums && terms,
+                 "pose_loss_search_fwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(sums, 0, sizeof(float) * 8 * g.n, st);
     const int HW = g.width * g.height;

@@ -73,20 +73,92 @@ def merge_rankings(local_losses, local_params, ranking_size, group=None):
     return losses[order], params[order], owner[order]
 
 
-def build_latent_object_sharded(model, cameras, color, mask, rank=0, world=1, group=None):
+class _AllGatherViews(torch.autograd.Function):
+    """Differentiable all-gather along `dim` of equally sized shards: forward concatenates the ranks' shards in rank
+    order, backward hands every rank the SUM over ranks of the gradient slice that belongs to its shard (each rank
+    back-propagates its own share of the loss through a replica of whatever consumed the gathered tensor)."""
+
+    @staticmethod
+    def forward(ctx, local, dim, group):
+        world = dist.get_world_size(group)
+        ctx.dim, ctx.group, ctx.world, ctx.rank = dim, group, world, dist.get_rank(group)
+        x = local.movedim(dim, 0).contiguous()
+        out = x.new_empty((world * x.shape[0], *x.shape[1:]))
+        dist.all_gather_into_tensor(out, x, group=group)
+        ctx.n = x.shape[0]
+        return out.movedim(0, dim)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.movedim(ctx.dim, 0).contiguous()
+        if dist.get_backend(ctx.group) == 'nccl':
+            part = g.new_empty((ctx.n, *g.shape[1:]))
+            dist.reduce_scatter_tensor(part, g, op=dist.ReduceOp.SUM, group=ctx.group)
+        else:                                   # gloo has no reduce-scatter: all-reduce, keep the own slice
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+            part = g[ctx.rank * ctx.n:(ctx.rank + 1) * ctx.n]
+        return part.movedim(0, ctx.dim), None, None
+
+
+def all_gather_views(local, dim=1, group=None):
+    """autograd-aware all-gather of per-rank view shards (identity when not distributed / world 1)"""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    return _AllGatherViews.apply(local, dim, group)
+
+
+def allreduce_gradients(parameters, group=None):
+    """DDP-style: SUM every parameter gradient over the ranks in one flat bucket (each rank's loss is already its
+    share of the global mean, so the sum is the gradient of the global loss).  Parameters a rank did not touch
+    contribute zeros."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    params = [p for p in parameters if p.requires_grad]
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for p in params:
+        n = p.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n
+
+
+@torch.no_grad()
+def build_latent_object_sharded(model, cameras, color, mask, rank=0, world=1, group=None, depth=None):
     """Sculptor.encode with the reference views sharded over ranks.  `cameras` (V zoomed cameras),
     `color` [1,V,3,H,W] and `mask` [1,V,1,H,W] are the full (replicated) host inputs; each rank encodes its
     slice on its own GPU.  Returns the fused z_obj [1,1,C,S,S,S] on every rank."""
     from .recon import fusion
     from .recon.models import gan_normalize
     dev = model.device
+    sc, fuser = model.sculptor, model.fuser
+    if isinstance(fuser, fusion.BlendFuser):
+        raise NotImplementedError("view-sharded reconstruction does not cover the BlendFuser (it needs the camera-space "
+                                  "intermediates of every view); use Sculptor.encode")
     V = color.shape[1]
     lo, hi = shard_range(V, rank, world)
-    x = torch.cat((color[0, lo:hi], gan_normalize(mask[0, lo:hi])), dim=1).to(dev)
-    z_local, _, _ = model.sculptor(x, cameras[lo:hi].to(dev))                     # [v_local, C, S, S, S]
-    fuser = model.fuser
+    # input planes exactly as Sculptor.encode assembles them (recon/models.py:226-246)
+    planes = []
+    if sc.input_color:
+        planes.append(color[0, lo:hi])
+    if sc.input_depth:
+        if depth is None:
+            raise ValueError("this Sculptor takes a depth plane (input_depth=True)")
+        planes.append(depth[0, lo:hi])
+    if sc.input_mask:
+        planes.append(gan_normalize(mask[0, lo:hi]))
+    x = torch.cat(planes, dim=1).to(dev)
+    z_local, _, _ = sc(x, cameras[lo:hi].to(dev))                                 # [v_local, C, S, S, S]
     if isinstance(fuser, fusion.PoolFuser) and fuser.pool_type in ('mean', 'max') and world > 1:
         return fuse_views_sharded(z_local, fuser.pool_type, V, rank, world, group).unsqueeze(0)
-    z_all = fuse_views_sharded(z_local, 'gather', V, rank, world, group)
+    if world > 1 and V % world == 0:
+        # equal shards: one all_gather_into_tensor straight into the [V, C, S^3] buffer the recurrence reads
+        z_all = z_local.new_empty((V, *z_local.shape[1:]))
+        dist.all_gather_into_tensor(z_all, z_local.contiguous(), group=group)
+    else:
+        z_all = fuse_views_sharded(z_local, 'gather', V, rank, world, group)
     z, _ = fuser(z_all.unsqueeze(0), [], [], cameras.to(dev))
     return z

@@ -849,6 +849,22 @@ class _PoseLoss(torch.autograd.Function):
         return g_dl.view(dshape), g_ml.view(mshape), g_vp, g_tz, None, None, None, None, None, None
 
 
+@torch.no_grad()
+def pose_search_terms(depth_logits, mask_logits, viewport, tz, target_depth, target_mask, z_span, eps=0.01,
+                      width=640, height=480):
+    """forward-only [N,4] (ov_depth, depth, iou, mask) for the coarse search: lf_pose_loss_search_fwd"""
+    _need_cuda(depth_logits, mask_logits, viewport, tz, target_depth, target_mask)
+    n, p = depth_logits.shape[0], depth_logits.shape[-1]
+    dl, ml = depth_logits.float().contiguous().view(n, p, p), mask_logits.float().contiguous().view(n, p, p)
+    desc = L.LossDesc(n, p, width, height, float(z_span), float(eps))
+    sums, terms = torch.empty(n, 8, device=dl.device), torch.empty(n, 4, device=dl.device)
+    _call('lf_pose_loss_search_fwd', L.lib().lf_pose_loss_search_fwd,
+          (ctypes.byref(desc), _p(dl), _p(ml), _p(viewport.float().contiguous()), _p(tz.float().contiguous()),
+           _p(target_depth.float().contiguous().view(height, width)), _p(target_mask.float().contiguous().view(height, width)),
+           _p(sums), _p(terms), _stream()), kernels=3)
+    return terms
+
+
 def pose_loss_terms(depth_logits, mask_logits, viewport, tz, target_depth, target_mask, z_span, eps=0.01,
                     width=640, height=480):
     return _PoseLoss.apply(depth_logits, mask_logits, viewport, tz, target_depth, target_mask, z_span, eps, width, height)

@@ -105,6 +105,7 @@ class PoseEstimator:
         self.return_camera_history, self.verbose = return_camera_history, verbose
 
     device = property(lambda self: self.model.device)
+    group = None
 
     @classmethod
     def initial_pose(cls, target_obs):
@@ -114,9 +115,21 @@ class PoseEstimator:
                                                     cam.height)
 
     def estimate(self, z_obj, target_obs, **kwargs):
+        """`group=` (a torch.distributed process group, or True for the default one) shards the hypotheses / samples
+        over its ranks: the cross-entropy search scores a slice of every generation per rank and all-gathers the
+        scores; the gradient refinement optimises a slice of the hypotheses per rank and merges the rankings at the
+        end (dist.merge_rankings).  Every rank returns the same cameras."""
         if len(target_obs) > 1:
             raise ValueError("The pose can only be estiamted for one observation at a time.")
-        return self._estimate(z_obj, target_obs, **kwargs)
+        group = kwargs.pop('group', None)
+        if group is True:
+            import torch.distributed as dist
+            group = dist.group.WORLD if dist.is_initialized() else None
+        self.group = group
+        try:
+            return self._estimate(z_obj, target_obs, **kwargs)
+        finally:
+            self.group = None
 
     def _estimate(self, z_obj, target_obs, **kwargs):
         raise NotImplementedError()
@@ -197,11 +210,54 @@ class CrossEntropyPoseEstimator(PoseEstimator):
         if self.loss_weights.get('latent', 0.0) > 0.0:
             with torch.no_grad():
                 target_code = self.model.compute_latent_code(target_obs, cameras[0])
-        depth, mask_logits, code, crop = self._render_observation(z_obj, cameras)
-        terms = self.loss_func(target_obs, depth, mask_logits, crop, z_pred_latent=code, z_target_latent=target_code)
-        score = sum(weigh_losses(terms, self.loss_weights).values())
+        # samples shard contiguously over the ranks of `group` (every rank drew the same population: same seed /
+        # broadcast GMM); the [n] scores are all-gathered and every rank picks the same elites
+        lo, hi = self._shard(len(cameras))
+        score = self._score(z_obj, target_obs, cameras[lo:hi] if (lo, hi) != (0, len(cameras)) else cameras, target_code)
+        score = self._gather_scores(score, len(cameras))
         best = torch.argsort(score)[:num_elites]
         return cameras[best], score[best]
+
+    group = None            # torch.distributed process group for sample sharding (None: not sharded)
+
+    def _shard(self, n):
+        import torch.distributed as dist
+        if self.group is None or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return 0, n
+        from .. import dist as lfdist
+        return lfdist.shard_range(n, dist.get_rank(self.group), dist.get_world_size(self.group))
+
+    def _gather_scores(self, score, n):
+        import torch.distributed as dist
+        if score.shape[0] == n:
+            return score
+        from .. import dist as lfdist
+        world = dist.get_world_size(self.group)
+        sizes = [lfdist.shard_range(n, r, world)[1] - lfdist.shard_range(n, r, world)[0] for r in range(world)]
+        return lfdist.all_gather_ragged(score.reshape(-1, 1), sizes, self.group).reshape(-1)
+
+    def _score(self, z_obj, target_obs, cameras, target_code):
+        """weighted fitness of each sample, forward only.  On the device path the crops never become full frames:
+        the raw head outputs go through the fused loss head (csrc/pose_loss.cu, the kernels the graphed refiner
+        uses), the latent term is a cosine distance of the projected features."""
+        ph = self.model.photographer
+        on_device = (self.loss_func is default_pose_loss and target_obs.depth.is_cuda and ph.predict_depth
+                     and ph.predict_mask and not ph.predict_color)
+        if not on_device:
+            depth, mask_logits, code, crop = self._render_observation(z_obj, cameras)
+            terms = self.loss_func(target_obs, depth, mask_logits, crop, z_pred_latent=code, z_target_latent=target_code)
+            return sum(weigh_losses(terms, self.loss_weights).values())
+        from .. import ops
+        crop = cameras.zoom(None, self.model.input_size, self.model.camera_dist).to(self.device)
+        with torch.no_grad():
+            logits, latent, _ = ph.decode(z_obj, crop, interpret_logits=False, return_latent=True)
+            t = ops.pose_search_terms(logits[:, 0], logits[:, 1], crop.viewport, crop.translation[:, 2], target_obs.depth,
+                                      target_obs.mask, crop.z_span, 0.01, crop.width, crop.height)
+            terms = {'ov_depth': t[:, 0], 'depth': t[:, 1], 'iou': t[:, 2], 'mask': t[:, 3]}
+            if target_code is not None:
+                rendered = latent.squeeze(0).flatten(1)
+                terms['latent'] = cosine_distance(rendered, target_code.flatten(1).expand_as(rendered))
+        return sum(weigh_losses(terms, self.loss_weights).values())
 
     def _sample_poses(self, gmm, n):
         """n draws (translation | log-quaternion) from the proposal, jittered so elites never collapse to a point"""
@@ -269,9 +325,16 @@ class GradientPoseEstimator(PoseEstimator):
         target_obs = target_obs.to(self.device)
         # the *zoomed* camera (viewport box around the object) is what gets optimised
         camera = camera.zoom(None, self.model.input_size, self.model.camera_dist).to(self.device)
+        sharded = self._sharded()
+        if sharded:
+            from .. import dist as lfdist
+            lo, hi = lfdist.shard_range(len(camera), sharded[0], sharded[1])
+            camera = camera[lo:hi]
         ranking = []
         stats, history = self._optimize_camera(z_obj, target_obs, camera, iters=self.num_iters, ranking=ranking)
         best = Camera.cat([c for c, _, _ in ranking])
+        if sharded:
+            best = self._merge_ranked(best, torch.tensor([loss for _, loss, _ in ranking]))
         if self.track_stats and self.return_camera_history:
             return best, stats, history
         if self.track_stats:
@@ -279,6 +342,24 @@ class GradientPoseEstimator(PoseEstimator):
         if self.return_camera_history:
             return best, history
         return best
+
+    def _sharded(self):
+        import torch.distributed as dist
+        if self.group is None or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return None
+        return dist.get_rank(self.group), dist.get_world_size(self.group)
+
+    def _merge_ranked(self, cameras, losses):
+        """global top-`ranking_size` over all ranks' local rankings (tiny all-gather of losses + the 6 pose floats)"""
+        from .. import dist as lfdist
+        dev = self.device
+        params = torch.cat([cameras.translation, cameras.log_quaternion], dim=-1).to(dev)
+        top_l, top_p, _ = lfdist.merge_rankings(losses.to(dev), params, self.ranking_size, self.group)
+        top_p = top_p.cpu()
+        k = top_p.shape[0]
+        return Camera(cameras.intrinsic[:1].cpu().expand(k, -1, -1).contiguous(), None, cameras.z_span, None,
+                      width=cameras.width, height=cameras.height, log_quaternion=top_p[:, 3:].contiguous(),
+                      translation=top_p[:, :3].contiguous())
 
     @classmethod
     def get_optimizer(cls, name, *args, **kwargs):
@@ -294,8 +375,7 @@ class GradientPoseEstimator(PoseEstimator):
     def _optimize_camera_graphed(self, z_obj, target_obs, cameras, iters, ranking):
         from .refine_graph import GraphedRefiner
         refiner = getattr(self, '_refiner', None)
-        probe = (len(cameras), tuple(z_obj.shape), tuple(target_obs.depth.shape), cameras.width, cameras.height,
-                 cameras.z_span)
+        probe = GraphedRefiner.make_signature(self, z_obj, target_obs, cameras, self.graph_chunk)
         if refiner is not None and refiner.signature() == probe:
             refiner.reset(z_obj, target_obs, cameras)           # same shapes: reuse the captured graph
         else:

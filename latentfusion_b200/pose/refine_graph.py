@@ -99,6 +99,7 @@ class GraphedRefiner:
         self.h_tr = torch.zeros(chunk, n, 3, device=dev)
         self.slot = torch.zeros(1, dtype=torch.long, device=dev)
         self.graph = None
+        self._signature = self.make_signature(estimator, z_obj, target_obs, cameras, chunk)
 
     # ---- one iteration, device only ----
     def _camera(self):
@@ -141,9 +142,20 @@ class GraphedRefiner:
         for k, sched in self.est.loss_schedules.items():
             self.sched_w[k].fill_(float(sched.get(step)))
 
+    @staticmethod
+    def make_signature(est, z_obj, target_obs, cameras, chunk):
+        """Everything the captured graph bakes in: shapes, the identity AND version of every network parameter (the
+        graph holds raw pointers into the packed-weight caches, which are keyed by parameter version), the convolution
+        precision, the loss weights / schedules and the optimiser hyper-parameters.  A mismatch means re-capture."""
+        model = est.model
+        params = tuple((id(p), p._version) for net in (model.photographer,) for p in net.parameters())
+        return (len(cameras), tuple(z_obj.shape), tuple(target_obs.depth.shape), cameras.width, cameras.height,
+                cameras.z_span, params, ops.get_default_precision(), tuple(sorted(est.loss_weights.items())),
+                tuple(sorted(est.loss_schedules)), est.learning_rate, est.lr_reduce_patience, est.lr_reduce_threshold,
+                est.lr_reduce_factor, bool(est.fused_loss), int(chunk))
+
     def signature(self):
-        return (self.n, tuple(self.z_obj.shape), tuple(self.target.depth.shape), self.template.width,
-                self.template.height, self.template.z_span)
+        return self._signature
 
     @torch.no_grad()
     def reset(self, z_obj, target_obs, cameras):
@@ -160,7 +172,14 @@ class GraphedRefiner:
         self.slot.zero_()
 
     def capture(self):
-        ops.KernelTrace.enabled = False
+        trace_was = ops.KernelTrace.enabled
+        ops.KernelTrace.enabled = False               # no CUDA events between captured nodes
+        try:
+            self._capture()
+        finally:
+            ops.KernelTrace.enabled = trace_was
+
+    def _capture(self):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         state = self._save_state()

@@ -99,6 +99,9 @@ class LatentFusionModel(object):
         options = dict(apply_mask=True, return_latent=False)
         pred = (self.render_latent_object(z_obj, cam, **options) if input_obs is None
                 else self.render_ibr_basic(z_obj, input_obs, cam, p=p, **options))[0]
+        # (the reference hands the [1, V, ...] render straight to Camera.uncrop, whose 2-D sampler rejects 5-D input;
+        #  the object axis is dropped here so the method actually runs — one object at a time, as everywhere in this class)
+        pred = {k: (v.squeeze(0) if v.dim() == 5 else v) for k, v in pred.items()}
         full = {'depth': cam.uncrop(cam.denormalize_depth(pred['depth']) * pred['mask'])[0],
                 'mask': cam.uncrop(pred['mask'])[0]}
         if 'color' in pred:
