@@ -352,6 +352,15 @@ def run_ours(args):
                   "hypothesis_renders_per_s": 64 * 1000.0 / ms_s, "steps": 5}
         del est_s
 
+    # ---------------- configs[3]: one reconstruction training iteration, views sharded over the ranks ----------------
+    train = None
+    if not args.no_train:
+        train = train_block(args, dev, rank, world, barrier, max_over_ranks)
+    # ---------------- configs[4]: cross-entropy coarse search on the latent loss, 128^3 cube, samples sharded --------
+    search = None
+    if not args.no_search:
+        search = search_block(args, dev, rank, world, barrier, max_over_ranks)
+
     # ---------------- end-to-end through the public API with HOST buffers ----------------
     # One user-level call: estimator.estimate(z_obj, HOST target observation, HOST hypothesis cameras) for K
     # iterations.  Inside the timed region: the H2D copy of the target (colour+depth+mask, pinned) and of the
@@ -447,10 +456,127 @@ def run_ours(args):
                     "note": "one estimator.estimate(z_obj, host target obs, host cameras) call of K iterations / K: includes H2D of target+cameras (graph captured once, during warm-up), per-iteration D2H of losses and camera snapshots"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_resample": resample_roof,
             "kernels": kernels, "cpu_baseline": cpu, "reference_cuda": ref_cuda, "strong_scaling": strong,
+            "train_step": train, "coarse_search": search,
             "recon": {"ms": round(recon_ms, 2), "ms_first_call": round(recon_times[0], 2), "views": V,
                       "views_per_gpu": (V + world - 1) // world, "fuser": "gru",
                       "note": "LatentFusionModel.build_latent_object, views sharded over the ranks (dist.py), max over ranks"}}
     print(json.dumps(line), flush=True)
+
+
+def train_block(args, dev, rank, world, barrier, max_over_ranks, B=8, vin=16, vout=8):
+    """BASELINE configs[3]: ReconTrainer.run_iteration (generator half, released recipe) on B objects x vin input views,
+    vout reconstruction views, LF-synth(64, 32).  The views of every object shard over the ranks (each rank encodes
+    vin/world views, decodes vout/world), per-view cubes are all-gathered with a differentiable collective, weight
+    gradients all-reduced in one flat bucket (latentfusion_b200/train.py)."""
+    from tests import parity_helpers as ph
+    from latentfusion_b200 import ops
+    from latentfusion_b200.train import ReconTrainStep
+    torch.cuda.reset_peak_memory_stats()
+    if vin % world or vout % world:
+        return {"skipped": f"views ({vin} in / {vout} out) do not divide over {world} ranks"}
+    import torch.distributed as dist
+    sculptor, fuser, photographer, _, _ = ph.random_lfsynth(S, C, seed=0, device=dev)
+    step = ReconTrainStep(sculptor, fuser, photographer, depth_k=4096, group=(dist.group.WORLD if world > 1 else None))
+    P, vi, vo = 2 * S, vin // world, vout // world
+    cin, _ = ph.synthetic_cameras(B * vin, S, seed=21, perturb=False)
+    cout, _ = ph.synthetic_cameras(B * vout, S, seed=22, perturb=False)
+    pick = lambda cams, v, vl: cams[[b * v + rank * vl + j for b in range(B) for j in range(vl)]]    # noqa: E731
+    g = torch.Generator().manual_seed(23 + rank)
+    host = {'image': (torch.rand(B, vi, 3, P, P, generator=g) * 2 - 1).pin_memory(),
+            'mask': (torch.rand(B, vi, 1, P, P, generator=g) > 0.4).float().pin_memory(),
+            'depth': (torch.rand(B, vo, 1, P, P, generator=g) * 2 - 1).pin_memory(),
+            'gmask': (torch.rand(B, vo, 1, P, P, generator=g) > 0.5).float().pin_memory()}
+
+    def one():
+        batch = {'in': {'camera': pick(cin, vin, vi).to(dev), 'image': host['image'].to(dev, non_blocking=True),
+                        'mask': host['mask'].to(dev, non_blocking=True)},
+                 'out_gt': {'camera': pick(cout, vout, vo).to(dev), 'depth': host['depth'].to(dev, non_blocking=True),
+                            'mask': host['gmask'].to(dev, non_blocking=True)}}
+        return float(step.run_iteration(batch)['total'])          # D2H of the loss: the step's result
+    one()
+    ops.KernelTrace.reset(False)
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    steps = 2
+    for _ in range(steps):
+        loss = one()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    launches = ops.KernelTrace.launches // steps
+    mem = torch.cuda.max_memory_allocated() / 2 ** 30
+    del step, sculptor, fuser, photographer
+    torch.cuda.empty_cache()
+    return {"workload": f"configs[3]: {B} objects x {vin} input + {vout} reconstruction views, LF-synth({S},{C}), "
+                        f"hard smooth-L1 depth + BCE mask, Adam(0, 0.99); views sharded x{world}",
+            "ms_per_step": round(ms, 2), "object_views_per_s": round(B * (vin + vout) * 1000.0 / ms, 2), "steps": steps,
+            "loss": loss, "lfb200_launches_per_step": launches, "peak_mem_gb": round(mem, 1),
+            "h2d_bytes_per_step": sum(t.numel() * 4 for t in host.values()), "precision": args.precision,
+            "note": "e2e: pinned host batch -> device inside the timed region, loss read back every step; weight gradients "
+                    "by lf_conv_bwd_weight"}
+
+
+def search_block(args, dev, rank, world, barrier, max_over_ranks, S4=128, C4=16, gens=2):
+    """BASELINE configs[4]: CrossEntropyPoseEstimator with configs/cross_entropy_latent.toml (latent = 1.0, 96 samples x
+    flips per generation) on a 128^3 latent cube: reconstruction of 16 views sharded over the ranks (NCCL all-gather of
+    the per-view cubes), then `gens` timed generations whose samples shard over the ranks (scores all-gathered)."""
+    import torch.distributed as dist
+    from tests import parity_helpers as ph
+    from latentfusion_b200 import dist as lfdist
+    from latentfusion_b200.observation import Observation
+    from latentfusion_b200.pose import estimation
+    from latentfusion_b200.recon.inference import LatentFusionModel
+    torch.cuda.reset_peak_memory_stats()
+    sculptor, fuser, photographer, _, _ = ph.random_lfsynth(S4, C4, seed=0, device=dev)
+    ref_cams, dist_ = ph.synthetic_cameras(V, S4, seed=31, perturb=False)
+    gt, _ = ph.synthetic_cameras(1, S4, seed=32, perturb=False)
+    model = LatentFusionModel(sculptor, fuser, photographer, dist_, dev)
+    P = 2 * S4
+    g = torch.Generator().manual_seed(33)
+    color = torch.rand(1, V, 3, P, P, generator=g) * 2 - 1
+    mask = (torch.rand(1, V, 1, P, P, generator=g) > 0.3).float()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    recon = []
+    for _ in range(2):
+        barrier(); e0.record()
+        with torch.no_grad():
+            z_obj = lfdist.build_latent_object_sharded(model, ref_cams, color, mask, rank, world)
+        e1.record(); barrier()
+        recon.append(max_over_ranks(e0.elapsed_time(e1)))
+    yy, xx = torch.meshgrid(torch.arange(480, dtype=torch.float32), torch.arange(640, dtype=torch.float32), indexing='ij')
+    tmask = (((yy - 251.5) ** 2 + (xx - 315.4) ** 2) <= 45.0 ** 2).float().view(1, 1, 480, 640)
+    gt_full = gt.uncrop()
+    # (a sloped disc: the reference's initial-pose estimate rejects outliers by MAD, which is 0 on a constant depth)
+    tdepth = tmask * (dist_ + 0.05 * ((xx - 315.4) / 45.0).view(1, 1, 480, 640))
+    target = Observation(torch.rand(1, 3, 480, 640, generator=g), tdepth, tmask, gt_full).to(dev)
+    cfg = {'type': 'cross_entropy',
+           'args': dict(num_samples=96, num_iters=30, ranking_size=16, num_elites=48, num_gmm_components=6,
+                        learning_rate=0.3, sample_flipped=True, init_hemisphere=False, init_upright=False),
+           'loss_weights': dict(depth=0.0, ov_depth=0.0, iou=0.0, mask=0.0, latent=1.0)}
+    est = estimation.load_from_config(cfg, model)
+    est.verbose = False
+    est.num_iters = 1                         # (the elite schedule keeps the config's 30-generation horizon)
+    group = dist.group.WORLD if world > 1 else None
+    torch.manual_seed(5)                      # every rank draws the same population
+    import numpy as np
+    np.random.seed(5)
+    est.estimate(z_obj, target, group=group)                      # warm-up generation
+    est.num_iters = gens
+    barrier(); e0.record()
+    est.estimate(z_obj, target, group=group)
+    e1.record(); barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / gens
+    renders = getattr(est, 'last_renders_per_generation', None) or 96
+    mem = torch.cuda.max_memory_allocated() / 2 ** 30
+    del est, model
+    torch.cuda.empty_cache()
+    return {"workload": f"configs[4]: cross_entropy_latent.toml (latent=1.0), LF-synth({S4},{C4}), 16 ref views; "
+                        f"samples sharded x{world}", "ms_per_generation": round(ms, 2), "renders_per_generation": renders,
+            "renders_per_s": round(renders * 1000.0 / ms, 1), "generations": gens,
+            "recon_ms": round(recon[-1], 2), "recon_ms_first_call": round(recon[0], 2), "peak_mem_gb": round(mem, 1),
+            "note": "generation = sample (GMM, host) -> zoom -> Photographer.decode forward -> fused forward-only loss head + latent "
+                    "cosine -> all-gather scores -> refit GMM on elites (host, sklearn)"}
 
 
 def cpu_baseline(sds, arch, inp):
@@ -521,6 +647,8 @@ def main():
     ap.add_argument('--no-kernel-events', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-strong', action='store_true', help='skip the configs[2] strong-scaling extra')
+    ap.add_argument('--no-train', action='store_true', help='skip the configs[3] training-iteration extra')
+    ap.add_argument('--no-search', action='store_true', help='skip the configs[4] coarse-search extra')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.hypotheses != N_HYP:

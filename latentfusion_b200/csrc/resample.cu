@@ -284,11 +284,25 @@ __device__ __forceinline__ float4 ldg_f4_at(const float4* base, uint32_t off) {
     return v;
 }
 
-template <int MODE, int LPVL, int MINB>
+// 256-bit variant (sm_100: LDG.E.ENL2.256): 8 channels per lane, so a voxel of C channels is C/8 lanes and one warp
+// instruction moves twice the voxels — half the LSU / address / predicate instructions per byte of the 128-bit form
+__device__ __forceinline__ void ldg_f8_at(const float4* base, uint32_t off, float4& a, float4& b) {
+    unsigned long long addr;
+    asm("mad.wide.u32 %0, %1, 32, %2;" : "=l"(addr) : "r"(off), "l"(base));
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(addr));
+}
+__device__ __forceinline__ void stcs_f8(float4* p, const float4& a, const float4& b) {
+    asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
+
+// W = float4s per lane (1: 128-bit accesses, C = 4*LPV; 2: 256-bit accesses, C = 8*LPV)
+template <int MODE, int LPVL, int MINB, int W>
 __global__ void __launch_bounds__(256, MINB)
 resample_march_kernel(const float* __restrict__ vol, const float* __restrict__ cam, float* __restrict__ out,
                       int views_per_obj, int N, int S, int KC) {
-    constexpr int LPV = 1 << LPVL, G = 32 / LPV, C = 4 * LPV;
+    constexpr int LPV = 1 << LPVL, G = 32 / LPV, C = 4 * W * LPV;
     constexpr int TI = 2 * G, TJ = 4;
     // record buffer of one warp and one round: 4 components (offsets 0-3, offsets 4-7, weights 0-3, weights 4-7) x
     // one 16-byte slot per (group, step); a group's slots are followed by one pad slot so that the 4 groups of a
@@ -323,9 +337,9 @@ resample_march_kernel(const float* __restrict__ vol, const float* __restrict__ c
 
     const int64_t S3 = (int64_t)S * S * S;
     const float4* vcube = reinterpret_cast<const float4*>(vol + (int64_t)(MODE == 0 ? n / views_per_obj : n) * S3 * C);
-    const float4* vb = vcube + sub;
-    float4* op = reinterpret_cast<float4*>(out + ((((int64_t)n * S + k0) * S + jc) * S + ic) * C) + sub;
-    const int64_t ostep = (int64_t)S * S * LPV;            // float4 units per depth step
+    const float4* vb = vcube + sub * W;
+    float4* op = reinterpret_cast<float4*>(out + ((((int64_t)n * S + k0) * S + jc) * S + ic) * C) + sub * W;
+    const int64_t ostep = (int64_t)S * S * LPV * W;        // float4 units per depth step
     const int slot = g * (LPV + 1) + sub;
 
     // ---- phase 1: lane (g, sub) prepares depth step kr + sub of column g
@@ -361,7 +375,7 @@ resample_march_kernel(const float* __restrict__ vol, const float* __restrict__ c
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int px = q & 1, py = (q >> 1) & 1, pz = q >> 2;
-            off[q] = (uint32_t)((Z[pz] * S + Y[py]) * S + X[px]) * LPV;       // float4 units
+            off[q] = (uint32_t)((Z[pz] * S + Y[py]) * S + X[px]) * LPV;       // units of one lane's W float4s
             w[q] = WX[px] * (WY[py] * WZ[pz]);
         }
         rec[warp][0][slot] = make_uint4(off[0], off[1], off[2], off[3]);
@@ -371,9 +385,13 @@ resample_march_kernel(const float* __restrict__ vol, const float* __restrict__ c
     };
 
     uint32_t held[8];
-    float4 val[8];
+    float4 val[8][W];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) { held[q] = 0xffffffffu; val[q] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    for (int q = 0; q < 8; ++q) {
+        held[q] = 0xffffffffu;
+#pragma unroll
+        for (int h = 0; h < W; ++h) val[q][h] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 
     for (int kr = k0; kr < k1; kr += LPV) {
         prepare(kr);
@@ -389,13 +407,24 @@ resample_march_kernel(const float* __restrict__ vol, const float* __restrict__ c
                                 __uint_as_float(w1.x), __uint_as_float(w1.y), __uint_as_float(w1.z), __uint_as_float(w1.w)};
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                if (col_ok && off[q] != held[q]) val[q] = ldg_f4_at(vb, off[q]);
+                if (col_ok && off[q] != held[q]) {
+                    if (W == 1) val[q][0] = ldg_f4_at(vb, off[q]);
+                    else ldg_f8_at(vb, off[q], val[q][0], val[q][W - 1]);
+                }
                 held[q] = off[q];          // (a slot is current after every step: no conditional bookkeeping)
             }
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 acc[W];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) Vec<4>::fma(acc, w[q], val[q]);
-            if (col_ok) __stcs(op, acc);
+            for (int h = 0; h < W; ++h) acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+#pragma unroll
+                for (int h = 0; h < W; ++h) Vec<4>::fma(acc[h], w[q], val[q][h]);
+            }
+            if (col_ok) {
+                if (W == 1) __stcs(op, acc[0]);
+                else stcs_f8(op, acc[0], acc[W - 1]);
+            }
             op += ostep;
         }
         __syncwarp();
@@ -608,7 +637,7 @@ static int env_int(const char* name, int dflt) {
     return (e && e[0]) ? atoi(e) : dflt;
 }
 
-template <int MODE, int LPVL>
+template <int MODE, int LPVL, int W>
 static int launch_march(const float* vol, const float* cam, float* out, int vpo, int N, int S, cudaStream_t st) {
     constexpr int LPV = 1 << LPVL, G = 32 / LPV;
     const int64_t cols = (int64_t)N * ((S + 2 * G - 1) / (2 * G)) * ((S + 3) / 4);
@@ -619,7 +648,7 @@ static int launch_march(const float* vol, const float* cam, float* out, int vpo,
     { const int k = env_int("LFB200_RESAMPLE_KC", 0); if (k >= LPV) KC = k / LPV * LPV; }
     const int64_t blocks = cols * ((S + KC - 1) / KC);
     LF_CHECK_ARG(blocks < (1ll << 31), "resample: too many columns");
-    resample_march_kernel<MODE, LPVL, 3><<<(unsigned)blocks, 256, 0, st>>>(vol, cam, out, vpo, N, S, KC);
+    resample_march_kernel<MODE, LPVL, (W == 1 ? 3 : 2), W><<<(unsigned)blocks, 256, 0, st>>>(vol, cam, out, vpo, N, S, KC);
     LF_RETURN_LAUNCH();
 }
 
@@ -632,9 +661,15 @@ static bool use_march() {
 template <int MODE>
 static int launch_fwd(const float* vol, const float* cam, float* out, int vpo, int N, int C, int S, cudaStream_t st) {
     if (use_march() && (int64_t)S * S * S * (C / 4) < (1ll << 32)) {
-        if (C == 16) return launch_march<MODE, 2>(vol, cam, out, vpo, N, S, st);
-        if (C == 32) return launch_march<MODE, 3>(vol, cam, out, vpo, N, S, st);
-        if (C == 64) return launch_march<MODE, 4>(vol, cam, out, vpo, N, S, st);
+        const int wide = env_int("LFB200_RESAMPLE_W", 1);
+        if (wide == 2) {
+            if (C == 16) return launch_march<MODE, 1, 2>(vol, cam, out, vpo, N, S, st);
+            if (C == 32) return launch_march<MODE, 2, 2>(vol, cam, out, vpo, N, S, st);
+            if (C == 64) return launch_march<MODE, 3, 2>(vol, cam, out, vpo, N, S, st);
+        }
+        if (C == 16) return launch_march<MODE, 2, 1>(vol, cam, out, vpo, N, S, st);
+        if (C == 32) return launch_march<MODE, 3, 1>(vol, cam, out, vpo, N, S, st);
+        if (C == 64) return launch_march<MODE, 4, 1>(vol, cam, out, vpo, N, S, st);
     }
     const int64_t blocks = (int64_t)N * brick_grid(S, BX, BY, BZ).per_cam();
     LF_CHECK_ARG(blocks < (1ll << 31), "resample: too many bricks");

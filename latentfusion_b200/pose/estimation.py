@@ -248,16 +248,22 @@ class CrossEntropyPoseEstimator(PoseEstimator):
             terms = self.loss_func(target_obs, depth, mask_logits, crop, z_pred_latent=code, z_target_latent=target_code)
             return sum(weigh_losses(terms, self.loss_weights).values())
         from .. import ops
-        crop = cameras.zoom(None, self.model.input_size, self.model.camera_dist).to(self.device)
+        crops = cameras.zoom(None, self.model.input_size, self.model.camera_dist).to(self.device)
+        scores = []
         with torch.no_grad():
-            logits, latent, _ = ph.decode(z_obj, crop, interpret_logits=False, return_latent=True)
-            t = ops.pose_search_terms(logits[:, 0], logits[:, 1], crop.viewport, crop.translation[:, 2], target_obs.depth,
-                                      target_obs.mask, crop.z_span, 0.01, crop.width, crop.height)
-            terms = {'ov_depth': t[:, 0], 'depth': t[:, 1], 'iou': t[:, 2], 'mask': t[:, 3]}
-            if target_code is not None:
-                rendered = latent.squeeze(0).flatten(1)
-                terms['latent'] = cosine_distance(rendered, target_code.flatten(1).expand_as(rendered))
-        return sum(weigh_losses(terms, self.loss_weights).values())
+            for lo in range(0, len(crops), self.render_chunk):          # bounds the frustum-volume working set
+                crop = crops[lo:lo + self.render_chunk]
+                logits, latent, _ = ph.decode(z_obj, crop, interpret_logits=False, return_latent=True)
+                t = ops.pose_search_terms(logits[:, 0], logits[:, 1], crop.viewport, crop.translation[:, 2],
+                                          target_obs.depth, target_obs.mask, crop.z_span, 0.01, crop.width, crop.height)
+                terms = {'ov_depth': t[:, 0], 'depth': t[:, 1], 'iou': t[:, 2], 'mask': t[:, 3]}
+                if target_code is not None:
+                    rendered = latent.squeeze(0).flatten(1)
+                    terms['latent'] = cosine_distance(rendered, target_code.flatten(1).expand_as(rendered))
+                scores.append(sum(weigh_losses(terms, self.loss_weights).values()))
+        return torch.cat(scores)
+
+    render_chunk = 32
 
     def _sample_poses(self, gmm, n):
         """n draws (translation | log-quaternion) from the proposal, jittered so elites never collapse to a point"""

@@ -26,7 +26,7 @@ def main():
         agg[k][0] += 1
         agg[k][1] += v
     tot = sum(v for _, v in agg.values())
-    ours = sum(v for k, (_, v) in agg.items() if 'lf::' in k or 'tc::' in k or k.startswith('lf') or 'conv_tc' in k)
+    ours = sum(v for k, (_, v) in agg.items() if 'lf::' in k or 'tc::' in k or 'dz::' in k or k.startswith('lf') or 'conv_tc' in k)
     print(f"{n} launches in the whole command; table = last {tail:.0%} of launches (graph replays of the refine iteration), "
           f"durations are cold-cache/serialised (ns): compare SHARES")
     print(f"share of lfb200 kernels: {100 * ours / tot:.1f}%   (torch glue {100 * (1 - ours / tot):.1f}%)\n")
