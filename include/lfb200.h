@@ -224,6 +224,18 @@ int lf_pose_loss_bwd(const lf_loss_desc* desc, const float* depth_logits, const 
                      float* grad_depth_logits, float* grad_mask_logits, float* grad_viewport /* [N][4] */,
                      float* grad_tz /* [N] */, void* stream);
 
+/* ---- weight gradient of the 3x3x3 convolution on the tensor cores (csrc/conv3d_dw.cu) ----
+ * Replaces the autograd of modules/equalized.py:57-64 w.r.t. the weight inside ReconTrainer.run_iteration
+ * (tools/train/train_reconstruct.py:523-534).  x_split / du_split: split-planar volumes (layout above) of the forward
+ * input and of d(loss)/d(pre-activation output).  grad_w_packed [27][Cin][Cout] = sum over positions of
+ * desc->scale * x[pos + tap] (.) du[pos] (overwritten; same quantity as lf_conv_bwd_weight);
+ * grad_bias [Cout] (nullable) = sum of du.  Supported: precision 1 with Cin_pad in {16, 32}, precision 2 with Cin_pad 32;
+ * Cout_pad <= 32.  ws: lf_conv3d_dw_ws(desc) floats of scratch.  Deterministic (fixed-order two-stage sums). */
+int lf_conv3d_dw_supported(const lf_conv_desc* desc);
+int64_t lf_conv3d_dw_ws(const lf_conv_desc* desc);
+int lf_conv3d_dw(const lf_conv_desc* desc, const void* x_split, const void* du_split, float* ws,
+                 float* grad_w_packed, float* grad_bias, void* stream);
+
 /* bwd-data convolution (or depth-expand, ndim -1) with the PixelNorm/LeakyReLU backward of the PRODUCER of the forward
  * input fused into the epilogue: writes du_prev = actnorm_bwd(conv_bwd_data(du), y_prev, rnorm_prev) in one kernel
  * (replaces blocks.py:152-164's autograd of conv -> LeakyReLU -> PixelNorm between two stacked convolutions).

@@ -1,0 +1,382 @@
+// Weight gradient of the 3x3x3 Equalized convolution on the 5th-gen tensor cores (sm_100a).
+//
+// Reference op: the autograd of modules/equalized.py:57-64 inside ReconTrainer.run_iteration
+// (tools/train/train_reconstruct.py:523-534) — 90 % of a training iteration while it ran on the FFMA kernel.
+//
+//   dW[dz][dy][dx][ci][co] = sum over (n, d, h, w) of  x[n, d+dz-1, h+dy-1, w+dx-1, ci] * du[n, d, h, w, co]
+//
+// GEMM view: M = ci, N = co, K = positions — tiny M and N, enormous K.  Both operands arrive in the library's
+// split-planar layout [hi|lo][n][d][c/8][(H+2)(W+2)][8 x bf16] (zero halo), i.e. with K (the flattened padded
+// position) strided by 16 bytes and 8 channels contiguous: that is exactly the UMMA *MN-major* no-swizzle canonical
+// form (core matrix = 8 positions x 8 channels = 128 contiguous bytes, LBO = 128 B between k-groups, SBO = the
+// stride between 8-channel groups), so a run of positions is staged by plain 1-D bulk TMA copies and consumed
+// without any transposition.  A filter tap is a start-address offset of the x operand relative to the du operand;
+// halo positions hold zeros in both, so the sum simply runs over the interior span of the flattened padded plane.
+//
+// To give the instruction a useful shape the M dimension is filled with
+//     [x_hi(ci) ; x_lo(ci)]  x  NCOPY copies of the same run shifted by +1 position (consecutive dx taps)
+// and N with [du_hi(co) | du_lo(co)]: ONE M=128 MMA yields all four hi/lo products of up to four dx taps (the row
+// and column halves are added in the reduction; hi*hi + hi*lo + lo*hi + lo*lo is the exact product of the bf16x2
+// splits, fp32 accumulation in TMEM).  A CTA owns one dy tap (dyt = blockIdx % 3: the x run is offset by
+// (dyt-1) rows), all three dz (x plane e pairs with du planes e+1, e, e-1: a 4-slot ring of du planes) and a
+// strided set of (sample, 128-position chunk) columns that it marches through in depth; its 3*NM accumulators
+// (<= 384 TMEM columns) live across all its items and are written once, as per-CTA partials that a second kernel
+// sums in a fixed order (deterministic, no atomics).
+#include "tc_common.cuh"
+
+#include <cuda_bf16.h>
+
+namespace lf {
+namespace dw {
+
+using namespace tcx;
+
+constexpr int kThreads = 256;      // warp 0: TMA producer, 1: MMA issuer, 2: TMEM allocator, 4..7: epilogue
+constexpr int kXStages = 2;
+constexpr int kDyRing = 4;
+constexpr int kChunk = 128;        // positions per item step (8 k-steps of 16)
+
+struct Params {
+    const uint16_t* x;             // split-planar forward input (hi part; lo part at + x_part)
+    const uint16_t* dy;            // split-planar gradient of the pre-activation output
+    int64_t x_part, dy_part;       // elements per part
+    const uint16_t* x_end;         // one past the last element that may be read (copies are clamped to it)
+    const uint16_t* dy_end;
+    float* ws;                     // [ctas][NACC][128][N] partial accumulators
+    int n, d, Wp, PP, KCi, KCo, nparts;
+    int NCOPY, NM, R, N;           // x copies stacked in M, MMAs per dz, rows per copy, columns
+    int span, nchunks, items, G;   // interior positions per plane, 128-position chunks, (sample, chunk) items, CTAs per dy tap
+    int Lx;                        // positions per x region (allocated)
+    uint32_t x_stage_bytes, dy_slot_bytes;
+};
+
+// instruction descriptor: kind::f16, D = F32, A = B = BF16, BOTH MN-major (bits 15, 16), M = 128
+__device__ __forceinline__ uint32_t idesc_mn(uint32_t n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3d_dw_kernel(const __grid_constant__ Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t xs0 = smem_u32(smem);
+    const uint32_t dys0 = xs0 + kXStages * p.x_stage_bytes;
+    uint8_t* tail = smem + (size_t)kXStages * p.x_stage_bytes + (size_t)kDyRing * p.dy_slot_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);     // full_x[2] empty_x[2] full_dy[4] empty_dy[4] done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kXStages + 2 * kDyRing + 1);
+    uint32_t* touched_s = tmem_slot + 1;
+    const uint32_t bar_fx = smem_u32(bars), bar_ex = bar_fx + 8 * kXStages;
+    const uint32_t bar_fd = bar_ex + 8 * kXStages, bar_ed = bar_fd + 8 * kDyRing, bar_done = bar_ed + 8 * kDyRing;
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const int dyt = blockIdx.x % 3, slot = blockIdx.x / 3;
+
+    // stale bytes behind a clamped copy must be finite: they are multiplied by du halo zeros
+    for (uint32_t i = threadIdx.x * 16; i < kXStages * p.x_stage_bytes; i += kThreads * 16)
+        *reinterpret_cast<uint4*>(smem + i) = make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2 * kXStages + 2 * kDyRing + 1; ++i) mbar_init(bar_fx + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int NACC = 3 * p.NM;
+    const uint32_t x_region = (uint32_t)p.Lx * 16u;                 // bytes per 8-channel group of one copy
+    const int xg = p.R / 8;                                         // 8-channel groups per copy (parts x chunks)
+    const int dg = p.N / 8;
+    const int first = p.Wp + 1;                                     // first interior position of a padded plane
+
+    if (warp == 0) {
+        // =========================== TMA PRODUCER ===========================
+        if (lane == 0) {
+            uint32_t sx = 0, pc = 0;                                 // x stage counter, du plane counter
+            for (int item = slot; item < p.items; item += p.G) {
+                const int n = item / p.nchunks, c = item - n * p.nchunks;
+                const int q0 = first + c * kChunk;
+                const int ksteps = min(kChunk / 16, (p.span - c * kChunk + 15) / 16);
+                const uint32_t dy_bytes = (uint32_t)ksteps * 256u;
+                const uint32_t x_bytes = (uint32_t)(ksteps * 16 + (p.NM - 1) * p.NCOPY) * 16u;
+                auto load_dy = [&](int dpl) {
+                    const uint32_t r = pc + (uint32_t)dpl, sl = r % kDyRing;
+                    mbar_wait(bar_ed + 8 * sl, ((r / kDyRing) & 1) ^ 1, 11);
+                    uint32_t total = 0;
+                    uint32_t bytes[16];
+                    const uint16_t* src[16];
+                    for (int g = 0; g < dg; ++g) {
+                        const int part = g / p.KCo, kc = g - part * p.KCo;
+                        src[g] = p.dy + part * p.dy_part + ((((int64_t)n * p.d + dpl) * p.KCo + kc) * p.PP + q0) * 8;
+                        const int64_t avail = (p.dy_end - src[g]) * 2;
+                        bytes[g] = avail <= 0 ? 0u : (uint32_t)min((int64_t)dy_bytes, avail);
+                        total += bytes[g];
+                    }
+                    mbar_arrive_expect_tx(bar_fd + 8 * sl, total);
+                    for (int g = 0; g < dg; ++g)
+                        if (bytes[g]) bulk_g2s(dys0 + sl * p.dy_slot_bytes + g * (kChunk * 16), src[g], bytes[g], bar_fd + 8 * sl);
+                };
+                load_dy(0);
+                for (int e = 0; e < p.d; ++e, ++sx) {
+                    const uint32_t st = sx % kXStages;
+                    mbar_wait(bar_ex + 8 * st, ((sx / kXStages) & 1) ^ 1, 12);
+                    uint32_t total = 0;
+                    uint32_t bytes[16];
+                    const uint16_t* src[16];
+                    for (int r = 0; r < p.NCOPY * xg; ++r) {
+                        const int cp = r / xg, g = r - cp * xg;
+                        const int part = g / p.KCi, kc = g - part * p.KCi;
+                        const int64_t pos = (int64_t)q0 + (dyt - 1) * p.Wp - 1 + cp;
+                        src[r] = p.x + part * p.x_part + ((((int64_t)n * p.d + e) * p.KCi + kc) * p.PP + pos) * 8;
+                        const int64_t avail = (p.x_end - src[r]) * 2;
+                        bytes[r] = avail <= 0 ? 0u : (uint32_t)min((int64_t)x_bytes, avail);
+                        total += bytes[r];
+                    }
+                    mbar_arrive_expect_tx(bar_fx + 8 * st, total);
+                    for (int r = 0; r < p.NCOPY * xg; ++r)
+                        if (bytes[r]) bulk_g2s(xs0 + st * p.x_stage_bytes + r * x_region, src[r], bytes[r], bar_fx + 8 * st);
+                    if (e + 1 < p.d) load_dy(e + 1);
+                }
+                pc += (uint32_t)p.d;
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA ISSUER ===========================
+        const uint32_t idesc = idesc_mn((uint32_t)p.N);
+        const uint32_t a_hi = (uint32_t)p.Lx | (1u << 14);           // SBO = one x region (16-byte units), version 1
+        const uint32_t b_hi = (uint32_t)kChunk | (1u << 14);         // SBO = one du region
+        const uint32_t lbo = 8u << 16;                               // LBO = 128 bytes: the next 8 positions
+        uint32_t touched = 0, sx = 0, pc = 0;
+        for (int item = slot; item < p.items; item += p.G) {
+            const int c = item % p.nchunks;
+            const int ksteps = min(kChunk / 16, (p.span - c * kChunk + 15) / 16);
+            for (int e = 0; e < p.d; ++e, ++sx) {
+                const uint32_t st = sx % kXStages;
+                if (e == 0) mbar_wait(bar_fd + 8 * (pc % kDyRing), (pc / kDyRing) & 1, 13);
+                if (e + 1 < p.d) {
+                    const uint32_t r = pc + (uint32_t)e + 1;
+                    mbar_wait(bar_fd + 8 * (r % kDyRing), (r / kDyRing) & 1, 14);
+                }
+                mbar_wait(bar_fx + 8 * st, (sx / kXStages) & 1, 15);
+                tc_fence_after();
+                const uint32_t a0 = lbo | ((xs0 + st * p.x_stage_bytes) >> 4);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    for (int dz = 0; dz < 3; ++dz) {
+                        const int dpl = e - dz + 1;                  // du plane paired with x plane e for this dz
+                        if (dpl < 0 || dpl >= p.d) continue;
+                        const uint32_t sl = (pc + (uint32_t)dpl) % kDyRing;
+                        const uint32_t b_lo = lbo | (((dys0 + sl * p.dy_slot_bytes) >> 4) + (uint32_t)ks * 16u);
+                        for (int j = 0; j < p.NM; ++j) {
+                            const int acc = dz * p.NM + j;
+                            const uint32_t a_lo = a0 + (uint32_t)(ks * 16 + j * p.NCOPY);
+                            if (elect_one())
+                                umma_f16(tmem_base + (uint32_t)(acc * p.N), a_lo, a_hi, b_lo, b_hi, idesc, (touched >> acc) & 1u);
+                            touched |= 1u << acc;
+                        }
+                    }
+                }
+                if (elect_one()) {
+                    umma_commit(bar_ex + 8 * st);
+                    if (e >= 1) umma_commit(bar_ed + 8 * ((pc + (uint32_t)e - 1) % kDyRing));
+                    if (e == p.d - 1) umma_commit(bar_ed + 8 * ((pc + (uint32_t)e) % kDyRing));
+                }
+                __syncwarp();
+            }
+            pc += (uint32_t)p.d;
+        }
+        if (lane == 0) { *touched_s = touched; __threadfence_block(); }
+        __syncwarp();
+        if (elect_one()) umma_commit(bar_done);
+    } else if (warp >= 4) {
+        // =========================== EPILOGUE: TMEM -> per-CTA partials ===========================
+        const int wq = warp & 3;
+        mbar_wait(bar_done, 0, 16);
+        tc_fence_after();
+        const uint32_t touched = *reinterpret_cast<volatile uint32_t*>(touched_s);
+        const int row = wq * 32 + lane;
+        float* out = p.ws + ((int64_t)blockIdx.x * NACC * 128 + row) * p.N;
+        for (int acc = 0; acc < NACC; ++acc) {
+            float* o = out + (int64_t)acc * 128 * p.N;
+            const bool live = (touched >> acc) & 1u;
+            for (int c0 = 0; c0 < p.N; c0 += 16) {
+                float v[16];
+                if (live) {
+                    tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * p.N + c0), v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i += 4)
+                    *reinterpret_cast<float4*>(o + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// partials [G*3 ctas][3*NM][128][N] -> grad_w [27][cin][cout]: fixed summation order (CTA slot, then x part, then du part)
+__global__ void dw_reduce_kernel(const float* __restrict__ ws, float* __restrict__ gw, int G, int NM, int NCOPY, int R, int N,
+                                 int cin, int cout, int cin_pad, int cout_pad, int nparts, float scale) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 27 * cin * cout) return;
+    const int co = idx % cout, ci = (idx / cout) % cin, tap = idx / (cout * cin);
+    const int dx = tap % 3, dyt = (tap / 3) % 3, dz = tap / 9;
+    const int j = dx / NCOPY, cp = dx - j * NCOPY;
+    const int NACC = 3 * NM;
+    float s = 0.f;
+    for (int g = 0; g < G; ++g) {
+        const float* base = ws + (((int64_t)(g * 3 + dyt) * NACC + dz * NM + j) * 128) * N;
+        for (int px = 0; px < nparts; ++px)
+            for (int py = 0; py < nparts; ++py)
+                s += base[(int64_t)(cp * R + px * cin_pad + ci) * N + py * cout_pad + co];
+    }
+    gw[idx] = s * scale;        // du is the gradient of conv(x, W * he): d/dW carries the He constant
+}
+
+// bias gradient: per-channel sum of a split-planar volume (hi + lo), two fixed-order stages
+__global__ void __launch_bounds__(256)
+split_colsum_kernel(const uint16_t* __restrict__ v, int64_t part_elems, int nparts, int KC, int PP, float* __restrict__ partial) {
+    const int plane = blockIdx.x;                      // (n, d)
+    __shared__ float red[8][8];
+    for (int kc = 0; kc < KC; ++kc) {
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int part = 0; part < nparts; ++part) {
+            const uint16_t* src = v + part * part_elems + ((int64_t)plane * KC + kc) * PP * 8;
+            for (int q = threadIdx.x; q < PP; q += 256) {
+                const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)q * 8));
+                const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    a[2 * u] += __uint_as_float(w[u] << 16);
+                    a[2 * u + 1] += __uint_as_float(w[u] & 0xffff0000u);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float s = warp_sum(a[i]);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            float s = 0.f;
+            for (int wv = 0; wv < 8; ++wv) s += red[wv][threadIdx.x];
+            partial[(int64_t)plane * KC * 8 + kc * 8 + threadIdx.x] = s;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void colsum_finish_kernel(const float* __restrict__ partial, int planes, int cpad, int c, float* __restrict__ out) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    float s = 0.f;
+    for (int pl = 0; pl < planes; ++pl) s += partial[(int64_t)pl * cpad + ch];
+    out[ch] = s;
+}
+
+struct Plan {
+    int cin_pad, cout_pad, KCi, KCo, nparts, NCOPY, NM, R, N, Wp, PP, span, nchunks, items, G, Lx;
+    uint32_t x_stage_bytes, dy_slot_bytes, smem_bytes;
+};
+
+static bool make_plan(const lf_conv_desc* d, Plan& pl) {
+    if (d->ndim != 3 || d->k != 3) return false;
+    if (d->precision != 1 && d->precision != 2) return false;
+    if (d->n < 1 || d->d < 1 || d->h < 1 || d->w < 1 || d->cin < 1 || d->cout < 1) return false;
+    pl.cin_pad = (d->cin + 15) / 16 * 16;
+    pl.cout_pad = (d->cout + 15) / 16 * 16;
+    pl.nparts = d->precision == 1 ? 2 : 1;
+    pl.R = pl.nparts * pl.cin_pad;
+    pl.N = pl.nparts * pl.cout_pad;
+    if (pl.R != 32 && pl.R != 64) return false;                 // M = NCOPY * R = 128 with NCOPY in {4, 2}
+    if (pl.N > 64) return false;                                // 3 * NM * N TMEM columns <= 512
+    pl.NCOPY = 128 / pl.R;
+    pl.NM = (3 + pl.NCOPY - 1) / pl.NCOPY;
+    pl.KCi = pl.cin_pad / 8; pl.KCo = pl.cout_pad / 8;
+    pl.Wp = d->w + 2;
+    pl.PP = (d->h + 2) * pl.Wp;
+    if (pl.Wp >= 4096 || pl.PP >= (1 << 20)) return false;
+    pl.span = (d->h - 1) * pl.Wp + d->w;
+    pl.nchunks = (pl.span + kChunk - 1) / kChunk;
+    const int64_t items = (int64_t)d->n * pl.nchunks;
+    if (items >= (1ll << 30)) return false;
+    pl.items = (int)items;
+    const int per_tap = sm_count() / 3;
+    pl.G = pl.items < per_tap ? pl.items : per_tap;
+    pl.Lx = kChunk + (pl.NM - 1) * pl.NCOPY;
+    pl.Lx = (pl.Lx + 7) / 8 * 8;
+    pl.x_stage_bytes = (uint32_t)(pl.NCOPY * (pl.R / 8)) * pl.Lx * 16u;
+    pl.dy_slot_bytes = (uint32_t)(pl.N / 8) * kChunk * 16u;
+    pl.smem_bytes = kXStages * pl.x_stage_bytes + kDyRing * pl.dy_slot_bytes + 8 * (2 * kXStages + 2 * kDyRing + 1) + 64;
+    return pl.smem_bytes <= 227u * 1024u;
+}
+
+}  // namespace dw
+}  // namespace lf
+
+using namespace lf;
+
+extern "C" int lf_conv3d_dw_supported(const lf_conv_desc* desc) {
+    dw::Plan pl;
+    return (desc != nullptr && dw::make_plan(desc, pl)) ? 1 : 0;
+}
+
+// workspace (floats): per-CTA partial accumulators + the bias column-sum partials
+extern "C" int64_t lf_conv3d_dw_ws(const lf_conv_desc* desc) {
+    dw::Plan pl;
+    if (desc == nullptr || !dw::make_plan(desc, pl)) return 0;
+    return (int64_t)pl.G * 3 * 3 * pl.NM * 128 * pl.N + (int64_t)desc->n * desc->d * pl.cout_pad;
+}
+
+// grad_w_packed [27][Cin][Cout] (overwritten) = desc->scale * sum x (.) du over all positions; grad_bias [Cout] (nullable) = sum du.
+// x_split / du_split: split-planar volumes of the forward input and of d(loss)/d(pre-activation output)
+// (precision 1: hi and lo parts; 2: hi parts only).  Reference: autograd of modules/equalized.py:57-64.
+extern "C" int lf_conv3d_dw(const lf_conv_desc* desc, const void* x_split, const void* du_split, float* ws,
+                            float* grad_w_packed, float* grad_bias, void* stream) {
+    dw::Plan pl;
+    if (desc == nullptr || !dw::make_plan(desc, pl)) {
+        set_error("conv3d_dw: unsupported shape/precision (3-D k=3, parts*Cin_pad in {32, 64}, parts*Cout_pad <= 64)");
+        return LF_EUNSUPPORTED;
+    }
+    LF_CHECK_ARG(x_split && du_split && ws && grad_w_packed, "conv3d_dw: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    dw::Params p;
+    p.x = reinterpret_cast<const uint16_t*>(x_split);
+    p.dy = reinterpret_cast<const uint16_t*>(du_split);
+    p.x_part = (int64_t)desc->n * desc->d * pl.cin_pad * pl.PP;
+    p.dy_part = (int64_t)desc->n * desc->d * pl.cout_pad * pl.PP;
+    p.x_end = p.x + 2 * p.x_part;            // the buffers always hold both parts (lf_split_bytes)
+    p.dy_end = p.dy + 2 * p.dy_part;
+    p.ws = ws;
+    p.n = desc->n; p.d = desc->d; p.Wp = pl.Wp; p.PP = pl.PP; p.KCi = pl.KCi; p.KCo = pl.KCo; p.nparts = pl.nparts;
+    p.NCOPY = pl.NCOPY; p.NM = pl.NM; p.R = pl.R; p.N = pl.N;
+    p.span = pl.span; p.nchunks = pl.nchunks; p.items = pl.items; p.G = pl.G; p.Lx = pl.Lx;
+    p.x_stage_bytes = pl.x_stage_bytes; p.dy_slot_bytes = pl.dy_slot_bytes;
+    cudaError_t e = cudaFuncSetAttribute(dw::conv3d_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    if (e != cudaSuccess) { set_error("conv3d_dw: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return (int)e; }
+    dw::conv3d_dw_kernel<<<pl.G * 3, dw::kThreads, pl.smem_bytes, st>>>(p);
+    const int total = 27 * desc->cin * desc->cout;
+    dw::dw_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(ws, grad_w_packed, pl.G, pl.NM, pl.NCOPY, pl.R, pl.N, desc->cin,
+                                                              desc->cout, pl.cin_pad, pl.cout_pad, pl.nparts, desc->scale);
+    if (grad_bias != nullptr) {
+        float* partial = ws + (int64_t)pl.G * 3 * 3 * pl.NM * 128 * pl.N;
+        const int planes = desc->n * desc->d;
+        dw::split_colsum_kernel<<<planes, 256, 0, st>>>(p.dy, p.dy_part, pl.nparts, pl.KCo, pl.PP, partial);
+        dw::colsum_finish_kernel<<<(desc->cout + 63) / 64, 64, 0, st>>>(partial, planes, pl.cout_pad, desc->cout, grad_bias);
+    }
+    LF_RETURN_LAUNCH();
+}

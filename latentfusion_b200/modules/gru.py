@@ -6,6 +6,11 @@ convolution is linear in its input channels, so here each gate is evaluated as `
 the two channel groups (x zero-padded to a multiple of 4 channels): both halves then have shapes the tcgen05
 kernel takes (Cin % 4 == 0, packed weights resident in shared memory) and the ``torch.cat`` copy disappears.
 ``precision=0`` keeps the single concatenated exact-fp32 convolution.
+
+The GRU fuser's input is ``[cube_i, voxel coordinates]``: the coordinate channels are the same constant field at
+every step, so their contribution ``conv(coords, W[:, C:C+3])`` is evaluated ONCE per forward per gate
+(``extra_terms``) and added at each step; the per-step convolutions then see exactly C input channels (no 35 -> 48
+channel padding, and the tensor-core weight-gradient kernel applies: Cin_pad in {16, 32}).
 """
 import math
 
@@ -56,7 +61,50 @@ class ConvGRUCell(nn.Module):
         return (ops.eq_conv(xp, wx, gate.bias, precision=prec, fan_in=fan_in)
                 + ops.eq_conv(h, wh, None, precision=prec, fan_in=fan_in))
 
-    def forward(self, x, h_cur):
+    # -- constant extra input channels (the fuser's coordinate field) ------------------------------
+    def splits_inputs(self, like):
+        """True when forward() runs the channel-group evaluation for tensors like `like` (tensor-core precisions)"""
+        prec = self.update_gate.precision
+        return like.is_cuda and (ops.get_default_precision() if prec is None else prec) != ops.PRECISION_FP32
+
+    def extra_terms(self, extra, main_channels):
+        """per-gate conv(extra, W[:, main:main+e]) (no bias) for an input laid out as [main | extra | hidden]"""
+        e = extra.shape[1]
+        ep = (e + 3) // 4 * 4
+        xe = ops.empty_cl((extra.shape[0], ep, *extra.shape[2:]), extra.device)
+        xe[:, :e] = extra
+        xe[:, e:] = 0
+        out = []
+        for gate in (self.update_gate, self.reset_gate, self.out_gate):
+            w = gate.module.weight[:, main_channels:main_channels + e]
+            if ep != e:
+                w = torch.cat([w, w.new_zeros(w.shape[0], ep - e, *w.shape[2:])], dim=1)
+            fan_in = int(math.prod(gate.module.weight.shape[1:]))
+            out.append(ops.eq_conv(xe, w.contiguous(), None, precision=gate.precision, fan_in=fan_in))
+        return tuple(out)
+
+    def _gate3(self, gate, x, h, term):
+        """conv over [x | extra | h] with the extra part precomputed: x and h both have hidden-size channel groups"""
+        w = gate.module.weight
+        cx, ch = x.shape[1], h.shape[1]
+        fan_in = int(math.prod(w.shape[1:]))
+        track = torch.is_grad_enabled() and w.requires_grad
+        key, hit = (w._version, w.data_ptr(), cx, ch), self._parts_cache.get(('3', id(gate)))
+        if not track and hit is not None and hit[0] == key:
+            wx, wh = hit[1], hit[2]
+        else:
+            wx, wh = w[:, :cx].contiguous(), w[:, w.shape[1] - ch:].contiguous()
+            if not track:       # frozen weights: keep the slices (and with them their packed-weight cache entries)
+                wx, wh = wx.detach(), wh.detach()
+                self._parts_cache[('3', id(gate))] = (key, wx, wh)
+        return (ops.eq_conv(x, wx, gate.bias, precision=gate.precision, fan_in=fan_in)
+                + ops.eq_conv(h, wh, None, precision=gate.precision, fan_in=fan_in) + term)
+
+    def forward(self, x, h_cur, extra=None):
+        if extra is not None:           # (x: the main channels only; extra = extra_terms(...) of the remaining inputs)
+            update, h_reset = ops.gru_gates1(self._gate3(self.update_gate, x, h_cur, extra[0]),
+                                             self._gate3(self.reset_gate, x, h_cur, extra[1]), h_cur)
+            return ops.gru_gates2(h_cur, update, self._gate3(self.out_gate, x, h_reset, extra[2]))
         prec = self.update_gate.precision
         if (ops.get_default_precision() if prec is None else prec) == ops.PRECISION_FP32 or not x.is_cuda:
             x_in = torch.cat([x, h_cur], dim=1)

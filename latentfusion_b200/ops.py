@@ -416,6 +416,23 @@ def conv3d_dz(xs, wpk, bias, cout, scale, act, slope, norm, precision, want_dens
     return y, ys, rnorm
 
 
+def conv3d_dw(xs, dus, precision, scale=1.0):
+    """weight / bias gradient of a 3x3x3 convolution from the split-planar twins of its input and of
+    d(loss)/d(pre-activation output): -> (grad_w_packed [27][Cin][Cout], grad_bias [1][Cout]).  lf_conv3d_dw"""
+    lib = L.lib()
+    desc = _desc(KIND_CONV, 3, xs.n, xs.d, xs.h, xs.w, xs.c, dus.c, 3, scale, 0, 0.0, 0, precision)
+    if not lib.lf_conv3d_dw_supported(ctypes.byref(desc)):
+        raise ValueError(f"conv3d_dw: unsupported shape (Cin {xs.c}, Cout {dus.c}, precision {precision})")
+    dev = xs.buf.device
+    gwp = torch.empty(27, xs.c, dus.c, device=dev, dtype=torch.float32)
+    gbp = torch.empty(1, dus.c, device=dev, dtype=torch.float32)
+    ws = torch.empty(lib.lf_conv3d_dw_ws(ctypes.byref(desc)), device=dev, dtype=torch.float32)
+    _call('lf_conv3d_dw', lib.lf_conv3d_dw,
+          (ctypes.byref(desc), _p(xs.buf), _p(dus.buf), _p(ws), _p(gwp), _p(gbp), _stream()), kernels=4,
+          nbytes=2 * (xs.buf.numel() + dus.buf.numel()), flops=2 * xs.n * xs.d * xs.h * xs.w * 27 * xs.c * dus.c)
+    return gwp, gbp
+
+
 class _ActRec:
     """What the backward of a fused conv+LeakyReLU+PixelNorm layer needs (its output and norms).  When the ONLY
     consumer of that output is another lfb200 convolution (Block: conv1 -> conv2; Photographer: camera block ->
@@ -440,6 +457,7 @@ def mark_single_consumer(t):
 # row of y (32 lines per load instruction) and the epilogue becomes the critical stage.  Opt-in (LFB200_FUSE_EPI=1)
 # until the row is staged through shared memory.
 _FUSE_EPI = _os.environ.get('LFB200_FUSE_EPI', '0') == '1'
+_DW_FFMA = _os.environ.get('LFB200_DW_FFMA', '0') == '1'     # A/B: weight gradients on the exact FFMA kernel
 
 
 class _EqConv(torch.autograd.Function):
@@ -566,6 +584,12 @@ class _EqConv(torch.autograd.Function):
                    _stream()), kernels=3 if precision == 1 else 1,
                   nbytes=4 * (2 * gy.numel() + gx.numel()), flops=bflops)
             fused_done = True
+        wdesc = _desc(kind, nd, n, d, h, w, cin, cout, k, scale, 0, 0.0, 0, 0)
+        if need_w and kind == KIND_CONV and nd == 3 and k == 3 and not _DW_FFMA:
+            wdesc.precision = {1: 1, 2: 2, 3: 1}.get(precision, 0)
+            if not (wdesc.precision and lib.lf_conv3d_dw_supported(ctypes.byref(wdesc))):
+                wdesc.precision = 0
+        use_dw = wdesc.precision != 0          # weight gradient on the tensor cores, from the split-planar twins
         use_dz_b = ctx.needs_input_grad[0] and kind == KIND_CONV and nd == 3 and k == 3 and _dz_ok(bdesc)
         if use_dz_b and not fused_done:
             # ---- depth-batched path: split-planar du straight out of the activation backward, and (when the producer
@@ -573,7 +597,7 @@ class _EqConv(torch.autograd.Function):
             if (act or norm) and not pre_applied:
                 du_split = SplitVol.empty(n, cout, d, h, w, x.device)
                 if cout in (16, 32):
-                    du = torch.empty_like(gy) if need_w else None
+                    du = torch.empty_like(gy) if (need_w and not use_dw) else None
                     _call('lf_actnorm_bwd', lib.lf_actnorm_bwd_split,
                           (_p(gy), _p(y), _p(rnorm), _p(du), _p(du_split.buf), n, d, h, w, cout, int(act), slope, int(norm),
                            _stream()), nbytes=4 * 2 * gy.numel() + 2 * du_split.buf.numel())
@@ -599,8 +623,6 @@ class _EqConv(torch.autograd.Function):
                 gx, _, _ = conv3d_dz(du_split, wpk_b, None, cin, scale, False, 0.0, False, bdesc.precision,
                                      name=_conv_name(kind, nd, k, 'bwd_data'))
             fused_done = True
-            if need_w and du is None:
-                du = du_split.to_dense()
         if not fused_done:
             if (act or norm) and not pre_applied:
                 du = torch.empty_like(gy)
@@ -639,11 +661,18 @@ class _EqConv(torch.autograd.Function):
                       nbytes=4 * (du.numel() + gx.numel()), flops=bflops)
         if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
             taps = wb.shape[0]
-            gwp = torch.zeros(taps, cin, cout, device=x.device, dtype=torch.float32)
-            gbp = torch.zeros(d if kind == KIND_EXPAND else 1, cout, device=x.device, dtype=torch.float32)
-            wdesc = _desc(kind, nd, n, d, h, w, cin, cout, k, scale, 0, 0.0, 0, 0)
-            _call('lf_conv_bwd_weight', lib.lf_conv_bwd_weight,
-                  (ctypes.byref(wdesc), _p(x), _p(du), _p(gwp), _p(gbp), _stream()))
+            if use_dw:
+                # tensor-core weight gradient straight from the split-planar twins of x and du (csrc/conv3d_dw.cu)
+                gwp, gbp = conv3d_dw(ctx.xs if ctx.xs is not None else split_pack(x),
+                                     du_split if du_split is not None else split_pack(du), wdesc.precision, scale)
+            else:
+                wdesc.precision = 0
+                if du is None:
+                    du = du_split.to_dense()
+                gwp = torch.zeros(taps, cin, cout, device=x.device, dtype=torch.float32)
+                gbp = torch.zeros(d if kind == KIND_EXPAND else 1, cout, device=x.device, dtype=torch.float32)
+                _call('lf_conv_bwd_weight', lib.lf_conv_bwd_weight,
+                      (ctypes.byref(wdesc), _p(x), _p(du), _p(gwp), _p(gbp), _stream()))
             if ctx.needs_input_grad[1]:
                 gw = _unpack_weight_grad(gwp, wshape, kind, depth)
             if has_bias and ctx.needs_input_grad[2]:

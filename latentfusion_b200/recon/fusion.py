@@ -116,6 +116,13 @@ class GRUFuser(_ParamFuser):
     def forward(self, z_obj, z_cam_mid, z_obj_mid, camera):
         seed = z_obj[:, 0]
         coords = (utils.get_normalized_pixel_coords if self._planar else utils.get_normalized_voxel_coords)(seed)
+        if not self._planar and self.in_channels % 4 == 0 and self.gru.splits_inputs(seed):
+            # the coordinate channels are the same constant field at every step: convolve them once per gate
+            terms = self.gru.extra_terms(coords, self.in_channels)
+            state = seed
+            for i in range(1, z_obj.shape[1]):
+                state = self.gru(z_obj[:, i], state, extra=terms)
+            return state.unsqueeze(1), {}
         return _scan_views(z_obj, coords, self.gru, seed).unsqueeze(1), {}
 
 

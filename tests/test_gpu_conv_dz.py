@@ -108,7 +108,10 @@ def test_block_forward_backward_through_dz_path(dev, c, size, train):
     finally:
         ops.KernelTrace.reset(False)
         ops.set_default_precision(old)
-    assert names.count('lf_split_pack') == 1, names            # only the block's input is packed
+    # only the block's input is packed (in training once more in the backward, for conv1's weight gradient: the
+    # split-planar twin of a leaf input is not kept alive between forward and backward)
+    assert names.count('lf_split_pack') == (2 if train else 1), names
+    assert ('lf_conv3d_dw' in names) == train and 'lf_conv_bwd_weight' not in names
     assert 'lf_conv_bwd_data[conv3d_k3]' in names
     xr = x.detach().double().requires_grad_(True)
     ws = {k: v.detach().double().requires_grad_(True) for k, v in blk.named_parameters()}
@@ -133,3 +136,30 @@ def test_block_forward_backward_through_dz_path(dev, c, size, train):
         for k, p in blk.named_parameters():
             rel = float((p.grad.double() - ws[k].grad).norm() / ws[k].grad.norm())
             assert rel < 2e-2, f'{k}: relative L2 error {rel:.3g}'
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shape', [(2, 32, 32, 16, 16, 16, 1), (1, 8, 8, 10, 12, 14, 1), (3, 32, 16, 5, 20, 9, 1),
+                                   (2, 32, 32, 12, 16, 16, 2), (1, 16, 32, 1, 24, 24, 1), (2, 12, 20, 7, 33, 17, 1)])
+def test_conv3d_weight_gradient_on_tensor_cores_vs_fp64(shape):
+    """lf_conv3d_dw (MN-major tcgen05 over the split-planar twins) against autograd of F.conv3d in fp64: weight gradient
+    [27][Cin][Cout] and bias gradient; precision 1 = all four bf16x2 split products (fp32-grade), 2 = bf16 operands."""
+    import torch.nn.functional as F
+    from latentfusion_b200 import ops
+    n, cin, cout, d, h, w, prec = shape
+    dev = torch.device('cuda:0')
+    torch.manual_seed(sum(shape))
+    x = torch.randn(n, cin, d, h, w, device=dev)
+    du = torch.randn(n, cout, d, h, w, device=dev)
+    gwp, gbp = ops.conv3d_dw(ops.split_pack(x), ops.split_pack(du), prec)
+    wz = torch.zeros(cout, cin, 3, 3, 3, device=dev, dtype=torch.float64, requires_grad=True)
+    F.conv3d(x.double(), wz, padding=1).backward(du.double())
+    ref = wz.grad.permute(2, 3, 4, 1, 0).reshape(27, cin, cout)
+    err = float((gwp.double() - ref).norm() / ref.norm())
+    worst = float((gwp.double() - ref).abs().max() / ref.abs().max())
+    tol = 2e-5 if prec == 1 else 1e-2
+    assert err < tol and worst < 10 * tol, f'relative L2 {err:.3g}, worst/max {worst:.3g}'
+    bref = du.double().sum(dim=(0, 2, 3, 4))
+    assert float((gbp.double().reshape(-1) - bref).abs().max() / bref.abs().max()) < (1e-4 if prec == 1 else 1e-2)
+    gwp2, _ = ops.conv3d_dw(ops.split_pack(x), ops.split_pack(du), prec)
+    assert torch.equal(gwp, gwp2)                       # fixed-order reduction: bit-reproducible
