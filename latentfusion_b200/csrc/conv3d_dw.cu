@@ -31,9 +31,9 @@ namespace dw {
 
 using namespace tcx;
 
-constexpr int kThreads = 256;      // warp 0: TMA producer, 1: MMA issuer, 2: TMEM allocator, 4..7: epilogue
-constexpr int kXStages = 2;
-constexpr int kDyRing = 4;
+constexpr int kThreads = 256;      // warp 0: TMA producer, 1..3: MMA issuers (one per dz; warp 2 also allocates TMEM), 4..7: epilogue
+constexpr int kXStages = 3;
+constexpr int kDyRing = 6;        // du planes e-1, e, e+1 of the step in flight + three prefetched
 constexpr int kChunk = 128;        // positions per item step (8 k-steps of 16)
 
 struct Params {
@@ -45,7 +45,8 @@ struct Params {
     float* ws;                     // [ctas][NACC][128][N] partial accumulators
     int n, d, Wp, PP, KCi, KCo, nparts;
     int NCOPY, NM, R, N;           // x copies stacked in M, MMAs per dz, rows per copy, columns
-    int span, nchunks, items, G;   // interior positions per plane, 128-position chunks, (sample, chunk) items, CTAs per dy tap
+    int span, nchunks, items, G;   // interior positions per plane, 128-position chunks, (sample, chunk, depth segment) items, CTAs per dy tap
+    int nseg, dseg;                // depth segments per column and planes per segment
     int Lx;                        // positions per x region (allocated)
     uint32_t x_stage_bytes, dy_slot_bytes;
 };
@@ -63,7 +64,7 @@ conv3d_dw_kernel(const __grid_constant__ Params p) {
     uint8_t* tail = smem + (size_t)kXStages * p.x_stage_bytes + (size_t)kDyRing * p.dy_slot_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail);     // full_x[2] empty_x[2] full_dy[4] empty_dy[4] done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kXStages + 2 * kDyRing + 1);
-    uint32_t* touched_s = tmem_slot + 1;
+    uint32_t* touched_s = tmem_slot + 1;                     // [3]: accumulators each issuer has written
     const uint32_t bar_fx = smem_u32(bars), bar_ex = bar_fx + 8 * kXStages;
     const uint32_t bar_fd = bar_ex + 8 * kXStages, bar_ed = bar_fd + 8 * kDyRing, bar_done = bar_ed + 8 * kDyRing;
 
@@ -75,7 +76,9 @@ conv3d_dw_kernel(const __grid_constant__ Params p) {
     for (uint32_t i = threadIdx.x * 16; i < kXStages * p.x_stage_bytes; i += kThreads * 16)
         *reinterpret_cast<uint4*>(smem + i) = make_uint4(0u, 0u, 0u, 0u);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2 * kXStages + 2 * kDyRing + 1; ++i) mbar_init(bar_fx + 8 * i, 1);
+        for (int i = 0; i < kXStages; ++i) { mbar_init(bar_fx + 8 * i, 1); mbar_init(bar_ex + 8 * i, 3); }
+        for (int i = 0; i < kDyRing; ++i) { mbar_init(bar_fd + 8 * i, 1); mbar_init(bar_ed + 8 * i, 3); }
+        mbar_init(bar_done, 3);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -96,100 +99,115 @@ conv3d_dw_kernel(const __grid_constant__ Params p) {
 
     if (warp == 0) {
         // =========================== TMA PRODUCER ===========================
-        if (lane == 0) {
-            uint32_t sx = 0, pc = 0;                                 // x stage counter, du plane counter
-            for (int item = slot; item < p.items; item += p.G) {
-                const int n = item / p.nchunks, c = item - n * p.nchunks;
-                const int q0 = first + c * kChunk;
-                const int ksteps = min(kChunk / 16, (p.span - c * kChunk + 15) / 16);
-                const uint32_t dy_bytes = (uint32_t)ksteps * 256u;
-                const uint32_t x_bytes = (uint32_t)(ksteps * 16 + (p.NM - 1) * p.NCOPY) * 16u;
-                auto load_dy = [&](int dpl) {
-                    const uint32_t r = pc + (uint32_t)dpl, sl = r % kDyRing;
-                    mbar_wait(bar_ed + 8 * sl, ((r / kDyRing) & 1) ^ 1, 11);
-                    uint32_t total = 0;
-                    uint32_t bytes[16];
-                    const uint16_t* src[16];
-                    for (int g = 0; g < dg; ++g) {
-                        const int part = g / p.KCo, kc = g - part * p.KCo;
-                        src[g] = p.dy + part * p.dy_part + ((((int64_t)n * p.d + dpl) * p.KCo + kc) * p.PP + q0) * 8;
-                        const int64_t avail = (p.dy_end - src[g]) * 2;
-                        bytes[g] = avail <= 0 ? 0u : (uint32_t)min((int64_t)dy_bytes, avail);
-                        total += bytes[g];
-                    }
-                    mbar_arrive_expect_tx(bar_fd + 8 * sl, total);
-                    for (int g = 0; g < dg; ++g)
-                        if (bytes[g]) bulk_g2s(dys0 + sl * p.dy_slot_bytes + g * (kChunk * 16), src[g], bytes[g], bar_fd + 8 * sl);
-                };
-                load_dy(0);
-                for (int e = 0; e < p.d; ++e, ++sx) {
-                    const uint32_t st = sx % kXStages;
-                    mbar_wait(bar_ex + 8 * st, ((sx / kXStages) & 1) ^ 1, 12);
-                    uint32_t total = 0;
-                    uint32_t bytes[16];
-                    const uint16_t* src[16];
-                    for (int r = 0; r < p.NCOPY * xg; ++r) {
-                        const int cp = r / xg, g = r - cp * xg;
-                        const int part = g / p.KCi, kc = g - part * p.KCi;
-                        const int64_t pos = (int64_t)q0 + (dyt - 1) * p.Wp - 1 + cp;
-                        src[r] = p.x + part * p.x_part + ((((int64_t)n * p.d + e) * p.KCi + kc) * p.PP + pos) * 8;
-                        const int64_t avail = (p.x_end - src[r]) * 2;
-                        bytes[r] = avail <= 0 ? 0u : (uint32_t)min((int64_t)x_bytes, avail);
-                        total += bytes[r];
-                    }
-                    mbar_arrive_expect_tx(bar_fx + 8 * st, total);
-                    for (int r = 0; r < p.NCOPY * xg; ++r)
-                        if (bytes[r]) bulk_g2s(xs0 + st * p.x_stage_bytes + r * x_region, src[r], bytes[r], bar_fx + 8 * st);
-                    if (e + 1 < p.d) load_dy(e + 1);
-                }
-                pc += (uint32_t)p.d;
+        // One bulk copy per lane: a single thread needs ~150 cycles to issue each cp.async.bulk, and a step has 24 of
+        // them (16 x regions + 8 du regions of ~2 KB) against ~2.3k cycles of MMA work.  Lanes 0..15 own the x regions of
+        // the step's stage, lanes 16..16+dg-1 the du regions of the next plane; lane 0 posts the byte counts.
+        uint32_t sx = 0, pc = 0;                                 // x stage counter, du plane counter
+        for (int item = slot; item < p.items; item += p.G) {
+            const int seg = item % p.nseg, col = item / p.nseg;
+            const int n = col / p.nchunks, c = col - n * p.nchunks;
+            const int e0 = seg * p.dseg, e1 = min(p.d, e0 + p.dseg);      // x planes of this item
+            const int dlo = max(e0 - 1, 0), dhi = min(e1, p.d - 1);       // du planes it touches
+            const int q0 = first + c * kChunk;
+            const int ksteps = min(kChunk / 16, (p.span - c * kChunk + 15) / 16);
+            const uint32_t dy_bytes = (uint32_t)ksteps * 256u;
+            const uint32_t x_bytes = (uint32_t)(ksteps * 16 + (p.NM - 1) * p.NCOPY) * 16u;
+            const bool x_lane = lane < p.NCOPY * xg, d_lane = lane >= 16 && lane < 16 + dg;
+            // this lane's x region: copy cp, channel group g (part, kc)
+            int64_t x_off = 0;
+            if (x_lane) {
+                const int cp = lane / xg, g = lane - cp * xg;
+                const int part = g / p.KCi, kc = g - part * p.KCi;
+                x_off = part * p.x_part + ((((int64_t)n * p.d) * p.KCi + kc) * p.PP + q0 + (dyt - 1) * p.Wp - 1 + cp) * 8;
             }
+            int64_t d_off = 0;
+            if (d_lane) {
+                const int g = lane - 16;
+                const int part = g / p.KCo, kc = g - part * p.KCo;
+                d_off = part * p.dy_part + ((((int64_t)n * p.d) * p.KCo + kc) * p.PP + q0) * 8;
+            }
+            const int64_t x_plane = (int64_t)p.KCi * p.PP * 8, d_plane = (int64_t)p.KCo * p.PP * 8;
+            auto load_dy = [&](int dpl) {
+                const uint32_t r = pc + (uint32_t)(dpl - dlo), sl = r % kDyRing;
+                if (lane == 0) {
+                    mbar_wait(bar_ed + 8 * sl, ((r / kDyRing) & 1) ^ 1, 11);
+                    mbar_arrive_expect_tx(bar_fd + 8 * sl, dy_bytes * (uint32_t)dg);
+                }
+                __syncwarp();
+                if (d_lane)
+                    bulk_g2s(dys0 + sl * p.dy_slot_bytes + (uint32_t)(lane - 16) * (kChunk * 16), p.dy + d_off + dpl * d_plane,
+                             dy_bytes, bar_fd + 8 * sl);
+            };
+            for (int dpl = dlo; dpl <= e0; ++dpl) load_dy(dpl);
+            for (int e = e0; e < e1; ++e, ++sx) {
+                const uint32_t st = sx % kXStages;
+                const uint16_t* src = p.x + x_off + e * x_plane;
+                uint32_t bytes = 0;
+                if (x_lane) {
+                    const int64_t avail = (p.x_end - src) * 2;       // the very last region may end at the buffer end
+                    bytes = avail <= 0 ? 0u : (uint32_t)min((int64_t)x_bytes, avail);
+                }
+                const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+                if (lane == 0) {
+                    mbar_wait(bar_ex + 8 * st, ((sx / kXStages) & 1) ^ 1, 12);
+                    mbar_arrive_expect_tx(bar_fx + 8 * st, total);
+                }
+                __syncwarp();
+                if (bytes) bulk_g2s(xs0 + st * p.x_stage_bytes + (uint32_t)lane * x_region, src, bytes, bar_fx + 8 * st);
+                if (e + 1 <= dhi) load_dy(e + 1);
+            }
+            pc += (uint32_t)(dhi - dlo + 1);
         }
-    } else if (warp == 1) {
-        // =========================== MMA ISSUER ===========================
+    } else if (warp <= 3) {
+        // =========================== MMA ISSUERS (warp 1 + dz) ===========================
+        // A warp issues one tcgen05.mma per ~120 cycles (uniform-datapath work + issue latency), the tensor pipe takes
+        // one of these every ~48: three issuers, one per dz (its own accumulators, its own du plane of the ring).
+        const int dz = warp - 1;
         const uint32_t idesc = idesc_mn((uint32_t)p.N);
         const uint32_t a_hi = (uint32_t)p.Lx | (1u << 14);           // SBO = one x region (16-byte units), version 1
         const uint32_t b_hi = (uint32_t)kChunk | (1u << 14);         // SBO = one du region
         const uint32_t lbo = 8u << 16;                               // LBO = 128 bytes: the next 8 positions
         uint32_t touched = 0, sx = 0, pc = 0;
         for (int item = slot; item < p.items; item += p.G) {
-            const int c = item % p.nchunks;
+            const int seg = item % p.nseg, c = (item / p.nseg) % p.nchunks;
+            const int e0 = seg * p.dseg, e1 = min(p.d, e0 + p.dseg);
+            const int dlo = max(e0 - 1, 0), dhi = min(e1, p.d - 1);
             const int ksteps = min(kChunk / 16, (p.span - c * kChunk + 15) / 16);
-            for (int e = 0; e < p.d; ++e, ++sx) {
+            for (int e = e0; e < e1; ++e, ++sx) {
                 const uint32_t st = sx % kXStages;
-                if (e == 0) mbar_wait(bar_fd + 8 * (pc % kDyRing), (pc / kDyRing) & 1, 13);
-                if (e + 1 < p.d) {
-                    const uint32_t r = pc + (uint32_t)e + 1;
-                    mbar_wait(bar_fd + 8 * (r % kDyRing), (r / kDyRing) & 1, 14);
+                const int dpl = e - dz + 1;                          // du plane paired with x plane e for this dz
+                const bool live = dpl >= 0 && dpl < p.d;
+                if (live) {
+                    const uint32_t r = pc + (uint32_t)(dpl - dlo);
+                    mbar_wait(bar_fd + 8 * (r % kDyRing), (r / kDyRing) & 1, 13);
                 }
                 mbar_wait(bar_fx + 8 * st, (sx / kXStages) & 1, 15);
                 tc_fence_after();
-                const uint32_t a0 = lbo | ((xs0 + st * p.x_stage_bytes) >> 4);
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    for (int dz = 0; dz < 3; ++dz) {
-                        const int dpl = e - dz + 1;                  // du plane paired with x plane e for this dz
-                        if (dpl < 0 || dpl >= p.d) continue;
-                        const uint32_t sl = (pc + (uint32_t)dpl) % kDyRing;
-                        const uint32_t b_lo = lbo | (((dys0 + sl * p.dy_slot_bytes) >> 4) + (uint32_t)ks * 16u);
+                if (live) {
+                    const uint32_t a0 = lbo | ((xs0 + st * p.x_stage_bytes) >> 4);
+                    const uint32_t b0 = lbo | ((dys0 + ((pc + (uint32_t)(dpl - dlo)) % kDyRing) * p.dy_slot_bytes) >> 4);
+                    for (int ks = 0; ks < ksteps; ++ks) {
                         for (int j = 0; j < p.NM; ++j) {
                             const int acc = dz * p.NM + j;
-                            const uint32_t a_lo = a0 + (uint32_t)(ks * 16 + j * p.NCOPY);
                             if (elect_one())
-                                umma_f16(tmem_base + (uint32_t)(acc * p.N), a_lo, a_hi, b_lo, b_hi, idesc, (touched >> acc) & 1u);
+                                umma_f16(tmem_base + (uint32_t)(acc * p.N), a0 + (uint32_t)(ks * 16 + j * p.NCOPY), a_hi,
+                                         b0 + (uint32_t)ks * 16u, b_hi, idesc, (touched >> acc) & 1u);
                             touched |= 1u << acc;
                         }
                     }
                 }
                 if (elect_one()) {
                     umma_commit(bar_ex + 8 * st);
-                    if (e >= 1) umma_commit(bar_ed + 8 * ((pc + (uint32_t)e - 1) % kDyRing));
-                    if (e == p.d - 1) umma_commit(bar_ed + 8 * ((pc + (uint32_t)e) % kDyRing));
+                    // a du plane is last used by the step of x plane (plane + 1), or by the item's last step
+                    if (e - 1 >= dlo) umma_commit(bar_ed + 8 * ((pc + (uint32_t)(e - 1 - dlo)) % kDyRing));
+                    if (e == e1 - 1)
+                        for (int q = e; q <= dhi; ++q) umma_commit(bar_ed + 8 * ((pc + (uint32_t)(q - dlo)) % kDyRing));
                 }
                 __syncwarp();
             }
-            pc += (uint32_t)p.d;
+            pc += (uint32_t)(dhi - dlo + 1);
         }
-        if (lane == 0) { *touched_s = touched; __threadfence_block(); }
+        if (lane == 0) { touched_s[dz] = touched; __threadfence_block(); }
         __syncwarp();
         if (elect_one()) umma_commit(bar_done);
     } else if (warp >= 4) {
@@ -197,7 +215,8 @@ conv3d_dw_kernel(const __grid_constant__ Params p) {
         const int wq = warp & 3;
         mbar_wait(bar_done, 0, 16);
         tc_fence_after();
-        const uint32_t touched = *reinterpret_cast<volatile uint32_t*>(touched_s);
+        const volatile uint32_t* tv = touched_s;
+        const uint32_t touched = tv[0] | tv[1] | tv[2];
         const int row = wq * 32 + lane;
         float* out = p.ws + ((int64_t)blockIdx.x * NACC * 128 + row) * p.N;
         for (int acc = 0; acc < NACC; ++acc) {
@@ -289,7 +308,7 @@ __global__ void colsum_finish_kernel(const float* __restrict__ partial, int plan
 }
 
 struct Plan {
-    int cin_pad, cout_pad, KCi, KCo, nparts, NCOPY, NM, R, N, Wp, PP, span, nchunks, items, G, Lx;
+    int cin_pad, cout_pad, KCi, KCo, nparts, NCOPY, NM, R, N, Wp, PP, span, nchunks, items, G, Lx, nseg, dseg;
     uint32_t x_stage_bytes, dy_slot_bytes, smem_bytes;
 };
 
@@ -312,10 +331,15 @@ static bool make_plan(const lf_conv_desc* d, Plan& pl) {
     if (pl.Wp >= 4096 || pl.PP >= (1 << 20)) return false;
     pl.span = (d->h - 1) * pl.Wp + d->w;
     pl.nchunks = (pl.span + kChunk - 1) / kChunk;
-    const int64_t items = (int64_t)d->n * pl.nchunks;
+    const int per_tap = sm_count() / 3;
+    // few columns (the GRU's 2-object batches): cut the depth march into segments (one extra du plane at each cut)
+    pl.nseg = 1;
+    while (pl.nseg < 8 && (int64_t)d->n * pl.nchunks * pl.nseg < 3ll * per_tap && d->d / (pl.nseg * 2) >= 8) pl.nseg *= 2;
+    pl.dseg = (d->d + pl.nseg - 1) / pl.nseg;
+    pl.nseg = (d->d + pl.dseg - 1) / pl.dseg;
+    const int64_t items = (int64_t)d->n * pl.nchunks * pl.nseg;
     if (items >= (1ll << 30)) return false;
     pl.items = (int)items;
-    const int per_tap = sm_count() / 3;
     pl.G = pl.items < per_tap ? pl.items : per_tap;
     pl.Lx = kChunk + (pl.NM - 1) * pl.NCOPY;
     pl.Lx = (pl.Lx + 7) / 8 * 8;
@@ -365,6 +389,7 @@ extern "C" int lf_conv3d_dw(const lf_conv_desc* desc, const void* x_split, const
     p.n = desc->n; p.d = desc->d; p.Wp = pl.Wp; p.PP = pl.PP; p.KCi = pl.KCi; p.KCo = pl.KCo; p.nparts = pl.nparts;
     p.NCOPY = pl.NCOPY; p.NM = pl.NM; p.R = pl.R; p.N = pl.N;
     p.span = pl.span; p.nchunks = pl.nchunks; p.items = pl.items; p.G = pl.G; p.Lx = pl.Lx;
+    p.nseg = pl.nseg; p.dseg = pl.dseg;
     p.x_stage_bytes = pl.x_stage_bytes; p.dy_slot_bytes = pl.dy_slot_bytes;
     cudaError_t e = cudaFuncSetAttribute(dw::conv3d_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) { set_error("conv3d_dw: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return (int)e; }
