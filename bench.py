@@ -255,7 +255,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        os.environ.setdefault('NCCL_DEBUG', 'WARN')      # keep NCCL's version banner off stdout (one JSON line only)
+        os.environ.setdefault('NCCL_DEBUG', 'WARN')
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # NCCL's version banner must not land on stdout (one JSON line only)
         dist.init_process_group('nccl', device_id=dev)
     ops.set_default_precision(args.precision)
 
@@ -513,8 +514,8 @@ def train_block(args, dev, rank, world, barrier, max_over_ranks, B=8, vin=16, vo
             "ms_per_step": round(ms, 2), "object_views_per_s": round(B * (vin + vout) * 1000.0 / ms, 2), "steps": steps,
             "loss": loss, "lfb200_launches_per_step": launches, "peak_mem_gb": round(mem, 1),
             "h2d_bytes_per_step": sum(t.numel() * 4 for t in host.values()), "precision": args.precision,
-            "note": "e2e: pinned host batch -> device inside the timed region, loss read back every step; weight gradients "
-                    "by lf_conv_bwd_weight"}
+            "note": "e2e: pinned host batch -> device inside the timed region, loss read back every step; 3x3x3 weight "
+                    "gradients on the tensor cores (lf_conv3d_dw), the 2-D / projection ones on lf_conv_bwd_weight"}
 
 
 def search_block(args, dev, rank, world, barrier, max_over_ranks, S4=128, C4=16, gens=2):
