@@ -12,7 +12,9 @@
  *   - `stream` is a cudaStream_t passed as void*.
  *   - feature maps are dense channels-last fp32: 3-D [N][D][H][W][C], 2-D [N][H][W][C].
  *   - return value: 0 ok; <0 invalid argument (lf_last_error() has the text); >0 a cudaError_t.
- *   - thread safety: no global mutable state besides the thread-local last-error string.
+ *   - thread safety: no global mutable state on the product path besides the thread-local last-error string.
+ *     Development only: the option table (environment, read once; lf_set_option) and a diagnostic timeline
+ *     buffer that a kernel writes only when LFB200_TC_DEBUG & 8 is set.
  */
 #ifndef LFB200_H
 #define LFB200_H
@@ -46,6 +48,11 @@ const char* lf_version(void);
 const char* lf_last_error(void);
 /* Number of SMs of the current device (used by callers to size workspaces). */
 int lf_sm_count(void);
+/* Tuning / A-B switches are the LFB200_* environment variables, read ONCE at first use (never per launch);
+ * lf_set_option overrides one by name afterwards (tests and profiling tools; not thread-safe).  The kernels' mbarrier
+ * waits are bounded: a pipeline bug prints "lfb200: mbarrier wait timed out" and traps (the launch then reports a CUDA
+ * error) instead of hanging the device. */
+int lf_set_option(const char* name, int value);
 
 /* ---- K1: ObjectToCameraTransform.forward  (modules/geometry.py:669-690; F.grid_sample :17) ----
  * vol  [B][S][S][S][C]   one latent cube per object (NOT replicated per camera; models.py:493-494)

@@ -1,6 +1,7 @@
 // C-ABI glue: version / error reporting / precision dispatch for lf_conv_fwd.
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace lf {
@@ -26,6 +27,22 @@ int sm_count() {
     return cached;
 }
 
+static const char* kOptName[OPT_COUNT] = {"LFB200_TC_DC", "LFB200_TC_DEBUG", "LFB200_TC_NO_DUAL", "LFB200_RESAMPLE_KC",
+                                           "LFB200_RESAMPLE_W", "LFB200_RESAMPLE_BRICK"};
+static int g_opt[OPT_COUNT];
+static bool g_opt_loaded = false;
+
+static void load_options() {
+    if (g_opt_loaded) return;
+    for (int i = 0; i < OPT_COUNT; ++i) {
+        const char* e = getenv(kOptName[i]);
+        g_opt[i] = (e && e[0]) ? atoi(e) : 0;
+    }
+    g_opt_loaded = true;
+}
+
+int option(Option o) { load_options(); return g_opt[o]; }
+
 int conv_fp32_launch(const lf_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
                      float* rnorm, cudaStream_t st);
 int conv_tc_supported(const lf_conv_desc* d);
@@ -37,6 +54,14 @@ int conv_tc_launch(const lf_conv_desc* d, const float* x, const float* w, const 
 extern "C" const char* lf_version(void) { return "lfb200 0.1.0 (sm_100a)"; }
 extern "C" const char* lf_last_error(void) { return lf::g_err; }
 extern "C" int lf_sm_count(void) { return lf::sm_count(); }
+// debug/tuning switches (the LFB200_* environment variables, read once at first use): explicit override; not thread-safe
+extern "C" int lf_set_option(const char* name, int value) {
+    lf::load_options();
+    for (int i = 0; i < lf::OPT_COUNT; ++i)
+        if (name != nullptr && strcmp(name, lf::kOptName[i]) == 0) { lf::g_opt[i] = value; return LF_OK; }
+    lf::set_error("lf_set_option: unknown option %s", name ? name : "(null)");
+    return LF_EINVAL;
+}
 
 extern "C" int lf_conv_fwd(const lf_conv_desc* desc, const float* x, const float* w, const float* bias,
                            float* y, float* rnorm, void* stream) {

@@ -30,6 +30,9 @@ void set_error(const char* fmt, ...);
     } while (0)
 
 int sm_count();
+// Tuning / A-B switches: read from the environment ONCE (first use), overridable through lf_set_option (tests, tools).
+enum Option { OPT_TC_DC, OPT_TC_DEBUG, OPT_TC_NO_DUAL, OPT_RESAMPLE_KC, OPT_RESAMPLE_W, OPT_RESAMPLE_BRICK, OPT_COUNT };
+int option(Option o);
 
 // torch.linspace(a, b, n)[i] exactly as ATen evaluates it (symmetric two-sided formula).
 __device__ __forceinline__ float linspace_at(float a, float b, int n, int i) {

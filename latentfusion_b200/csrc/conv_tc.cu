@@ -691,7 +691,7 @@ static bool make_plan(const lf_conv_desc* d, Plan& pl, bool dual = false) {
         // DC 8 -> 0.33 ms, 16 -> 0.31, 32 -> 0.30 for the config-B 3x3x3 conv)
         while (pl.DC > 4 && (int64_t)d->n * pl.nstrips * ((d->d + pl.DC - 1) / pl.DC) < sms) pl.DC = (pl.DC + 1) / 2;
     }
-    { const char* dc = getenv("LFB200_TC_DC"); if (dc && hz > 0 && atoi(dc) > 0) pl.DC = min(d->d, atoi(dc)); }
+    { const int dc = option(OPT_TC_DC); if (hz > 0 && dc > 0) pl.DC = min(d->d, dc); }
     pl.ndchunks = (d->d + pl.DC - 1) / pl.DC;
     return true;
 }
@@ -742,7 +742,7 @@ static int conv_tc_launch_pass(const lf_conv_desc* d, const tc::Plan& pl, const 
     p.nstrips = pl.nstrips; p.ndchunks = pl.ndchunks; p.items = d->n * pl.nstrips * pl.ndchunks;
     p.scale = d->scale; p.act = d->act; p.slope = d->slope; p.norm = d->norm;
     p.slab_bytes = pl.slab_bytes; p.w_bytes = pl.w_bytes;
-    { const char* dbg = getenv("LFB200_TC_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+    p.debug = option(OPT_TC_DEBUG);
     p.magic_q4 = ((1ull << 40) + (pl.cin_pad / 4) - 1) / (uint64_t)(pl.cin_pad / 4);
     p.magic_P = ((1ull << 40) + pl.P - 1) / (uint64_t)pl.P;
     // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1,
@@ -772,7 +772,7 @@ int conv_tc_launch_ex(const lf_conv_desc* d, const float* x, const float* w, con
     const uint16_t* wbase = reinterpret_cast<const uint16_t*>(w);
     const size_t part = (size_t)pl.w_bytes / 2;
     if (d->precision == 2) return conv_tc_launch_pass(d, pl, x, wbase, bias, y, rnorm, pro, 0, tc::PASS_ONLY, 0, st, epi);
-    static const bool no_dual = getenv("LFB200_TC_NO_DUAL") != nullptr;
+    const bool no_dual = option(OPT_TC_NO_DUAL) != 0;
     if (!no_dual && pro == nullptr && (d->cout & 3) == 0 && pl.cout_pad <= 64) {
         // bf16x3 in TWO passes: x_hi * [W_hi | W_lo] (one N = 2*Cout MMA per tap: the A tile is fetched from shared
         // memory once for both products), then x_lo * W_hi accumulated in the epilogue
@@ -780,7 +780,7 @@ int conv_tc_launch_ex(const lf_conv_desc* d, const float* x, const float* w, con
         if (tc::make_plan(d, pd, true)) {
             int e = conv_tc_launch_pass(d, pd, x, wbase + 2 * part, bias, y, rnorm, nullptr, 0, tc::PASS_FIRST, 1, st);
             if (e != LF_OK) return e;
-            { const char* dbg = getenv("LFB200_TC_DEBUG"); if (dbg && (atoi(dbg) & 16)) return LF_OK; }   // profiling: first pass only
+            if (option(OPT_TC_DEBUG) & 16) return LF_OK;   // profiling: first pass only
             return conv_tc_launch_pass(d, pl, x, wbase, bias, y, rnorm, nullptr, 1, tc::PASS_LAST, 0, st, epi);
         }
     }
@@ -871,7 +871,7 @@ extern "C" int lf_conv_tc_passes(const lf_conv_desc* desc) {
     tc::Plan pl;
     if (desc == nullptr || desc->precision == 0 || !tc::make_plan(desc, pl)) return 0;
     if (desc->precision == 2) return 1;
-    if (getenv("LFB200_TC_NO_DUAL") == nullptr && (desc->cout & 3) == 0 && pl.cout_pad <= 64) {
+    if (option(OPT_TC_NO_DUAL) == 0 && (desc->cout & 3) == 0 && pl.cout_pad <= 64) {
         tc::Plan pd;
         if (tc::make_plan(desc, pd, true)) return 2;
     }

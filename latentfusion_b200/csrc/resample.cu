@@ -632,10 +632,6 @@ static int grid_for(int64_t total_groups, int lpv_log2) {
     return (int)blocks;
 }
 
-static int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return (e && e[0]) ? atoi(e) : dflt;
-}
 
 template <int MODE, int LPVL, int W>
 static int launch_march(const float* vol, const float* cam, float* out, int vpo, int N, int S, cudaStream_t st) {
@@ -645,7 +641,7 @@ static int launch_march(const float* vol, const float* cam, float* out, int vpo,
     // chunk start) while still giving the machine several waves of CTAs
     int KC = (S + LPV - 1) / LPV * LPV;
     while (KC > LPV && KC > 16 && cols * ((S + KC - 1) / KC) < 12ll * sm_count()) KC = ((KC / 2) + LPV - 1) / LPV * LPV;
-    { const int k = env_int("LFB200_RESAMPLE_KC", 0); if (k >= LPV) KC = k / LPV * LPV; }
+    { const int k = option(OPT_RESAMPLE_KC); if (k >= LPV) KC = k / LPV * LPV; }
     const int64_t blocks = cols * ((S + KC - 1) / KC);
     LF_CHECK_ARG(blocks < (1ll << 31), "resample: too many columns");
     resample_march_kernel<MODE, LPVL, (W == 1 ? 3 : 2), W><<<(unsigned)blocks, 256, 0, st>>>(vol, cam, out, vpo, N, S, KC);
@@ -653,16 +649,12 @@ static int launch_march(const float* vol, const float* cam, float* out, int vpo,
 }
 
 // LFB200_RESAMPLE_BRICK=1 selects the brick kernel for every shape (A/B timing and the cross-check test)
-static bool use_march() {
-    const char* e = getenv("LFB200_RESAMPLE_BRICK");
-    return !(e && e[0] == '1');
-}
+static bool use_march() { return option(OPT_RESAMPLE_BRICK) != 1; }
 
 template <int MODE>
 static int launch_fwd(const float* vol, const float* cam, float* out, int vpo, int N, int C, int S, cudaStream_t st) {
     if (use_march() && (int64_t)S * S * S * (C / 4) < (1ll << 32)) {
-        const int wide = env_int("LFB200_RESAMPLE_W", 1);
-        if (wide == 2) {
+        if (option(OPT_RESAMPLE_W) == 2) {
             if (C == 16) return launch_march<MODE, 1, 2>(vol, cam, out, vpo, N, S, st);
             if (C == 32) return launch_march<MODE, 2, 2>(vol, cam, out, vpo, N, S, st);
             if (C == 64) return launch_march<MODE, 3, 2>(vol, cam, out, vpo, N, S, st);

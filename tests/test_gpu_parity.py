@@ -103,11 +103,12 @@ def test_march_and_brick_resamplers_agree_at_full_size(dev):
     vol = torch.randn(1, C, S, S, S, device=dev)
     vols = torch.randn(N, C, S, S, S, device=dev)
     march = (ObjectToCameraTransform(1.0)(vol, cam), CameraToObjectTransform(1.0)(vols, cam))
-    os.environ['LFB200_RESAMPLE_BRICK'] = '1'
+    from latentfusion_b200 import _lib as L
+    L.check(L.lib().lf_set_option(b'LFB200_RESAMPLE_BRICK', 1), 'set_option')     # (the env var is only read at load time)
     try:
         brick = (ObjectToCameraTransform(1.0)(vol, cam), CameraToObjectTransform(1.0)(vols, cam))
     finally:
-        del os.environ['LFB200_RESAMPLE_BRICK']
+        L.lib().lf_set_option(b'LFB200_RESAMPLE_BRICK', 0)
     for a, b in zip(march, brick):
         torch.testing.assert_close(a, b, atol=2e-6, rtol=1e-5)
 
