@@ -279,6 +279,16 @@ int lf_ibr_warp_blend_fwd(const float* logits, const float* image_reproj /* [B][
                           float* image /* [B][C][H][W] */, float* weights /* [B][Vi][H][W] */,
                           float* flow_dx /* [B][Vi][H][W] */, float* flow_dy /* [B][Vi][H][W] */,
                           int b, int vi, int c, int h, int w, void* stream);
+/* Backward of the two blend heads (the IBR generator is trained through them, tools/train/train_ibr.py:367-376; the
+ * reprojection itself runs without grad there).  blend: grad_wts[b][i][p] = sum_c grad_out[b][c][p] * img[b][i][c][p].
+ * warp_blend: gradient of all four outputs of ibr.py:237-249 (image; blend weights / flow_dx / flow_dy upstream
+ * gradients nullable) w.r.t. the logits: softmax, tanh, clamp (inclusive, as torch.clamp) and the bilinear sampler's
+ * coordinate gradient (ATen grid_sampler_2d_backward, zeros padding, align_corners=False). */
+int lf_ibr_blend_bwd(const float* grad_out /* [B][C][HW] */, const float* img /* [B][Vi][C][HW] */,
+                     float* grad_wts /* [B][Vi][HW] */, int b, int vi, int c, int hw, void* stream);
+int lf_ibr_warp_blend_bwd(const float* logits, const float* image_reproj, float flow_size, const float* grad_image,
+                          const float* grad_weights, const float* grad_flow_dx, const float* grad_flow_dy,
+                          float* grad_logits /* [B][3*Vi][H][W] */, int b, int vi, int c, int h, int w, void* stream);
 
 #ifdef __cplusplus
 }

@@ -50,6 +50,8 @@ _SIGNATURES = {
     'lf_conv3d_dz': (c_int, [ctypes.POINTER(ConvDesc), c_vp, c_vp, c_f32p, c_f32p, c_vp, c_f32p, c_vp]),
     'lf_conv3d_dz_bwd_epi': (c_int, [ctypes.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_f32p, c_int, c_float, c_int, c_f32p, c_vp, c_vp]),
     'lf_actnorm_bwd_split': (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_vp] + [c_int] * 6 + [c_float, c_int, c_vp]),
+    'lf_ibr_blend_bwd': (c_int, [c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_vp]),
+    'lf_ibr_warp_blend_bwd': (c_int, [c_f32p, c_f32p, c_float, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_int, c_vp]),
     'lf_set_option': (c_int, [ctypes.c_char_p, c_int]),
     'lf_conv3d_dw_supported': (c_int, [ctypes.POINTER(ConvDesc)]),
     'lf_conv3d_dw_ws': (c_i64, [ctypes.POINTER(ConvDesc)]),

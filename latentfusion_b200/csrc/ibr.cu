@@ -9,8 +9,10 @@
 // align_corners=False), plus a [V_o*V_i, 1, H, W] transformed-depth image that exists only to be sampled.
 // Here one thread owns one output pixel of one (o, i) pair: the warp coordinate is generated in registers from
 // two 48-float camera blocks, the four taps of the colour image are gathered directly, and the transformed
-// depth is evaluated at the four taps on the fly (it is a closed form of depth_in at the tap).  Forward only
-// (the pose loop does not differentiate this branch).
+// depth is evaluated at the four taps on the fly (it is a closed form of depth_in at the tap).  The reprojection is
+// forward only (the recon networks are frozen in tools/train/train_ibr.py: _render_reprojections runs without grad);
+// the two blend heads have backward kernels to the logits / weights that the IBR generator is trained through
+// (train_ibr.py:367-376).
 #include "common.cuh"
 
 namespace lf {
@@ -166,6 +168,95 @@ ibr_warp_blend_kernel(const float* __restrict__ logits, const float* __restrict_
     for (int c = 0; c < C && c < 8; ++c) image[((int64_t)b * C + c) * HW + p] = acc[c];
 }
 
+// ---- backward of the blend heads (tools/train/train_ibr.py:367-376 trains the generator through them) ----
+// d/d weights of out[b][c][p] = sum_i w[b][i][p] * img[b][i][c][p]:  gw[b][i][p] = sum_c g[b][c][p] * img[b][i][c][p]
+__global__ void __launch_bounds__(256)
+ibr_blend_bwd_kernel(const float* __restrict__ g, const float* __restrict__ img, float* __restrict__ gw,
+                     int B, int VI, int C, int HW) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)B * VI * HW) return;
+    const int p = (int)(e % HW);
+    const int i = (int)((e / HW) % VI);
+    const int b = (int)(e / ((int64_t)HW * VI));
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c)
+        acc += __ldg(g + ((int64_t)b * C + c) * HW + p) * __ldg(img + (((int64_t)b * VI + i) * C + c) * HW + p);
+    gw[e] = acc;
+}
+
+// bilinear sample of one plane and its derivatives w.r.t. the unnormalised coordinates (ATen grid_sampler_2d_backward,
+// zeros padding: taps outside the image read as 0 and still carry weight derivatives)
+__device__ __forceinline__ void tap_grad(float gx, float gy, int W, int H, const float* __restrict__ plane,
+                                         float& val, float& dix, float& diy) {
+    const float ix = ((gx + 1.f) * (float)W - 1.f) / 2.f;
+    const float iy = ((gy + 1.f) * (float)H - 1.f) / 2.f;
+    val = dix = diy = 0.f;
+    if (!((ix > -2.f) && (ix < (float)W + 1.f) && (iy > -2.f) && (iy < (float)H + 1.f))) return;
+    const float fx = floorf(ix), fy = floorf(iy);
+    const int x0 = (int)fx, y0 = (int)fy;
+    const float ax = (fx + 1.f) - ix, bx = ix - fx, ay = (fy + 1.f) - iy, by = iy - fy;
+    const bool xa = x0 >= 0 && x0 < W, xb = x0 + 1 >= 0 && x0 + 1 < W, ya = y0 >= 0 && y0 < H, yb = y0 + 1 >= 0 && y0 + 1 < H;
+    const float nw = (xa && ya) ? __ldg(plane + y0 * W + x0) : 0.f;
+    const float ne = (xb && ya) ? __ldg(plane + y0 * W + x0 + 1) : 0.f;
+    const float sw = (xa && yb) ? __ldg(plane + (y0 + 1) * W + x0) : 0.f;
+    const float se = (xb && yb) ? __ldg(plane + (y0 + 1) * W + x0 + 1) : 0.f;
+    val = nw * (ax * ay) + ne * (bx * ay) + sw * (ax * by) + se * (bx * by);
+    dix = (ne - nw) * ay + (se - sw) * by;
+    diy = (sw - nw) * ax + (se - ne) * bx;
+}
+
+// backward of warp_blend_logits to the logits [B][3*Vi][H][W]; upstream gradients of all four outputs
+// (g_w / g_dx / g_dy may be null)
+__global__ void __launch_bounds__(256)
+ibr_warp_blend_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ image_reproj, float flow_size,
+                          const float* __restrict__ g_image, const float* __restrict__ g_w, const float* __restrict__ g_dx,
+                          const float* __restrict__ g_dy, float* __restrict__ g_logits, int B, int VI, int C, int H, int W) {
+    const int HW = H * W;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (p >= HW) return;
+    const int y = p / W, x = p - y * W;
+    const float* lg = logits + (int64_t)b * 3 * VI * HW + p;
+    float* gl = g_logits + (int64_t)b * 3 * VI * HW + p;
+    float m = -INFINITY;
+    for (int i = 0; i < VI; ++i) m = fmaxf(m, lg[(int64_t)i * HW]);
+    float den = 0.f;
+    for (int i = 0; i < VI; ++i) den += expf(lg[(int64_t)i * HW] - m);
+    const float bx = linspace_at(-1.f, 1.f, W, x), by = linspace_at(-1.f, 1.f, H, y);
+    float gc[8];
+    for (int c = 0; c < C && c < 8; ++c) gc[c] = __ldg(g_image + ((int64_t)b * C + c) * HW + p);
+    // pass 1: a_i = <g, S_i>, the flow gradients; A = sum_i w_i (a_i + gw_i)
+    float A = 0.f;
+    for (int i = 0; i < VI; ++i) {
+        const float wgt = expf(lg[(int64_t)i * HW] - m) / den;
+        const float tx = tanhf(lg[(int64_t)(VI + i) * HW]), ty = tanhf(lg[(int64_t)(2 * VI + i) * HW]);
+        const float ux = bx + flow_size / (float)W * tx, uy = by + flow_size / (float)H * ty;
+        const float gx = fminf(fmaxf(ux, -1.f), 1.f), gy = fminf(fmaxf(uy, -1.f), 1.f);
+        const float* src = image_reproj + ((int64_t)b * VI + i) * C * HW;
+        float a = 0.f, ddx = 0.f, ddy = 0.f;
+        for (int c = 0; c < C && c < 8; ++c) {
+            float v, dix, diy;
+            tap_grad(gx, gy, W, H, src + (int64_t)c * HW, v, dix, diy);
+            a += gc[c] * v; ddx += gc[c] * dix; ddy += gc[c] * diy;
+        }
+        const int64_t wi = ((int64_t)b * VI + i) * HW + p;
+        const float up = a + (g_w != nullptr ? __ldg(g_w + wi) : 0.f);
+        A += wgt * up;
+        gl[(int64_t)i * HW] = up;                               // finished in pass 2
+        // clamp passes the gradient inside [-1, 1] (inclusive, as torch.clamp); unnormalisation d ix / d gx = W / 2
+        float gfx = (ux >= -1.f && ux <= 1.f) ? wgt * ddx * (0.5f * (float)W) : 0.f;
+        float gfy = (uy >= -1.f && uy <= 1.f) ? wgt * ddy * (0.5f * (float)H) : 0.f;
+        if (g_dx != nullptr) gfx += __ldg(g_dx + wi);
+        if (g_dy != nullptr) gfy += __ldg(g_dy + wi);
+        gl[(int64_t)(VI + i) * HW] = gfx * (flow_size / (float)W) * (1.f - tx * tx);
+        gl[(int64_t)(2 * VI + i) * HW] = gfy * (flow_size / (float)H) * (1.f - ty * ty);
+    }
+    for (int i = 0; i < VI; ++i) {                              // softmax backward: w_i (up_i - A)
+        const float wgt = expf(lg[(int64_t)i * HW] - m) / den;
+        gl[(int64_t)i * HW] = wgt * (gl[(int64_t)i * HW] - A);
+    }
+}
+
 }  // namespace lf
 
 using namespace lf;
@@ -200,5 +291,26 @@ extern "C" int lf_ibr_warp_blend_fwd(const float* logits, const float* image_rep
     dim3 grid((unsigned)((h * w + 255) / 256), (unsigned)b);
     ibr_warp_blend_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, image_reproj, flow_size, image, weights,
                                                                    flow_dx, flow_dy, b, vi, c, h, w);
+    LF_RETURN_LAUNCH();
+}
+
+extern "C" int lf_ibr_blend_bwd(const float* grad_out, const float* img, float* grad_wts, int b, int vi, int c, int hw,
+                                void* stream) {
+    LF_CHECK_ARG(grad_out && img && grad_wts, "ibr_blend_bwd: null pointer");
+    LF_CHECK_ARG(b > 0 && vi > 0 && c > 0 && hw > 0, "ibr_blend_bwd: bad extents");
+    const int64_t total = (int64_t)b * vi * hw;
+    LF_CHECK_ARG((total + 255) / 256 < (1ll << 31), "ibr_blend_bwd: too many elements");
+    ibr_blend_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(grad_out, img, grad_wts, b, vi, c, hw);
+    LF_RETURN_LAUNCH();
+}
+
+extern "C" int lf_ibr_warp_blend_bwd(const float* logits, const float* image_reproj, float flow_size, const float* grad_image,
+                                     const float* grad_weights, const float* grad_flow_dx, const float* grad_flow_dy,
+                                     float* grad_logits, int b, int vi, int c, int h, int w, void* stream) {
+    LF_CHECK_ARG(logits && image_reproj && grad_image && grad_logits, "ibr_warp_blend_bwd: null pointer");
+    LF_CHECK_ARG(b > 0 && b < 65536 && vi > 0 && c > 0 && c <= 8 && h > 1 && w > 1, "ibr_warp_blend_bwd: bad extents (C <= 8)");
+    dim3 grid((unsigned)((h * w + 255) / 256), (unsigned)b);
+    ibr_warp_blend_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, image_reproj, flow_size, grad_image, grad_weights,
+                                                                       grad_flow_dx, grad_flow_dy, grad_logits, b, vi, c, h, w);
     LF_RETURN_LAUNCH();
 }

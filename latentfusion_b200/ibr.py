@@ -3,8 +3,10 @@
 render_latent_ibr2 :158-178, render_ibr :181-228, blend_logits :231-234, warp_blend_logits :237-249).
 
 The arithmetic runs in three lfb200 kernels (``csrc/ibr.cu``): the per-(output view, input view) reprojection of
-colour and depth, the view blend, and the flow-refined blend.  They are forward-only — this branch is not on the pose
-loop's gradient path; calling it on tensors that require grad with autograd enabled raises.
+colour and depth, the view blend, and the flow-refined blend.  The reprojection is forward-only (the reference's IBR
+training keeps the reconstruction networks frozen and reprojects without grad, tools/train/train_ibr.py:319-340; asking
+it for a gradient raises); ``blend_logits`` / ``warp_blend_logits`` — the heads the IBR generator is trained through,
+train_ibr.py:367-376 — are differentiable w.r.t. their logits (``lf_ibr_blend_bwd`` / ``lf_ibr_warp_blend_bwd``).
 The [V_o, V_i] view weights (camera-distance softmaxes) are a handful of floats and stay in torch.
 """
 import math

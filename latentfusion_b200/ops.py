@@ -1045,38 +1045,88 @@ def ibr_reproject(image_in, depth_in, depth_out, cam_in_block, cam_out_block):
     return image_reproj, depth_reproj
 
 
+class _IbrBlend(torch.autograd.Function):
+    """out[b,c,p] = sum_i w[b,i,(p)] * img[b,i,c,p]; differentiable w.r.t. the weights (kernel) and the images."""
+
+    @staticmethod
+    def forward(ctx, img, wts, per_pixel):
+        b, vi, c, h, w = img.shape
+        out = torch.empty(b, c, h, w, device=img.device)
+        _call('lf_ibr_blend_fwd', L.lib().lf_ibr_blend_fwd, (_p(img), _p(wts), _p(out), b, vi, c, h * w, int(per_pixel), _stream()),
+              nbytes=4 * (img.numel() + out.numel()))
+        ctx.save_for_backward(img, wts)
+        ctx.per_pixel = per_pixel
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        img, wts = ctx.saved_tensors
+        b, vi, c, h, w = img.shape
+        g = g.float().contiguous()
+        gw = gi = None
+        if ctx.needs_input_grad[1]:
+            gw = torch.empty(b, vi, h, w, device=img.device)
+            _call('lf_ibr_blend_bwd', L.lib().lf_ibr_blend_bwd, (_p(g), _p(img), _p(gw), b, vi, c, h * w, _stream()),
+                  nbytes=4 * (img.numel() + g.numel() + gw.numel()))
+            if not ctx.per_pixel:
+                gw = gw.sum(dim=(2, 3))
+        if ctx.needs_input_grad[0]:
+            wv = wts.view(b, vi, 1, h, w) if ctx.per_pixel else wts.view(b, vi, 1, 1, 1)
+            gi = g.unsqueeze(1) * wv
+        return gi, gw, None
+
+
 def ibr_blend(image_reproj, weights):
     """sum over views of weights * image_reproj.  image_reproj [B,Vi,C,H,W]; weights [B,Vi] (per view) or
     [B,Vi,H,W] (per pixel).  latentfusion/ibr.py:223-224, :231-234."""
     _need_cuda(image_reproj, weights)
-    _no_grad_path('ibr_blend', image_reproj, weights)
     b, vi, c, h, w = image_reproj.shape
     per_pixel = weights.dim() == 4
     if tuple(weights.shape[:2]) != (b, vi) or (per_pixel and tuple(weights.shape[2:]) != (h, w)) or weights.dim() not in (2, 4):
         raise ValueError("ibr_blend: weights must be [B,Vi] or [B,Vi,H,W]")
-    img = image_reproj.detach().float().contiguous()
-    wts = weights.detach().float().contiguous()
-    out = torch.empty(b, c, h, w, device=img.device)
-    _call('lf_ibr_blend_fwd', L.lib().lf_ibr_blend_fwd, (_p(img), _p(wts), _p(out), b, vi, c, h * w, int(per_pixel), _stream()),
-          nbytes=4 * (img.numel() + out.numel()))
-    return out
+    return _IbrBlend.apply(image_reproj.float().contiguous(), weights.float().contiguous(), per_pixel)
+
+
+class _IbrWarpBlend(torch.autograd.Function):
+    """latentfusion/ibr.py:237-249; differentiable w.r.t. the logits (all four outputs)."""
+
+    @staticmethod
+    def forward(ctx, lg, img, flow_size):
+        b, vi, c, h, w = img.shape
+        image = torch.empty(b, c, h, w, device=img.device)
+        wts = torch.empty(b, vi, h, w, device=img.device)
+        dx, dy = torch.empty_like(wts), torch.empty_like(wts)
+        _call('lf_ibr_warp_blend_fwd', L.lib().lf_ibr_warp_blend_fwd,
+              (_p(lg), _p(img), float(flow_size), _p(image), _p(wts), _p(dx), _p(dy), b, vi, c, h, w, _stream()),
+              nbytes=4 * (lg.numel() + img.numel() + image.numel() + 3 * wts.numel()))
+        ctx.save_for_backward(lg, img)
+        ctx.flow_size = float(flow_size)
+        return image, wts, dx, dy
+
+    @staticmethod
+    def backward(ctx, g_image, g_w, g_dx, g_dy):
+        lg, img = ctx.saved_tensors
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("ibr_warp_blend: no gradient w.r.t. the reprojected images (the reference trains "
+                                      "the generator with the recon networks frozen, train_ibr.py:320)")
+        b, vi, c, h, w = img.shape
+        prep = lambda t: None if t is None else t.float().contiguous()     # noqa: E731
+        g_image = torch.zeros(b, c, h, w, device=img.device) if g_image is None else prep(g_image)
+        g_w, g_dx, g_dy = prep(g_w), prep(g_dx), prep(g_dy)
+        gl = torch.empty_like(lg)
+        _call('lf_ibr_warp_blend_bwd', L.lib().lf_ibr_warp_blend_bwd,
+              (_p(lg), _p(img), ctx.flow_size, _p(g_image), _p(g_w), _p(g_dx), _p(g_dy), _p(gl), b, vi, c, h, w, _stream()),
+              nbytes=4 * (2 * lg.numel() + img.numel() + g_image.numel()))
+        return gl, None, None
 
 
 def ibr_warp_blend(logits, image_reproj, flow_size):
     """latentfusion/ibr.py:237-249 -> (image [B,C,H,W], blend_weights [B,Vi,1,H,W], flow_dx, flow_dy [B,Vi,H,W])."""
     _need_cuda(logits, image_reproj)
-    _no_grad_path('ibr_warp_blend', logits, image_reproj)
     b, vi, c, h, w = image_reproj.shape
     if tuple(logits.shape) != (b, 3 * vi, h, w):
         raise ValueError(f"ibr_warp_blend: logits must be [B, 3*Vi, H, W] = {(b, 3 * vi, h, w)}, got {tuple(logits.shape)}")
     if c > 8:
         raise ValueError("ibr_warp_blend: at most 8 colour channels")
-    lg = logits.detach().float().contiguous()
-    img = image_reproj.detach().float().contiguous()
-    image = torch.empty(b, c, h, w, device=img.device)
-    wts = torch.empty(b, vi, h, w, device=img.device)
-    dx, dy = torch.empty_like(wts), torch.empty_like(wts)
-    _call('lf_ibr_warp_blend_fwd', L.lib().lf_ibr_warp_blend_fwd,
-          (_p(lg), _p(img), float(flow_size), _p(image), _p(wts), _p(dx), _p(dy), b, vi, c, h, w, _stream()),
-          nbytes=4 * (lg.numel() + img.numel() + image.numel() + 3 * wts.numel()))
+    image, wts, dx, dy = _IbrWarpBlend.apply(logits.float().contiguous(), image_reproj.float().contiguous(), flow_size)
     return image, wts.unsqueeze(2), dx, dy

@@ -113,3 +113,57 @@ def test_ibr_is_forward_only_and_has_no_cpu_path(dev):
     with pytest.raises((RuntimeError, ValueError)):
         ibr.reproject_views(g['image_in'], g['depth_in'], g['depth_out'], ph.product_camera(g.cam('cam_in'), 'cpu'),
                             ph.product_camera(g.cam('cam_out'), 'cpu'))
+
+
+def _ref_blend_logits(logits, image_reproj):
+    """latentfusion/ibr.py:231-234 in torch ops (fp64 on the device)"""
+    w = torch.softmax(logits, dim=1).unsqueeze(2)
+    return (w * image_reproj).sum(dim=1), w
+
+
+def _ref_warp_blend_logits(logits, image_reproj, flow_size):
+    """latentfusion/ibr.py:237-249 in torch ops"""
+    vi = image_reproj.shape[1]
+    h, w = image_reproj.shape[-2:]
+    bl, fx, fy = torch.split(logits, vi, dim=1)
+    wts = torch.softmax(bl, dim=1).unsqueeze(2)
+    dx, dy = flow_size / w * torch.tanh(fx), flow_size / h * torch.tanh(fy)
+    yy, xx = torch.meshgrid([torch.linspace(-1, 1, h, device=logits.device, dtype=logits.dtype),
+                             torch.linspace(-1, 1, w, device=logits.device, dtype=logits.dtype)], indexing='ij')
+    grid = torch.stack((xx[None, None] + dx, yy[None, None] + dy), dim=-1).clamp(-1, 1)
+    samp = F.grid_sample(image_reproj.flatten(0, 1), grid.flatten(0, 1), mode='bilinear', align_corners=False)
+    samp = samp.view(*image_reproj.shape)
+    return (wts * samp).sum(dim=1), wts, dx, dy
+
+
+def test_blend_heads_backward_vs_torch_autograd(dev):
+    """The two heads the IBR generator is trained through (tools/train/train_ibr.py:367-376): gradients of
+    blend_logits / warp_blend_logits w.r.t. the logits, incl. the paths through the returned weights and flows,
+    against fp64 autograd of the reference formulation."""
+    from latentfusion_b200 import ibr
+    torch.manual_seed(11)
+    b, vi, c, h, w, flow = 3, 5, 3, 20, 28, 6.0
+    image_reproj = torch.rand(b, vi, c, h, w, device=dev) * 2 - 1
+    for name in ('blend', 'warp'):
+        logits = (torch.randn(b, vi if name == 'blend' else 3 * vi, h, w, device=dev) * 1.5).requires_grad_(True)
+        l64 = logits.detach().double().requires_grad_(True)
+        g_img = torch.randn(b, c, h, w, device=dev)
+        g_aux = torch.randn(b, vi, h, w, device=dev)
+        if name == 'blend':
+            img, wts = ibr.blend_logits(logits, image_reproj)
+            rimg, rw = _ref_blend_logits(l64, image_reproj.double())
+            loss = (img * g_img).sum() + (wts.squeeze(2) * g_aux).sum()
+            rloss = (rimg * g_img.double()).sum() + (rw.squeeze(2) * g_aux.double()).sum()
+        else:
+            img, wts, dx, dy = ibr.warp_blend_logits(logits, image_reproj, flow)
+            rimg, rw, rdx, rdy = _ref_warp_blend_logits(l64, image_reproj.double(), flow)
+            loss = (img * g_img).sum() + (wts.squeeze(2) * g_aux).sum() + (dx * g_aux).sum() - 0.5 * (dy * g_aux).sum()
+            rloss = ((rimg * g_img.double()).sum() + (rw.squeeze(2) * g_aux.double()).sum() + (rdx * g_aux.double()).sum()
+                     - 0.5 * (rdy * g_aux.double()).sum())
+        torch.testing.assert_close(img.double(), rimg, atol=1e-5, rtol=1e-4)
+        loss.backward()
+        rloss.backward()
+        err = (logits.grad.double() - l64.grad).abs()
+        # a sample position within rounding of a pixel boundary takes the other bilinear cell in fp32: its flow gradient
+        # then differs by a finite jump — allow a handful of such pixels
+        assert float((err > 1e-4 + 1e-3 * l64.grad.abs()).float().mean()) < 2e-4, (name, float(err.max()))
