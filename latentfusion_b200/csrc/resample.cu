@@ -274,7 +274,13 @@ resample_fwd_kernel(const float* __restrict__ vol, const float* __restrict__ cam
 // round trip of the ~3.7 new lines of a step (the FMAs of a step wait for its own loads; 24 warps per SM at 80
 // registers).  Variants measured and dropped: prefetch.global.L1 one round ahead (CCTL.PF1: no gain, lower L1 hit
 // rate), 4 CTAs/SM at 64 registers (150 us: the larger shared-memory carve-out costs more L1 than the extra
-// warps give), 2x2 column patches per warp, block-level lockstep (both neutral or worse).
+// warps give), 2x2 column patches per warp, block-level lockstep (both neutral or worse).  Round 2 (profiles/r02_*):
+// 256-bit accesses (LDG.E.ENL2.256, W = 2 below: half the warp instructions per byte, 118 registers, 2 CTAs/SM) 124 us;
+// a one-step software pipeline (the slots that change are loaded into a second register set during the previous step's
+// arithmetic, records prepared one round ahead) cuts the long-scoreboard stall from 6.4 to 2.1 per issue but needs 122
+// registers and +47 % instructions (the predicated register moves that commit the new lines): 118 us.  The kernel sits at
+// ~50 % issue, ~56 % L1 data pipe and ~57 % long-scoreboard samples at once: every variant that relieves one of the three
+// loads another, so the 128-bit / 3 CTAs per SM form stays the default.
 // 128-bit read-only load at base + off (float4 units): one IMAD.WIDE for the address instead of a 64-bit add chain
 __device__ __forceinline__ float4 ldg_f4_at(const float4* base, uint32_t off) {
     unsigned long long addr;
