@@ -72,8 +72,8 @@ conv3d_dw_kernel(const __grid_constant__ Params p) {
     const int lane = threadIdx.x & 31;
     const int dyt = blockIdx.x % 3, slot = blockIdx.x / 3;
 
-    // stale bytes behind a clamped copy must be finite: they are multiplied by du halo zeros
-    for (uint32_t i = threadIdx.x * 16; i < kXStages * p.x_stage_bytes; i += kThreads * 16)
+    // stale bytes behind a copy clamped at the end of a buffer must be finite: they meet halo zeros of the other operand
+    for (uint32_t i = threadIdx.x * 16; i < kXStages * p.x_stage_bytes + kDyRing * p.dy_slot_bytes; i += kThreads * 16)
         *reinterpret_cast<uint4*>(smem + i) = make_uint4(0u, 0u, 0u, 0u);
     if (threadIdx.x == 0) {
         for (int i = 0; i < kXStages; ++i) { mbar_init(bar_fx + 8 * i, 1); mbar_init(bar_ex + 8 * i, 3); }
@@ -129,14 +129,20 @@ conv3d_dw_kernel(const __grid_constant__ Params p) {
             const int64_t x_plane = (int64_t)p.KCi * p.PP * 8, d_plane = (int64_t)p.KCo * p.PP * 8;
             auto load_dy = [&](int dpl) {
                 const uint32_t r = pc + (uint32_t)(dpl - dlo), sl = r % kDyRing;
+                const uint16_t* dsrc = p.dy + d_off + dpl * d_plane;
+                uint32_t dbytes = 0;
+                if (d_lane) {            // a narrow plane's rounded-up run may pass the end of the buffer: clamp
+                    const int64_t avail = (p.dy_end - dsrc) * 2;
+                    dbytes = avail <= 0 ? 0u : (uint32_t)min((int64_t)dy_bytes, avail);
+                }
+                const uint32_t dtotal = __reduce_add_sync(0xffffffffu, dbytes);
                 if (lane == 0) {
                     mbar_wait(bar_ed + 8 * sl, ((r / kDyRing) & 1) ^ 1, 11);
-                    mbar_arrive_expect_tx(bar_fd + 8 * sl, dy_bytes * (uint32_t)dg);
+                    mbar_arrive_expect_tx(bar_fd + 8 * sl, dtotal);
                 }
                 __syncwarp();
-                if (d_lane)
-                    bulk_g2s(dys0 + sl * p.dy_slot_bytes + (uint32_t)(lane - 16) * (kChunk * 16), p.dy + d_off + dpl * d_plane,
-                             dy_bytes, bar_fd + 8 * sl);
+                if (dbytes)
+                    bulk_g2s(dys0 + sl * p.dy_slot_bytes + (uint32_t)(lane - 16) * (kChunk * 16), dsrc, dbytes, bar_fd + 8 * sl);
             };
             for (int dpl = dlo; dpl <= e0; ++dpl) load_dy(dpl);
             for (int e = e0; e < e1; ++e, ++sx) {

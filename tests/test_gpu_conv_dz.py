@@ -140,7 +140,8 @@ def test_block_forward_backward_through_dz_path(dev, c, size, train):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize('shape', [(2, 32, 32, 16, 16, 16, 1), (1, 8, 8, 10, 12, 14, 1), (3, 32, 16, 5, 20, 9, 1),
-                                   (2, 32, 32, 12, 16, 16, 2), (1, 16, 32, 1, 24, 24, 1), (2, 12, 20, 7, 33, 17, 1)])
+                                   (2, 32, 32, 12, 16, 16, 2), (1, 16, 32, 1, 24, 24, 1), (2, 12, 20, 7, 33, 17, 1),
+                                   (1, 16, 16, 6, 7, 8, 1)])      # (narrow plane: the rounded-up run ends past the buffer)
 def test_conv3d_weight_gradient_on_tensor_cores_vs_fp64(shape):
     """lf_conv3d_dw (MN-major tcgen05 over the split-planar twins) against autograd of F.conv3d in fp64: weight gradient
     [27][Cin][Cout] and bias gradient; precision 1 = all four bf16x2 split products (fp32-grade), 2 = bf16 operands."""
