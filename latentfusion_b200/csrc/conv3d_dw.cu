@@ -33,7 +33,7 @@ using namespace tcx;
 
 constexpr int kThreads = 256;      // warp 0: TMA producer, 1..3: MMA issuers (one per dz; warp 2 also allocates TMEM), 4..7: epilogue
 constexpr int kXStages = 3;
-constexpr int kDyRing = 6;        // du planes e-1, e, e+1 of the step in flight + three prefetched
+constexpr int kDyRing = 6;        // du planes e-1, e, e+1 of the step in flight + three prefetched (Params::dring <= this)
 constexpr int kChunk = 128;        // positions per item step (8 k-steps of 16)
 
 struct Params {
@@ -47,6 +47,7 @@ struct Params {
     int NCOPY, NM, R, N;           // x copies stacked in M, MMAs per dz, rows per copy, columns
     int span, nchunks, items, G;   // interior positions per plane, 128-position chunks, (sample, chunk, depth segment) items, CTAs per dy tap
     int nseg, dseg;                // depth segments per column and planes per segment
+    int two_d, dring;              // 2-D convolution (one plane per image, dz = 1 only); du ring slots in use
     int Lx;                        // positions per x region (allocated)
     uint32_t x_stage_bytes, dy_slot_bytes;
 };
@@ -61,7 +62,7 @@ conv3d_dw_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t xs0 = smem_u32(smem);
     const uint32_t dys0 = xs0 + kXStages * p.x_stage_bytes;
-    uint8_t* tail = smem + (size_t)kXStages * p.x_stage_bytes + (size_t)kDyRing * p.dy_slot_bytes;
+    uint8_t* tail = smem + (size_t)kXStages * p.x_stage_bytes + (size_t)p.dring * p.dy_slot_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail);     // full_x[2] empty_x[2] full_dy[4] empty_dy[4] done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kXStages + 2 * kDyRing + 1);
     uint32_t* touched_s = tmem_slot + 1;                     // [3]: accumulators each issuer has written
@@ -73,7 +74,7 @@ conv3d_dw_kernel(const __grid_constant__ Params p) {
     const int dyt = blockIdx.x % 3, slot = blockIdx.x / 3;
 
     // stale bytes behind a copy clamped at the end of a buffer must be finite: they meet halo zeros of the other operand
-    for (uint32_t i = threadIdx.x * 16; i < kXStages * p.x_stage_bytes + kDyRing * p.dy_slot_bytes; i += kThreads * 16)
+    for (uint32_t i = threadIdx.x * 16; i < kXStages * p.x_stage_bytes + p.dring * p.dy_slot_bytes; i += kThreads * 16)
         *reinterpret_cast<uint4*>(smem + i) = make_uint4(0u, 0u, 0u, 0u);
     if (threadIdx.x == 0) {
         for (int i = 0; i < kXStages; ++i) { mbar_init(bar_fx + 8 * i, 1); mbar_init(bar_ex + 8 * i, 3); }
@@ -91,7 +92,8 @@ conv3d_dw_kernel(const __grid_constant__ Params p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int NACC = 3 * p.NM;
+    const int NACC = p.two_d ? p.NM : 3 * p.NM;
+    const uint32_t DR = (uint32_t)p.dring;
     const uint32_t x_region = (uint32_t)p.Lx * 16u;                 // bytes per 8-channel group of one copy
     const int xg = p.R / 8;                                         // 8-channel groups per copy (parts x chunks)
     const int dg = p.N / 8;
@@ -128,7 +130,7 @@ conv3d_dw_kernel(const __grid_constant__ Params p) {
             }
             const int64_t x_plane = (int64_t)p.KCi * p.PP * 8, d_plane = (int64_t)p.KCo * p.PP * 8;
             auto load_dy = [&](int dpl) {
-                const uint32_t r = pc + (uint32_t)(dpl - dlo), sl = r % kDyRing;
+                const uint32_t r = pc + (uint32_t)(dpl - dlo), sl = r % DR;
                 const uint16_t* dsrc = p.dy + d_off + dpl * d_plane;
                 uint32_t dbytes = 0;
                 if (d_lane) {            // a narrow plane's rounded-up run may pass the end of the buffer: clamp
@@ -137,7 +139,7 @@ conv3d_dw_kernel(const __grid_constant__ Params p) {
                 }
                 const uint32_t dtotal = __reduce_add_sync(0xffffffffu, dbytes);
                 if (lane == 0) {
-                    mbar_wait(bar_ed + 8 * sl, ((r / kDyRing) & 1) ^ 1, 11);
+                    mbar_wait(bar_ed + 8 * sl, ((r / DR) & 1) ^ 1, 11);
                     mbar_arrive_expect_tx(bar_fd + 8 * sl, dtotal);
                 }
                 __syncwarp();
@@ -168,7 +170,9 @@ conv3d_dw_kernel(const __grid_constant__ Params p) {
         // =========================== MMA ISSUERS (warp 1 + dz) ===========================
         // A warp issues one tcgen05.mma per ~120 cycles (uniform-datapath work + issue latency), the tensor pipe takes
         // one of these every ~48: three issuers, one per dz (its own accumulators, its own du plane of the ring).
-        const int dz = warp - 1;
+        const int iz = warp - 1;
+        const int dz = p.two_d ? 1 : iz;                             // 2-D: one plane per image, the centre dz only
+        const int j0 = p.two_d ? iz : 0, j1 = p.two_d ? min(iz + 1, p.NM) : p.NM;   // 2-D: issuer iz owns accumulator iz
         const uint32_t idesc = idesc_mn((uint32_t)p.N);
         const uint32_t a_hi = (uint32_t)p.Lx | (1u << 14);           // SBO = one x region (16-byte units), version 1
         const uint32_t b_hi = (uint32_t)kChunk | (1u << 14);         // SBO = one du region
@@ -182,19 +186,19 @@ conv3d_dw_kernel(const __grid_constant__ Params p) {
             for (int e = e0; e < e1; ++e, ++sx) {
                 const uint32_t st = sx % kXStages;
                 const int dpl = e - dz + 1;                          // du plane paired with x plane e for this dz
-                const bool live = dpl >= 0 && dpl < p.d;
+                const bool live = dpl >= 0 && dpl < p.d && j0 < j1;
                 if (live) {
                     const uint32_t r = pc + (uint32_t)(dpl - dlo);
-                    mbar_wait(bar_fd + 8 * (r % kDyRing), (r / kDyRing) & 1, 13);
+                    mbar_wait(bar_fd + 8 * (r % DR), (r / DR) & 1, 13);
                 }
                 mbar_wait(bar_fx + 8 * st, (sx / kXStages) & 1, 15);
                 tc_fence_after();
                 if (live) {
                     const uint32_t a0 = lbo | ((xs0 + st * p.x_stage_bytes) >> 4);
-                    const uint32_t b0 = lbo | ((dys0 + ((pc + (uint32_t)(dpl - dlo)) % kDyRing) * p.dy_slot_bytes) >> 4);
+                    const uint32_t b0 = lbo | ((dys0 + ((pc + (uint32_t)(dpl - dlo)) % DR) * p.dy_slot_bytes) >> 4);
                     for (int ks = 0; ks < ksteps; ++ks) {
-                        for (int j = 0; j < p.NM; ++j) {
-                            const int acc = dz * p.NM + j;
+                        for (int j = j0; j < j1; ++j) {
+                            const int acc = p.two_d ? j : dz * p.NM + j;
                             if (elect_one())
                                 umma_f16(tmem_base + (uint32_t)(acc * p.N), a0 + (uint32_t)(ks * 16 + j * p.NCOPY), a_hi,
                                          b0 + (uint32_t)ks * 16u, b_hi, idesc, (touched >> acc) & 1u);
@@ -205,15 +209,15 @@ conv3d_dw_kernel(const __grid_constant__ Params p) {
                 if (elect_one()) {
                     umma_commit(bar_ex + 8 * st);
                     // a du plane is last used by the step of x plane (plane + 1), or by the item's last step
-                    if (e - 1 >= dlo) umma_commit(bar_ed + 8 * ((pc + (uint32_t)(e - 1 - dlo)) % kDyRing));
+                    if (e - 1 >= dlo) umma_commit(bar_ed + 8 * ((pc + (uint32_t)(e - 1 - dlo)) % DR));
                     if (e == e1 - 1)
-                        for (int q = e; q <= dhi; ++q) umma_commit(bar_ed + 8 * ((pc + (uint32_t)(q - dlo)) % kDyRing));
+                        for (int q = e; q <= dhi; ++q) umma_commit(bar_ed + 8 * ((pc + (uint32_t)(q - dlo)) % DR));
                 }
                 __syncwarp();
             }
             pc += (uint32_t)(dhi - dlo + 1);
         }
-        if (lane == 0) { touched_s[dz] = touched; __threadfence_block(); }
+        if (lane == 0) { touched_s[iz] = touched; __threadfence_block(); }
         __syncwarp();
         if (elect_one()) umma_commit(bar_done);
     } else if (warp >= 4) {
@@ -254,13 +258,13 @@ conv3d_dw_kernel(const __grid_constant__ Params p) {
 
 // partials [G*3 ctas][3*NM][128][N] -> grad_w [27][cin][cout]: fixed summation order (CTA slot, then x part, then du part)
 __global__ void dw_reduce_kernel(const float* __restrict__ ws, float* __restrict__ gw, int G, int NM, int NCOPY, int R, int N,
-                                 int cin, int cout, int cin_pad, int cout_pad, int nparts, float scale) {
+                                 int cin, int cout, int cin_pad, int cout_pad, int nparts, float scale, int two_d) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= 27 * cin * cout) return;
+    if (idx >= (two_d ? 9 : 27) * cin * cout) return;
     const int co = idx % cout, ci = (idx / cout) % cin, tap = idx / (cout * cin);
-    const int dx = tap % 3, dyt = (tap / 3) % 3, dz = tap / 9;
+    const int dx = tap % 3, dyt = (tap / 3) % 3, dz = two_d ? 0 : tap / 9;
     const int j = dx / NCOPY, cp = dx - j * NCOPY;
-    const int NACC = 3 * NM;
+    const int NACC = two_d ? NM : 3 * NM;
     float s = 0.f;
     for (int g = 0; g < G; ++g) {
         const float* base = ws + (((int64_t)(g * 3 + dyt) * NACC + dz * NM + j) * 128) * N;
@@ -314,12 +318,13 @@ __global__ void colsum_finish_kernel(const float* __restrict__ partial, int plan
 }
 
 struct Plan {
-    int cin_pad, cout_pad, KCi, KCo, nparts, NCOPY, NM, R, N, Wp, PP, span, nchunks, items, G, Lx, nseg, dseg;
+    int cin_pad, cout_pad, KCi, KCo, nparts, NCOPY, NM, R, N, Wp, PP, span, nchunks, items, G, Lx, nseg, dseg, two_d, dring, nacc;
     uint32_t x_stage_bytes, dy_slot_bytes, smem_bytes;
 };
 
 static bool make_plan(const lf_conv_desc* d, Plan& pl) {
-    if (d->ndim != 3 || d->k != 3) return false;
+    if (d->k != 3 || !(d->ndim == 3 || (d->ndim == 2 && d->d == 1))) return false;
+    pl.two_d = d->ndim == 2;
     if (d->precision != 1 && d->precision != 2) return false;
     if (d->n < 1 || d->d < 1 || d->h < 1 || d->w < 1 || d->cin < 1 || d->cout < 1) return false;
     pl.cin_pad = (d->cin + 15) / 16 * 16;
@@ -327,10 +332,11 @@ static bool make_plan(const lf_conv_desc* d, Plan& pl) {
     pl.nparts = d->precision == 1 ? 2 : 1;
     pl.R = pl.nparts * pl.cin_pad;
     pl.N = pl.nparts * pl.cout_pad;
-    if (pl.R != 32 && pl.R != 64) return false;                 // M = NCOPY * R = 128 with NCOPY in {4, 2}
-    if (pl.N > 64) return false;                                // 3 * NM * N TMEM columns <= 512
+    if (pl.R != 32 && pl.R != 64 && !(pl.two_d && pl.R == 128)) return false;   // M = NCOPY * R = 128, NCOPY in {4, 2, 1}
     pl.NCOPY = 128 / pl.R;
     pl.NM = (3 + pl.NCOPY - 1) / pl.NCOPY;
+    pl.nacc = pl.two_d ? pl.NM : 3 * pl.NM;
+    if (pl.N > 128 || pl.nacc * pl.N > 512) return false;       // accumulators live in TMEM (512 columns)
     pl.KCi = pl.cin_pad / 8; pl.KCo = pl.cout_pad / 8;
     pl.Wp = d->w + 2;
     pl.PP = (d->h + 2) * pl.Wp;
@@ -351,8 +357,12 @@ static bool make_plan(const lf_conv_desc* d, Plan& pl) {
     pl.Lx = (pl.Lx + 7) / 8 * 8;
     pl.x_stage_bytes = (uint32_t)(pl.NCOPY * (pl.R / 8)) * pl.Lx * 16u;
     pl.dy_slot_bytes = (uint32_t)(pl.N / 8) * kChunk * 16u;
-    pl.smem_bytes = kXStages * pl.x_stage_bytes + kDyRing * pl.dy_slot_bytes + 8 * (2 * kXStages + 2 * kDyRing + 1) + 64;
-    return pl.smem_bytes <= 227u * 1024u;
+    const uint32_t tail = 8 * (2 * kXStages + 2 * kDyRing + 1) + 64;
+    for (pl.dring = kDyRing; pl.dring >= (pl.two_d ? 2 : 4); --pl.dring) {
+        pl.smem_bytes = kXStages * pl.x_stage_bytes + pl.dring * pl.dy_slot_bytes + tail;
+        if (pl.smem_bytes <= 227u * 1024u) return true;
+    }
+    return false;
 }
 
 }  // namespace dw
@@ -369,7 +379,7 @@ extern "C" int lf_conv3d_dw_supported(const lf_conv_desc* desc) {
 extern "C" int64_t lf_conv3d_dw_ws(const lf_conv_desc* desc) {
     dw::Plan pl;
     if (desc == nullptr || !dw::make_plan(desc, pl)) return 0;
-    return (int64_t)pl.G * 3 * 3 * pl.NM * 128 * pl.N + (int64_t)desc->n * desc->d * pl.cout_pad;
+    return (int64_t)pl.G * 3 * pl.nacc * 128 * pl.N + (int64_t)desc->n * desc->d * pl.cout_pad;
 }
 
 // grad_w_packed [27][Cin][Cout] (overwritten) = desc->scale * sum x (.) du over all positions; grad_bias [Cout] (nullable) = sum du.
@@ -379,7 +389,7 @@ extern "C" int lf_conv3d_dw(const lf_conv_desc* desc, const void* x_split, const
                             float* grad_w_packed, float* grad_bias, void* stream) {
     dw::Plan pl;
     if (desc == nullptr || !dw::make_plan(desc, pl)) {
-        set_error("conv3d_dw: unsupported shape/precision (3-D k=3, parts*Cin_pad in {32, 64}, parts*Cout_pad <= 64)");
+        set_error("conv3d_dw: unsupported shape/precision (k=3; 3-D: parts*Cin_pad in {32, 64}, parts*Cout_pad <= 64; 2-D: <= 128)");
         return LF_EUNSUPPORTED;
     }
     LF_CHECK_ARG(x_split && du_split && ws && grad_w_packed, "conv3d_dw: null pointer");
@@ -395,16 +405,16 @@ extern "C" int lf_conv3d_dw(const lf_conv_desc* desc, const void* x_split, const
     p.n = desc->n; p.d = desc->d; p.Wp = pl.Wp; p.PP = pl.PP; p.KCi = pl.KCi; p.KCo = pl.KCo; p.nparts = pl.nparts;
     p.NCOPY = pl.NCOPY; p.NM = pl.NM; p.R = pl.R; p.N = pl.N;
     p.span = pl.span; p.nchunks = pl.nchunks; p.items = pl.items; p.G = pl.G; p.Lx = pl.Lx;
-    p.nseg = pl.nseg; p.dseg = pl.dseg;
+    p.nseg = pl.nseg; p.dseg = pl.dseg; p.two_d = pl.two_d; p.dring = pl.dring;
     p.x_stage_bytes = pl.x_stage_bytes; p.dy_slot_bytes = pl.dy_slot_bytes;
     cudaError_t e = cudaFuncSetAttribute(dw::conv3d_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) { set_error("conv3d_dw: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return (int)e; }
     dw::conv3d_dw_kernel<<<pl.G * 3, dw::kThreads, pl.smem_bytes, st>>>(p);
-    const int total = 27 * desc->cin * desc->cout;
+    const int total = (pl.two_d ? 9 : 27) * desc->cin * desc->cout;
     dw::dw_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(ws, grad_w_packed, pl.G, pl.NM, pl.NCOPY, pl.R, pl.N, desc->cin,
-                                                              desc->cout, pl.cin_pad, pl.cout_pad, pl.nparts, desc->scale);
+                                                              desc->cout, pl.cin_pad, pl.cout_pad, pl.nparts, desc->scale, pl.two_d);
     if (grad_bias != nullptr) {
-        float* partial = ws + (int64_t)pl.G * 3 * 3 * pl.NM * 128 * pl.N;
+        float* partial = ws + (int64_t)pl.G * 3 * pl.nacc * 128 * pl.N;
         const int planes = desc->n * desc->d;
         dw::split_colsum_kernel<<<planes, 256, 0, st>>>(p.dy, p.dy_part, pl.nparts, pl.KCo, pl.PP, partial);
         dw::colsum_finish_kernel<<<(desc->cout + 63) / 64, 64, 0, st>>>(partial, planes, pl.cout_pad, desc->cout, grad_bias);

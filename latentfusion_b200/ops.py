@@ -416,20 +416,21 @@ def conv3d_dz(xs, wpk, bias, cout, scale, act, slope, norm, precision, want_dens
     return y, ys, rnorm
 
 
-def conv3d_dw(xs, dus, precision, scale=1.0):
-    """weight / bias gradient of a 3x3x3 convolution from the split-planar twins of its input and of
-    d(loss)/d(pre-activation output): -> (grad_w_packed [27][Cin][Cout], grad_bias [1][Cout]).  lf_conv3d_dw"""
+def conv3d_dw(xs, dus, precision, scale=1.0, ndim=3):
+    """weight / bias gradient of a 3x3x3 (ndim 3) or 3x3 (ndim 2: one plane per image) convolution from the
+    split-planar twins of its input and of d(loss)/d(pre-activation output):
+    -> (grad_w_packed [27 | 9][Cin][Cout], grad_bias [1][Cout]).  lf_conv3d_dw"""
     lib = L.lib()
-    desc = _desc(KIND_CONV, 3, xs.n, xs.d, xs.h, xs.w, xs.c, dus.c, 3, scale, 0, 0.0, 0, precision)
+    desc = _desc(KIND_CONV, ndim, xs.n, xs.d, xs.h, xs.w, xs.c, dus.c, 3, scale, 0, 0.0, 0, precision)
     if not lib.lf_conv3d_dw_supported(ctypes.byref(desc)):
         raise ValueError(f"conv3d_dw: unsupported shape (Cin {xs.c}, Cout {dus.c}, precision {precision})")
     dev = xs.buf.device
-    gwp = torch.empty(27, xs.c, dus.c, device=dev, dtype=torch.float32)
+    gwp = torch.empty(27 if ndim == 3 else 9, xs.c, dus.c, device=dev, dtype=torch.float32)
     gbp = torch.empty(1, dus.c, device=dev, dtype=torch.float32)
     ws = torch.empty(lib.lf_conv3d_dw_ws(ctypes.byref(desc)), device=dev, dtype=torch.float32)
     _call('lf_conv3d_dw', lib.lf_conv3d_dw,
           (ctypes.byref(desc), _p(xs.buf), _p(dus.buf), _p(ws), _p(gwp), _p(gbp), _stream()), kernels=4,
-          nbytes=2 * (xs.buf.numel() + dus.buf.numel()), flops=2 * xs.n * xs.d * xs.h * xs.w * 27 * xs.c * dus.c)
+          nbytes=2 * (xs.buf.numel() + dus.buf.numel()), flops=2 * xs.n * xs.d * xs.h * xs.w * gwp.shape[0] * xs.c * dus.c)
     return gwp, gbp
 
 
@@ -585,7 +586,7 @@ class _EqConv(torch.autograd.Function):
                   nbytes=4 * (2 * gy.numel() + gx.numel()), flops=bflops)
             fused_done = True
         wdesc = _desc(kind, nd, n, d, h, w, cin, cout, k, scale, 0, 0.0, 0, 0)
-        if need_w and kind == KIND_CONV and nd == 3 and k == 3 and not _DW_FFMA:
+        if need_w and kind == KIND_CONV and nd in (2, 3) and k == 3 and not _DW_FFMA:
             wdesc.precision = {1: 1, 2: 2, 3: 1}.get(precision, 0)
             if not (wdesc.precision and lib.lf_conv3d_dw_supported(ctypes.byref(wdesc))):
                 wdesc.precision = 0
@@ -663,8 +664,9 @@ class _EqConv(torch.autograd.Function):
             taps = wb.shape[0]
             if use_dw:
                 # tensor-core weight gradient straight from the split-planar twins of x and du (csrc/conv3d_dw.cu)
-                gwp, gbp = conv3d_dw(ctx.xs if ctx.xs is not None else split_pack(x),
-                                     du_split if du_split is not None else split_pack(du), wdesc.precision, scale)
+                as5 = (lambda t: t) if nd == 3 else (lambda t: t.unsqueeze(2))       # a 2-D map is a one-plane volume
+                gwp, gbp = conv3d_dw(ctx.xs if ctx.xs is not None else split_pack(as5(x)),
+                                     du_split if du_split is not None else split_pack(as5(du)), wdesc.precision, scale, nd)
             else:
                 wdesc.precision = 0
                 if du is None:

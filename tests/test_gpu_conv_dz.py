@@ -164,3 +164,25 @@ def test_conv3d_weight_gradient_on_tensor_cores_vs_fp64(shape):
     assert float((gbp.double().reshape(-1) - bref).abs().max() / bref.abs().max()) < (1e-4 if prec == 1 else 1e-2)
     gwp2, _ = ops.conv3d_dw(ops.split_pack(x), ops.split_pack(du), prec)
     assert torch.equal(gwp, gwp2)                       # fixed-order reduction: bit-reproducible
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shape', [(3, 32, 64, 24, 20, 1), (2, 64, 64, 16, 16, 1), (4, 4, 32, 33, 17, 1), (2, 64, 32, 12, 12, 1),
+                                   (2, 32, 32, 16, 16, 2)])
+def test_conv2d_weight_gradient_on_tensor_cores_vs_fp64(shape):
+    """the same kernel on 2-D maps (the U-Nets' 3x3 convolutions): one plane per image, centre dz only, up to 64 channels"""
+    import torch.nn.functional as F
+    from latentfusion_b200 import ops
+    n, cin, cout, h, w, prec = shape
+    dev = torch.device('cuda:0')
+    torch.manual_seed(sum(shape))
+    x = torch.randn(n, cin, h, w, device=dev)
+    du = torch.randn(n, cout, h, w, device=dev)
+    gwp, gbp = ops.conv3d_dw(ops.split_pack(x.unsqueeze(2)), ops.split_pack(du.unsqueeze(2)), prec, ndim=2)
+    wz = torch.zeros(cout, cin, 3, 3, device=dev, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double(), wz, padding=1).backward(du.double())
+    ref = wz.grad.permute(2, 3, 1, 0).reshape(9, cin, cout)
+    err = float((gwp.double() - ref).norm() / ref.norm())
+    assert err < (2e-5 if prec == 1 else 1e-2), f'relative L2 {err:.3g}'
+    bref = du.double().sum(dim=(0, 2, 3))
+    assert float((gbp.double().reshape(-1) - bref).abs().max() / bref.abs().max()) < (1e-4 if prec == 1 else 1e-2)
