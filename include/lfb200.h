@@ -190,6 +190,25 @@ int lf_gru_gates1(const float* u_pre, const float* r_pre, const float* h, float*
                   int64_t numel, void* stream);
 int lf_gru_gates2(const float* h, const float* update, const float* o, float* h_new,
                   int64_t numel, void* stream);
+/* backward of the two gate kernels (autograd of modules/gru.py:38-41), one pass each */
+int lf_gru_gates1_bwd(const float* g_update, const float* g_hr, const float* update, const float* r_pre, const float* h,
+                      float* g_u_pre, float* g_r_pre, float* g_h, int64_t numel, void* stream);
+int lf_gru_gates2_bwd(const float* g, const float* h, const float* update, const float* o, float* g_h, float* g_update,
+                      float* g_o, int64_t numel, void* stream);
+/* ConvLSTM gate non-linearities (modules/lstm.py:41-56): gates [P][4*hidden] channels-last = (i | f | o | g)
+ * pre-activations; c_next = sig(f) c_cur + sig(i) tanh(g); h_next = sig(o) tanh(c_next).  bwd: g_h / g_c nullable. */
+int lf_lstm_gates_fwd(const float* gates, const float* c_cur, float* h_next, float* c_next, int64_t positions, int hidden,
+                      void* stream);
+int lf_lstm_gates_bwd(const float* g_h, const float* g_c, const float* gates, const float* c_cur, float* g_gates,
+                      float* g_c_cur, int64_t positions, int hidden, void* stream);
+/* softmax over the outer axis V of scores [B][V][P] and the weighted sum of z [B][V][P][C] over it, channels-last:
+ * the BlendFuser's view blend (recon/fusion.py:92-96).  Writes the weights [B][V][P] too.  bwd: g_weights and g_z nullable. */
+int lf_softmax_blend_fwd(const float* scores, const float* z, float* weights, float* out, int b, int v, int64_t p, int c,
+                         void* stream);
+int lf_softmax_blend_bwd(const float* g_out, const float* g_weights, const float* weights, const float* z, float* g_scores,
+                         float* g_z, int b, int v, int64_t p, int c, void* stream);
+/* projection_type='sum' (recon/models.py:436-437): x [N][D][HW][C] -> out [N][HW][C] */
+int lf_depth_sum_fwd(const float* x, float* out, int n, int d, int64_t hw, int c, void* stream);
 
 /* ---- camera algebra (modules/geometry.py:106-108,147-163,207-213,249-255; three/quaternion.py:287-311,39-93) ----
  * The ten learnable floats of each hypothesis -> the object->camera constant block, and its analytic VJP

@@ -52,6 +52,13 @@ _SIGNATURES = {
     'lf_actnorm_bwd_split': (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_vp] + [c_int] * 6 + [c_float, c_int, c_vp]),
     'lf_ibr_blend_bwd': (c_int, [c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_vp]),
     'lf_ibr_warp_blend_bwd': (c_int, [c_f32p, c_f32p, c_float, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    'lf_gru_gates1_bwd': (c_int, [c_f32p] * 8 + [c_i64, c_vp]),
+    'lf_gru_gates2_bwd': (c_int, [c_f32p] * 7 + [c_i64, c_vp]),
+    'lf_lstm_gates_fwd': (c_int, [c_f32p] * 4 + [c_i64, c_int, c_vp]),
+    'lf_lstm_gates_bwd': (c_int, [c_f32p] * 6 + [c_i64, c_int, c_vp]),
+    'lf_softmax_blend_fwd': (c_int, [c_f32p] * 4 + [c_int, c_int, c_i64, c_int, c_vp]),
+    'lf_softmax_blend_bwd': (c_int, [c_f32p] * 6 + [c_int, c_int, c_i64, c_int, c_vp]),
+    'lf_depth_sum_fwd': (c_int, [c_f32p, c_f32p, c_int, c_int, c_i64, c_int, c_vp]),
     'lf_set_option': (c_int, [ctypes.c_char_p, c_int]),
     'lf_conv3d_dw_supported': (c_int, [ctypes.POINTER(ConvDesc)]),
     'lf_conv3d_dw_ws': (c_i64, [ctypes.POINTER(ConvDesc)]),

@@ -193,6 +193,123 @@ __global__ void gru_gates2_kernel(const float* __restrict__ h, const float* __re
     }
 }
 
+// backward of the two GRU gate kernels (modules/gru.py:38-41), one pass each
+__global__ void gru_gates1_bwd_kernel(const float* __restrict__ g_update, const float* __restrict__ g_hr,
+                                      const float* __restrict__ update, const float* __restrict__ r_pre,
+                                      const float* __restrict__ h, float* __restrict__ g_u_pre, float* __restrict__ g_r_pre,
+                                      float* __restrict__ g_h, int64_t n) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const float u = update[e], r = sigmoidf_(r_pre[e]), gh = g_hr[e];
+        g_u_pre[e] = g_update[e] * u * (1.f - u);
+        g_r_pre[e] = gh * h[e] * r * (1.f - r);
+        g_h[e] = gh * r;
+    }
+}
+
+__global__ void gru_gates2_bwd_kernel(const float* __restrict__ g, const float* __restrict__ h, const float* __restrict__ update,
+                                      const float* __restrict__ o, float* __restrict__ g_h, float* __restrict__ g_update,
+                                      float* __restrict__ g_o, int64_t n) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const float u = update[e], gg = g[e];
+        g_h[e] = gg * (1.f - u);
+        g_update[e] = gg * (o[e] - h[e]);
+        g_o[e] = gg * u;
+    }
+}
+
+// ConvLSTM gates (modules/lstm.py:41-56): gates [P][4H] channels-last = (i | f | o | g) pre-activations, c_cur [P][H]
+//   c_next = sigmoid(f) * c_cur + sigmoid(i) * tanh(g);   h_next = sigmoid(o) * tanh(c_next)
+__global__ void lstm_gates_fwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_cur,
+                                      float* __restrict__ h_next, float* __restrict__ c_next, int64_t P, int H) {
+    const int64_t total = P * H;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pos = e / H; const int c = (int)(e - pos * H);
+        const float* gp = gates + pos * 4 * H + c;
+        const float gi = sigmoidf_(gp[0]), gf = sigmoidf_(gp[H]), go = sigmoidf_(gp[2 * H]), gg = tanhf(gp[3 * H]);
+        const float cn = gf * c_cur[e] + gi * gg;
+        c_next[e] = cn;
+        h_next[e] = go * tanhf(cn);
+    }
+}
+
+__global__ void lstm_gates_bwd_kernel(const float* __restrict__ g_h, const float* __restrict__ g_c, const float* __restrict__ gates,
+                                      const float* __restrict__ c_cur, float* __restrict__ g_gates, float* __restrict__ g_c_cur,
+                                      int64_t P, int H) {
+    const int64_t total = P * H;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pos = e / H; const int c = (int)(e - pos * H);
+        const float* gp = gates + pos * 4 * H + c;
+        float* go_ = g_gates + pos * 4 * H + c;
+        const float gi = sigmoidf_(gp[0]), gf = sigmoidf_(gp[H]), go = sigmoidf_(gp[2 * H]), gg = tanhf(gp[3 * H]);
+        const float cc = c_cur[e], cn = gf * cc + gi * gg, tc = tanhf(cn);
+        const float gh = g_h != nullptr ? g_h[e] : 0.f;
+        const float dcn = (g_c != nullptr ? g_c[e] : 0.f) + gh * go * (1.f - tc * tc);
+        go_[0] = dcn * gg * gi * (1.f - gi);
+        go_[H] = dcn * cc * gf * (1.f - gf);
+        go_[2 * H] = gh * tc * go * (1.f - go);
+        go_[3 * H] = dcn * gi * (1.f - gg * gg);
+        g_c_cur[e] = dcn * gf;
+    }
+}
+
+// softmax over an outer axis followed by a weighted sum over it (channels-last):
+//   BlendFuser (recon/fusion.py:92-96): scores [B][V][P], z [B][V][P][C]  -> w = softmax_V(scores), out[b][p][c] = sum_v w z
+__global__ void softmax_blend_fwd_kernel(const float* __restrict__ scores, const float* __restrict__ z, float* __restrict__ wts,
+                                         float* __restrict__ out, int B, int V, int64_t P, int C) {
+    const int64_t total = (int64_t)B * P;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = e / P, pp = e - b * P;
+        const float* sp = scores + b * V * P + pp;
+        float m = -INFINITY;
+        for (int v = 0; v < V; ++v) m = fmaxf(m, sp[(int64_t)v * P]);
+        float den = 0.f;
+        for (int v = 0; v < V; ++v) den += expf(sp[(int64_t)v * P] - m);
+        for (int c = 0; c < C; ++c) out[e * C + c] = 0.f;
+        for (int v = 0; v < V; ++v) {
+            const float w = expf(sp[(int64_t)v * P] - m) / den;
+            wts[(b * V + v) * P + pp] = w;
+            const float* zp = z + ((b * V + v) * P + pp) * C;
+            for (int c = 0; c < C; ++c) out[e * C + c] += w * zp[c];
+        }
+    }
+}
+
+__global__ void softmax_blend_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ g_wts,
+                                         const float* __restrict__ wts, const float* __restrict__ z, float* __restrict__ g_scores,
+                                         float* __restrict__ g_z, int B, int V, int64_t P, int C) {
+    const int64_t total = (int64_t)B * P;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = e / P, pp = e - b * P;
+        const float* go = g_out + e * C;
+        float A = 0.f;
+        for (int v = 0; v < V; ++v) {                 // up_v = <g_out, z_v> + g_wts_v;  A = sum_v w_v up_v
+            const int64_t wi = (b * V + v) * P + pp;
+            const float* zp = z + wi * C;
+            float up = g_wts != nullptr ? g_wts[wi] : 0.f;
+            for (int c = 0; c < C; ++c) up += go[c] * zp[c];
+            g_scores[wi] = up;
+            A += wts[wi] * up;
+        }
+        for (int v = 0; v < V; ++v) {
+            const int64_t wi = (b * V + v) * P + pp;
+            const float w = wts[wi];
+            g_scores[wi] = w * (g_scores[wi] - A);
+            if (g_z != nullptr) for (int c = 0; c < C; ++c) g_z[wi * C + c] = w * go[c];
+        }
+    }
+}
+
+// 'sum' projection (recon/models.py:436-437): x [N][D][Q][C] (Q = H*W) -> out [N][Q][C] = sum over depth
+__global__ void depth_sum_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int D, int64_t QC) {
+    const int64_t total = (int64_t)N * QC;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = e / QC, r = e - n * QC;
+        float s = 0.f;
+        for (int d = 0; d < D; ++d) s += x[(n * D + d) * QC + r];
+        out[e] = s;
+    }
+}
+
 static unsigned ew_grid(int64_t total) {
     int64_t b = (total + 255) / 256;
     const int64_t cap = (int64_t)sm_count() * 32;
@@ -245,6 +362,56 @@ extern "C" int lf_gru_gates1(const float* u_pre, const float* r_pre, const float
                              int64_t numel, void* stream) {
     LF_CHECK_ARG(u_pre && r_pre && h && update && hr && numel > 0, "gru_gates1: bad arguments");
     gru_gates1_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(u_pre, r_pre, h, update, hr, numel);
+    LF_RETURN_LAUNCH();
+}
+
+extern "C" int lf_gru_gates1_bwd(const float* g_update, const float* g_hr, const float* update, const float* r_pre,
+                                 const float* h, float* g_u_pre, float* g_r_pre, float* g_h, int64_t numel, void* stream) {
+    LF_CHECK_ARG(g_update && g_hr && update && r_pre && h && g_u_pre && g_r_pre && g_h && numel > 0, "gru_gates1_bwd: bad arguments");
+    gru_gates1_bwd_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(g_update, g_hr, update, r_pre, h, g_u_pre, g_r_pre, g_h, numel);
+    LF_RETURN_LAUNCH();
+}
+
+extern "C" int lf_gru_gates2_bwd(const float* g, const float* h, const float* update, const float* o, float* g_h,
+                                 float* g_update, float* g_o, int64_t numel, void* stream) {
+    LF_CHECK_ARG(g && h && update && o && g_h && g_update && g_o && numel > 0, "gru_gates2_bwd: bad arguments");
+    gru_gates2_bwd_kernel<<<ew_grid(numel), 256, 0, (cudaStream_t)stream>>>(g, h, update, o, g_h, g_update, g_o, numel);
+    LF_RETURN_LAUNCH();
+}
+
+extern "C" int lf_lstm_gates_fwd(const float* gates, const float* c_cur, float* h_next, float* c_next, int64_t positions,
+                                 int hidden, void* stream) {
+    LF_CHECK_ARG(gates && c_cur && h_next && c_next && positions > 0 && hidden > 0, "lstm_gates: bad arguments");
+    lstm_gates_fwd_kernel<<<ew_grid(positions * hidden), 256, 0, (cudaStream_t)stream>>>(gates, c_cur, h_next, c_next, positions, hidden);
+    LF_RETURN_LAUNCH();
+}
+
+extern "C" int lf_lstm_gates_bwd(const float* g_h, const float* g_c, const float* gates, const float* c_cur, float* g_gates,
+                                 float* g_c_cur, int64_t positions, int hidden, void* stream) {
+    LF_CHECK_ARG(gates && c_cur && g_gates && g_c_cur && positions > 0 && hidden > 0, "lstm_gates_bwd: bad arguments");
+    lstm_gates_bwd_kernel<<<ew_grid(positions * hidden), 256, 0, (cudaStream_t)stream>>>(g_h, g_c, gates, c_cur, g_gates, g_c_cur,
+                                                                                     positions, hidden);
+    LF_RETURN_LAUNCH();
+}
+
+extern "C" int lf_softmax_blend_fwd(const float* scores, const float* z, float* weights, float* out, int b, int v, int64_t p,
+                                    int c, void* stream) {
+    LF_CHECK_ARG(scores && z && weights && out && b > 0 && v > 0 && p > 0 && c > 0, "softmax_blend: bad arguments");
+    softmax_blend_fwd_kernel<<<ew_grid((int64_t)b * p), 256, 0, (cudaStream_t)stream>>>(scores, z, weights, out, b, v, p, c);
+    LF_RETURN_LAUNCH();
+}
+
+extern "C" int lf_softmax_blend_bwd(const float* g_out, const float* g_weights, const float* weights, const float* z,
+                                    float* g_scores, float* g_z, int b, int v, int64_t p, int c, void* stream) {
+    LF_CHECK_ARG(g_out && weights && z && g_scores && b > 0 && v > 0 && p > 0 && c > 0, "softmax_blend_bwd: bad arguments");
+    softmax_blend_bwd_kernel<<<ew_grid((int64_t)b * p), 256, 0, (cudaStream_t)stream>>>(g_out, g_weights, weights, z, g_scores, g_z,
+                                                                                     b, v, p, c);
+    LF_RETURN_LAUNCH();
+}
+
+extern "C" int lf_depth_sum_fwd(const float* x, float* out, int n, int d, int64_t hw, int c, void* stream) {
+    LF_CHECK_ARG(x && out && n > 0 && d > 0 && hw > 0 && c > 0, "depth_sum: bad arguments");
+    depth_sum_fwd_kernel<<<ew_grid((int64_t)n * hw * c), 256, 0, (cudaStream_t)stream>>>(x, out, n, d, hw * c);
     LF_RETURN_LAUNCH();
 }
 

@@ -1,10 +1,11 @@
 """Convolutional LSTM cell.  API/checkpoint mirror of reference ``latentfusion/modules/lstm.py``
-(ConvLSTMCell :7-56).  The 4-gate convolution is the fused lfb200 kernel; the gate non-linearities
-are small elementwise torch ops (the LSTM fuser is not used by the released recipe)."""
+(ConvLSTMCell :7-56).  The 4-gate convolution is the fused lfb200 kernel; the gate non-linearities run in one
+elementwise kernel each way (``lf_lstm_gates_fwd`` / ``_bwd``) on CUDA tensors."""
 import torch
 from torch import nn
 
 from . import EqualizedConv3d
+from .. import ops
 
 
 class ConvLSTMCell(nn.Module):
@@ -19,6 +20,8 @@ class ConvLSTMCell(nn.Module):
     def forward(self, input_tensor, cur_state):
         h_cur, c_cur = cur_state
         gates = self.conv(torch.cat([input_tensor, h_cur], dim=1))
+        if gates.is_cuda:
+            return ops.lstm_gates(gates, c_cur)
         gi, gf, go, gg = torch.split(gates, self.hidden_channels, dim=1)
         c_next = torch.sigmoid(gf) * c_cur + torch.sigmoid(gi) * torch.tanh(gg)
         return torch.sigmoid(go) * torch.tanh(c_next), c_next

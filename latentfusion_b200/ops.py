@@ -807,8 +807,13 @@ class _GruGates1(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_update, g_hr):
         update, r_pre, h = ctx.saved_tensors
-        r = torch.sigmoid(r_pre)
-        return g_update * update * (1 - update), g_hr * h * r * (1 - r), g_hr * r
+        zero = lambda: torch.zeros_like(h)                                    # noqa: E731
+        gu = to_cl(g_update.float()) if g_update is not None else zero()
+        gh = to_cl(g_hr.float()) if g_hr is not None else zero()
+        g_u, g_r, g_h = torch.empty_like(h), torch.empty_like(h), torch.empty_like(h)
+        _call('lf_gru_gates1_bwd', L.lib().lf_gru_gates1_bwd,
+              (_p(gu), _p(gh), _p(update), _p(r_pre), _p(h), _p(g_u), _p(g_r), _p(g_h), h.numel(), _stream()))
+        return g_u, g_r, g_h
 
 
 class _GruGates2(torch.autograd.Function):
@@ -826,7 +831,11 @@ class _GruGates2(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         h, update, o = ctx.saved_tensors
-        return g * (1 - update), g * (o - h), g * update
+        g = to_cl(g.float())
+        g_h, g_u, g_o = torch.empty_like(h), torch.empty_like(h), torch.empty_like(h)
+        _call('lf_gru_gates2_bwd', L.lib().lf_gru_gates2_bwd,
+              (_p(g), _p(h), _p(update), _p(o), _p(g_h), _p(g_u), _p(g_o), h.numel(), _stream()))
+        return g_h, g_u, g_o
 
 
 def gru_gates1(u_pre, r_pre, h):
@@ -835,6 +844,102 @@ def gru_gates1(u_pre, r_pre, h):
 
 def gru_gates2(h, update, o):
     return _GruGates2.apply(h, update, o)
+
+
+class _LstmGates(torch.autograd.Function):
+    """ConvLSTM gate non-linearities in one pass (modules/lstm.py:41-56); gates [N,4H,...] = (i | f | o | g)."""
+
+    @staticmethod
+    def forward(ctx, gates, c_cur):
+        _need_cuda(gates, c_cur)
+        gates, c_cur = to_cl(gates), to_cl(c_cur)
+        hid = c_cur.shape[1]
+        pos = c_cur.numel() // hid
+        h_next, c_next = torch.empty_like(c_cur), torch.empty_like(c_cur)
+        _call('lf_lstm_gates_fwd', L.lib().lf_lstm_gates_fwd, (_p(gates), _p(c_cur), _p(h_next), _p(c_next), pos, hid, _stream()))
+        ctx.save_for_backward(gates, c_cur)
+        return h_next, c_next
+
+    @staticmethod
+    def backward(ctx, g_h, g_c):
+        gates, c_cur = ctx.saved_tensors
+        hid = c_cur.shape[1]
+        pos = c_cur.numel() // hid
+        g_h = None if g_h is None else to_cl(g_h.float())
+        g_c = None if g_c is None else to_cl(g_c.float())
+        g_gates, g_cc = torch.empty_like(gates), torch.empty_like(c_cur)
+        _call('lf_lstm_gates_bwd', L.lib().lf_lstm_gates_bwd,
+              (_p(g_h), _p(g_c), _p(gates), _p(c_cur), _p(g_gates), _p(g_cc), pos, hid, _stream()))
+        return g_gates, g_cc
+
+
+def lstm_gates(gates, c_cur):
+    """-> (h_next, c_next)"""
+    return _LstmGates.apply(gates, c_cur)
+
+
+class _SoftmaxBlend(torch.autograd.Function):
+    """w = softmax over axis 1 of scores [B,V,P...]; out = sum_v w * z with z [B,V,P...,C] in memory (channels-last)."""
+
+    @staticmethod
+    def forward(ctx, scores, z, B, V, P, C):
+        wts = torch.empty(B, V, P, device=z.device)
+        out = torch.empty(B, P, C, device=z.device)
+        _call('lf_softmax_blend_fwd', L.lib().lf_softmax_blend_fwd, (_p(scores), _p(z), _p(wts), _p(out), B, V, P, C, _stream()),
+              nbytes=4 * (z.numel() + out.numel()))
+        ctx.save_for_backward(wts, z)
+        ctx.dims = (B, V, P, C)
+        return out, wts
+
+    @staticmethod
+    def backward(ctx, g_out, g_wts):
+        wts, z = ctx.saved_tensors
+        B, V, P, C = ctx.dims
+        g_out = torch.zeros(B, P, C, device=z.device) if g_out is None else g_out.float().contiguous()
+        g_wts = None if g_wts is None else g_wts.float().contiguous()
+        g_scores = torch.empty(B, V, P, device=z.device)
+        g_z = torch.empty_like(z) if ctx.needs_input_grad[1] else None
+        _call('lf_softmax_blend_bwd', L.lib().lf_softmax_blend_bwd,
+              (_p(g_out), _p(g_wts), _p(wts), _p(z), _p(g_scores), _p(g_z), B, V, P, C, _stream()),
+              nbytes=4 * (2 * z.numel() + g_out.numel()))
+        return g_scores, g_z, None, None, None, None
+
+
+def view_softmax_blend(scores, z_obj):
+    """BlendFuser (recon/fusion.py:92-96): scores [B,V,1,D,H,W], z_obj [B,V,C,D,H,W] ->
+    (sum_v softmax_v(scores) * z_obj  [B,1,C,D,H,W], weights [B,V,1,D,H,W])."""
+    _need_cuda(scores, z_obj)
+    B, V, C = z_obj.shape[:3]
+    sp = tuple(z_obj.shape[3:])
+    P = 1
+    for e in sp:
+        P *= e
+    zc = z_obj.float().movedim(2, -1).contiguous()                   # [B,V,D,H,W,C]: a no-op for per-view channels-last cubes
+    out, wts = _SoftmaxBlend.apply(scores.float().reshape(B, V, P).contiguous(), zc.view(B, V, P, C), B, V, P, C)
+    return out.view(B, *sp, C).movedim(-1, 1).unsqueeze(1), wts.view(B, V, 1, *sp)
+
+
+class _DepthSum(torch.autograd.Function):
+    """projection_type='sum' (recon/models.py:436-437): [N,C,D,H,W] -> [N,C,H,W]"""
+
+    @staticmethod
+    def forward(ctx, x):
+        _need_cuda(x)
+        x = to_cl(x)
+        n, c, d, h, w = x.shape
+        out = empty_cl((n, c, h, w), x.device)
+        _call('lf_depth_sum_fwd', L.lib().lf_depth_sum_fwd, (_p(x), _p(out), n, d, h * w, c, _stream()),
+              nbytes=4 * (x.numel() + out.numel()))
+        ctx.d = d
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.unsqueeze(2).expand(-1, -1, ctx.d, -1, -1)
+
+
+def depth_sum(x):
+    return _DepthSum.apply(x)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -91,7 +91,16 @@ class BlendFuser(_ParamFuser):
         scores = self.unet(torch.cat((flat, utils.get_normalized_voxel_depth(flat)), dim=1))
         return torch.softmax(b2bv(self.transform_block(scores, camera), views), dim=1)
 
+    def compute_blend_scores(self, z_cam, camera):
+        views = z_cam.shape[1]
+        flat = bv2b(z_cam)
+        scores = self.unet(torch.cat((flat, utils.get_normalized_voxel_depth(flat)), dim=1))
+        return b2bv(self.transform_block(scores, camera), views)
+
     def forward(self, z_obj, z_cam_mid, z_obj_mid, camera):
+        if z_obj.is_cuda:           # softmax over the views and the weighted sum in one pass (lf_softmax_blend_*)
+            fused, weights = ops.view_softmax_blend(self.compute_blend_scores(z_cam_mid[-1], camera), z_obj)
+            return fused, {'blend_weights': weights.squeeze(2)}
         weights = self.compute_blend_weights(z_cam_mid[-1], camera)
         return (z_obj * weights).sum(dim=1, keepdim=True), {'blend_weights': weights.squeeze(2)}
 

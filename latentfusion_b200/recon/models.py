@@ -253,7 +253,7 @@ class Photographer(_Checkpointable, nn.Module):
             # without the occlusion branch the projection is the only consumer of the camera block's output
             z = self.projection_block(z if self.occlusion_module else ops.mark_single_consumer(z))
         elif self.projection_type == 'sum':
-            z = z.sum(dim=2)
+            z = ops.depth_sum(z) if z.is_cuda else z.sum(dim=2)
         y = self.image_decoder(z)
         if len(self.output_blocks):
             y = self._heads(y)

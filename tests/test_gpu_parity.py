@@ -552,3 +552,48 @@ def test_mixed_precision_path_stated_tolerance(g, dev):
             torch.testing.assert_close(getattr(cam, k).grad.cpu(), g[f'grad.{k}'], atol=5e-2, rtol=5e-2)
     finally:
         ops.set_default_precision(old)
+
+
+def test_small_fused_kernels_vs_torch_autograd(dev):
+    """GRU gate backward, ConvLSTM gates, the BlendFuser's softmax-over-views blend and the 'sum' projection:
+    each kernel (forward and backward) against fp64 autograd of the reference expression
+    (modules/gru.py:38-41, modules/lstm.py:41-56, recon/fusion.py:92-96, recon/models.py:436-437)."""
+    from latentfusion_b200 import ops
+    torch.manual_seed(21)
+    n, c, d, h, w = 2, 8, 5, 6, 7
+    mk = lambda *s: torch.randn(*s, device=dev)                                          # noqa: E731
+
+    def check(outs, refs, ins, rins):
+        gs = [torch.randn_like(o) for o in outs]
+        sum((o * g).sum() for o, g in zip(outs, gs)).backward()
+        sum((o * g.double()).sum() for o, g in zip(refs, gs)).backward()
+        for o, r in zip(outs, refs):
+            torch.testing.assert_close(o.double(), r, atol=1e-5, rtol=1e-5)
+        for a, b in zip(ins, rins):
+            torch.testing.assert_close(a.grad.double(), b.grad, atol=2e-5, rtol=1e-4)
+
+    # GRU gates
+    u, r, hh = (mk(n, c, d, h, w).requires_grad_(True) for _ in range(3))
+    u6, r6, h6 = (t.detach().double().requires_grad_(True) for t in (u, r, hh))
+    upd, hr = ops.gru_gates1(u, r, hh)
+    check([upd, hr], [torch.sigmoid(u6), h6 * torch.sigmoid(r6)], [u, r, hh], [u6, r6, h6])
+    a, b, o = (mk(n, c, d, h, w).requires_grad_(True) for _ in range(3))
+    a6, b6, o6 = (t.detach().double().requires_grad_(True) for t in (a, b, o))
+    check([ops.gru_gates2(a, b, o)], [a6 * (1 - b6) + o6 * b6], [a, b, o], [a6, b6, o6])
+    # LSTM gates
+    gates, cc = mk(n, 4 * c, d, h, w).requires_grad_(True), mk(n, c, d, h, w).requires_grad_(True)
+    g6, c6 = gates.detach().double().requires_grad_(True), cc.detach().double().requires_grad_(True)
+    gi, gf, go, gg = torch.split(g6, c, dim=1)
+    cn = torch.sigmoid(gf) * c6 + torch.sigmoid(gi) * torch.tanh(gg)
+    check(list(ops.lstm_gates(gates, cc)), [torch.sigmoid(go) * torch.tanh(cn), cn], [gates, cc], [g6, c6])
+    # BlendFuser blend
+    v = 4
+    sc, z = mk(n, v, 1, d, h, w).requires_grad_(True), mk(n, v, c, d, h, w).requires_grad_(True)
+    s6, z6 = sc.detach().double().requires_grad_(True), z.detach().double().requires_grad_(True)
+    w6 = torch.softmax(s6, dim=1)
+    fused, wts = ops.view_softmax_blend(sc, z)
+    check([fused, wts], [(z6 * w6).sum(dim=1, keepdim=True), w6], [sc, z], [s6, z6])
+    # 'sum' projection
+    x = mk(n, c, d, h, w).requires_grad_(True)
+    x6 = x.detach().double().requires_grad_(True)
+    check([ops.depth_sum(x)], [x6.sum(dim=2)], [x], [x6])
