@@ -482,11 +482,14 @@ def train_block(args, dev, rank, world, barrier, max_over_ranks, B=8, vin=16, vo
     cin, _ = ph.synthetic_cameras(B * vin, S, seed=21, perturb=False)
     cout, _ = ph.synthetic_cameras(B * vout, S, seed=22, perturb=False)
     pick = lambda cams, v, vl: cams[[b * v + rank * vl + j for b in range(B) for j in range(vl)]]    # noqa: E731
-    g = torch.Generator().manual_seed(23 + rank)
-    host = {'image': (torch.rand(B, vi, 3, P, P, generator=g) * 2 - 1).pin_memory(),
-            'mask': (torch.rand(B, vi, 1, P, P, generator=g) > 0.4).float().pin_memory(),
-            'depth': (torch.rand(B, vo, 1, P, P, generator=g) * 2 - 1).pin_memory(),
-            'gmask': (torch.rand(B, vo, 1, P, P, generator=g) > 0.5).float().pin_memory()}
+    # the same global batch at every world size (each rank keeps its view slice): the reported loss is then comparable
+    # across N (equal up to fp32 reassociation of the sharded sums)
+    g = torch.Generator().manual_seed(23)
+    cut = lambda t, vl: t[:, rank * vl:(rank + 1) * vl].contiguous().pin_memory()                 # noqa: E731
+    host = {'image': cut(torch.rand(B, vin, 3, P, P, generator=g) * 2 - 1, vi),
+            'mask': cut((torch.rand(B, vin, 1, P, P, generator=g) > 0.4).float(), vi),
+            'depth': cut(torch.rand(B, vout, 1, P, P, generator=g) * 2 - 1, vo),
+            'gmask': cut((torch.rand(B, vout, 1, P, P, generator=g) > 0.5).float(), vo)}
 
     def one():
         batch = {'in': {'camera': pick(cin, vin, vi).to(dev), 'image': host['image'].to(dev, non_blocking=True),
