@@ -376,7 +376,7 @@ class GradientPoseEstimator(PoseEstimator):
 
     def _can_graph(self, cameras):
         return (self.cuda_graph and self.optimizer == 'adam' and self.loss_func is default_pose_loss
-                and self.loss_weights.get('latent', 0.0) == 0.0 and cameras.device.type == 'cuda')
+                and cameras.device.type == 'cuda')
 
     def _optimize_camera_graphed(self, z_obj, target_obs, cameras, iters, ranking):
         from .refine_graph import GraphedRefiner

@@ -70,7 +70,7 @@ class _BatchedAdamPlateau:
 class GraphedRefiner:
     """Owns the static tensors, the captured graph and the device-side history of one refinement run."""
 
-    TERMS = ('ov_depth', 'depth', 'iou', 'mask')
+    TERMS = ('ov_depth', 'depth', 'iou', 'mask')            # + 'latent' on instances whose loss weights use it
 
     def __init__(self, estimator, z_obj, target_obs, cameras, chunk=16):
         self.est = estimator
@@ -90,6 +90,14 @@ class GraphedRefiner:
                                        estimator.lr_reduce_patience, estimator.lr_reduce_threshold,
                                        estimator.lr_reduce_factor)
         self.weights = dict(estimator.loss_weights)
+        # latent loss (configs/adam_latent.toml; reference estimation.py:605-609): the target code is the autoencoding of
+        # the PREPROCESSED target observation through the current hypothesis cameras, recomputed every iteration without
+        # grad.  The preprocessing depends on the observation only, so it is hoisted out of the captured loop.
+        self.use_latent = float(self.weights.get('latent', 0.0)) > 0.0
+        self.target_inputs = None
+        if self.use_latent:
+            self.TERMS = GraphedRefiner.TERMS + ('latent',)
+            self._set_target_inputs(target_obs, n)
         self.sched_w = {k: torch.tensor(float(self.weights.get(k, 0.0)), device=dev) for k in estimator.loss_schedules}
         # device history (one chunk)
         self.h_rank = torch.zeros(chunk, n, device=dev)
@@ -100,6 +108,23 @@ class GraphedRefiner:
         self.slot = torch.zeros(1, dtype=torch.long, device=dev)
         self.graph = None
         self._signature = self.make_signature(estimator, z_obj, target_obs, cameras, chunk)
+
+    def _set_target_inputs(self, target_obs, n):
+        obs = self.model.preprocess_observation(target_obs).to(self.model.device)
+        if len(obs) == 1:
+            obs = obs.expand(n)
+        fresh = {k: v.detach().clone() for k, v in self.model._inputs(obs, 1).items()}
+        if self.target_inputs is None:
+            self.target_inputs = fresh
+        else:                                   # keep the addresses the captured graph reads
+            for k, v in fresh.items():
+                self.target_inputs[k].copy_(v)
+
+    def _target_code(self, cam):
+        from ..recon import models
+        with torch.no_grad():
+            return models.autoencode(self.model.sculptor, self.model.fuser, self.model.photographer, camera=cam.detach(),
+                                     **self.target_inputs)[1]
 
     # ---- one iteration, device only ----
     def _camera(self):
@@ -115,13 +140,18 @@ class GraphedRefiner:
         ph = self.model.photographer
         if est.fused_loss and ph.predict_depth and ph.predict_mask and not ph.predict_color:
             # raw head outputs -> fused loss head (csrc/pose_loss.cu): no full-frame intermediates
-            logits, _, _ = ph.decode(self.z_obj, cam, interpret_logits=False)
+            logits, latent, _ = ph.decode(self.z_obj, cam, interpret_logits=False, return_latent=self.use_latent)
             terms = ops.pose_loss_terms(logits[:, 0], logits[:, 1], cam.viewport, cam.translation[:, 2],
                                         self.target.depth, self.target.mask, cam.z_span, 0.01, cam.width, cam.height)
-            losses = {k: terms[:, i] for i, k in enumerate(self.TERMS)}
+            losses = {k: terms[:, i] for i, k in enumerate(self.TERMS[:4])}
+            if self.use_latent:
+                from .estimation import cosine_distance
+                rendered = latent.squeeze(0).flatten(1)
+                losses['latent'] = cosine_distance(rendered, self._target_code(cam).flatten(1).expand_as(rendered))
         else:
-            z_depth, _, z_mask_logits, _ = est._render_observation(self.z_obj, cam)
-            losses = est.loss_func(self.target, z_depth, z_mask_logits, cam)
+            z_depth, _, z_mask_logits, z_latent = est._render_observation(self.z_obj, cam)
+            code = self._target_code(cam) if self.use_latent else None
+            losses = est.loss_func(self.target, z_depth, z_mask_logits, cam, z_pred_latent=z_latent, z_target_latent=code)
         rank = sum(self.weights.get(k, 0.0) * v for k, v in losses.items())
         optim = rank
         if self.sched_w:
@@ -148,7 +178,10 @@ class GraphedRefiner:
         graph holds raw pointers into the packed-weight caches, which are keyed by parameter version), the convolution
         precision, the loss weights / schedules and the optimiser hyper-parameters.  A mismatch means re-capture."""
         model = est.model
-        params = tuple((id(p), p._version) for net in (model.photographer,) for p in net.parameters())
+        nets = (model.photographer,)
+        if float(est.loss_weights.get('latent', 0.0)) > 0.0:       # the target code runs the encoder side too
+            nets += (model.sculptor, model.fuser)
+        params = tuple((id(p), p._version) for net in nets for p in net.parameters())
         return (len(cameras), tuple(z_obj.shape), tuple(target_obs.depth.shape), cameras.width, cameras.height,
                 cameras.z_span, params, ops.get_default_precision(), tuple(sorted(est.loss_weights.items())),
                 tuple(sorted(est.loss_schedules)), est.learning_rate, est.lr_reduce_patience, est.lr_reduce_threshold,
@@ -163,6 +196,8 @@ class GraphedRefiner:
         self.z_obj.copy_(z_obj)
         self.target.color.copy_(target_obs.color); self.target.depth.copy_(target_obs.depth)
         self.target.mask.copy_(target_obs.mask)
+        if self.use_latent:
+            self._set_target_inputs(target_obs, self.n)
         self.template.intrinsic.copy_(cameras.intrinsic)
         self.lq.copy_(cameras.log_quaternion); self.tr.copy_(cameras.translation); self.vp.copy_(cameras.viewport)
         o = self.opt

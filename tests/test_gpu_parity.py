@@ -597,3 +597,36 @@ def test_small_fused_kernels_vs_torch_autograd(dev):
     x = mk(n, c, d, h, w).requires_grad_(True)
     x6 = x.detach().double().requires_grad_(True)
     check([ops.depth_sum(x)], [x6.sum(dim=2)], [x], [x6])
+
+
+def test_latent_loss_refinement_graphed_equals_eager(g, dev):
+    """configs/adam_latent.toml (latent = 0.2; reference estimation.py:605-609): the captured-graph refiner — fused loss
+    head + latent cosine against a target code recomputed through the hypothesis cameras every iteration — follows the
+    same trajectory as the eager loop (per-hypothesis torch optimisers, default_pose_loss on uncropped frames)."""
+    from latentfusion_b200.pose import estimation
+    from latentfusion_b200.observation import Observation
+    from latentfusion_b200.recon.inference import LatentFusionModel
+    sculptor, fuser, photographer = ph.build_product_models(g, dev)
+    model = LatentFusionModel(sculptor, fuser, photographer, g.meta['camera_dist'], dev)
+    cfg = {'type': 'gradient', 'args': dict(optimizer='adam', num_iters=3, num_samples=g.meta['N'], ranking_size=g.meta['N'],
+                                            learning_rate=0.01, lr_reduce_patience=10, lr_reduce_threshold=1e-4,
+                                            converge_threshold=1e-6, converge_patience=10),
+           'loss_weights': dict(depth=1.0, ov_depth=0.3, iou=0.0, mask=0.0, latent=0.2)}
+    gt = ph.product_camera(g.cam('ref_cam_full'), 'cpu')[0:1]
+    torch.manual_seed(5)
+    target = Observation(torch.rand(1, 3, 480, 640), g['target.depth'], g['target.mask'], gt)
+    init = ph.product_camera(g.cam('est.init_cam'), 'cpu')
+    runs = {}
+    for graphed in (True, False):
+        est = estimation.load_from_config(cfg, model, track_stats=True, return_camera_history=True)
+        est.cuda_graph = graphed
+        best, stats, history = est.estimate(g['z_obj_gru'].to(dev), target, camera=init)
+        assert (getattr(est, '_refiner', None) is not None) == graphed
+        runs[graphed] = (best, stats, history)
+    a, b = runs[True], runs[False]
+    assert float(a[1]['latent_loss'].abs().max()) > 1e-3                       # the term is really there
+    torch.testing.assert_close(a[1]['latent_loss'], b[1]['latent_loss'], atol=2e-4, rtol=2e-3)
+    torch.testing.assert_close(a[1]['rank_loss'], b[1]['rank_loss'], atol=1e-3, rtol=2e-3)
+    for (_, ca), (_, cb) in zip(a[2], b[2]):
+        torch.testing.assert_close(ca.translation, cb.translation, atol=3e-4, rtol=1e-3)
+        torch.testing.assert_close(ca.log_quaternion, cb.log_quaternion, atol=3e-4, rtol=1e-3)
