@@ -250,6 +250,21 @@ int lf_pose_loss_bwd(const lf_loss_desc* desc, const float* depth_logits, const 
                      float* grad_depth_logits, float* grad_mask_logits, float* grad_viewport /* [N][4] */,
                      float* grad_tz /* [N] */, void* stream);
 
+/* ---- wide 3x3x3 layers: weights streamed through shared memory (csrc/conv3d_ws.cu) ----
+ * The same reference op as lf_conv3d_dz for the released network widths (tools/train/train.sh:37-46: 64/128/256-channel
+ * camera / object blocks on a 16^3 latent), where 27*Cin*Cout weights do not fit in shared memory: one item = (sample,
+ * output plane, chunk of 64|128 output channels); the activation slab of one plane and one 32-channel input group is
+ * staged by bulk TMA, weight tiles of one (dz, group, tap) stream through a 4-slot ring, accumulators of all M-tiles of
+ * the (small) plane live in TMEM across the whole K loop.  x_split: split-planar input (Cin padded to 16 must be a
+ * multiple of 32); y32 fp32 channels-last; PixelNorm (desc->norm) runs as a second small kernel over `scratch`
+ * (lf_conv3d_ws_scratch floats) and writes rnorm.  Planes up to (tiles x chunk <= 512 TMEM columns), e.g. 16x16 at 128. */
+int lf_conv3d_ws_supported(const lf_conv_desc* desc);
+int64_t lf_conv3d_ws_weight_bytes(int cin, int cout);
+int lf_conv3d_ws_pack_weights(const float* w_packed27 /* [27][Cin][Cout] */, void* out, int cin, int cout, void* stream);
+int64_t lf_conv3d_ws_scratch(const lf_conv_desc* desc);
+int lf_conv3d_ws(const lf_conv_desc* desc, const void* x_split, const void* w_packed, const float* bias, float* y32,
+                 float* rnorm, float* scratch, void* stream);
+
 /* ---- weight gradient of the 3x3x3 convolution on the tensor cores (csrc/conv3d_dw.cu) ----
  * Replaces the autograd of modules/equalized.py:57-64 w.r.t. the weight inside ReconTrainer.run_iteration
  * (tools/train/train_reconstruct.py:523-534).  x_split / du_split: split-planar volumes (layout above) of the forward

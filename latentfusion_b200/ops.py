@@ -372,6 +372,36 @@ def _dz_pack(wf, key):
     return out
 
 
+def _ws_pack(wf, key):
+    """[27][Cin][Cout] fp32 -> the weight-streaming kernel's tile order (cached per parameter version)"""
+    hit = _TC_PACK_CACHE.get(key[1:])
+    if hit is not None and hit[0]() is key[0]:
+        return hit[1]
+    taps, cin, cout = wf.shape
+    out = torch.empty(L.lib().lf_conv3d_ws_weight_bytes(cin, cout) // 2, device=wf.device, dtype=torch.int16)
+    _call('lf_conv3d_ws_pack_weights', L.lib().lf_conv3d_ws_pack_weights, (_p(wf), _p(out), cin, cout, _stream()))
+    _cache_put(_TC_PACK_CACHE, key[1:], (weakref.ref(key[0]), out), 256)
+    return out
+
+
+def _ws_ok(desc):
+    return desc.precision in (1, 2) and bool(L.lib().lf_conv3d_ws_supported(ctypes.byref(desc)))
+
+
+def conv3d_ws(xs, wpk, bias, desc, name='lf_conv3d_ws'):
+    """wide 3x3x3 layer with streamed weights: SplitVol -> (dense fp32 channels-last, rnorm | None)"""
+    lib = L.lib()
+    dev = xs.buf.device
+    y = empty_cl((xs.n, desc.cout, xs.d, xs.h, xs.w), dev)
+    positions = xs.n * xs.d * xs.h * xs.w
+    rnorm = torch.empty(positions, device=dev, dtype=torch.float32) if desc.norm else None
+    scratch = torch.empty(lib.lf_conv3d_ws_scratch(ctypes.byref(desc)), device=dev, dtype=torch.float32) if desc.norm else None
+    _call(name, lib.lf_conv3d_ws,
+          (ctypes.byref(desc), _p(xs.buf), _p(wpk), _p(bias), _p(y), _p(rnorm), _p(scratch), _stream()),
+          kernels=2 if desc.norm else 1, nbytes=xs.buf.numel() * 2 + 4 * y.numel(), flops=2 * positions * 27 * xs.c * desc.cout)
+    return y, rnorm
+
+
 _GRAD_SPLIT = [None]       # (data_ptr, numel, SplitVol) of the most recent fused bwd-data result: its single consumer is
 #                            the very next backward node (the producer layer's), which takes it instead of re-packing
 
@@ -514,8 +544,9 @@ class _EqConv(torch.autograd.Function):
         desc = _desc(kind, nd, n, d, h, w, gcin, gcout, k, scale, act, slope, norm,
                      PRECISION_BF16X3 if precision == PRECISION_MIXED else precision)
         use_dz = kind == KIND_CONV and nd == 3 and k == 3 and _dz_ok(desc)
-        y = None if use_dz else empty_cl(out_shape, dev)
-        rnorm = torch.empty(positions, device=dev, dtype=torch.float32) if (norm and not use_dz) else None
+        use_ws = (not use_dz) and kind == KIND_CONV and nd == 3 and k == 3 and _ws_ok(desc)      # wide layers
+        y = None if (use_dz or use_ws) else empty_cl(out_shape, dev)
+        rnorm = torch.empty(positions, device=dev, dtype=torch.float32) if (norm and not (use_dz or use_ws)) else None
         taps = wf.shape[0]
         wkey = (weight, id(weight), weight._version, kind)
         _EqConv.last_split = None
@@ -528,6 +559,9 @@ class _EqConv(torch.autograd.Function):
             y, ys, rnorm = conv3d_dz(xs, _dz_pack(wf, wkey + ('dzf',)), bpk, gcout, scale, act, slope, norm, desc.precision,
                                      want_dense=True, want_split=emit_split, name=_conv_name(kind, nd, k, 'fwd'))
             _EqConv.last_split = ys
+        elif use_ws:
+            xs = x_split if x_split is not None else split_pack(x)
+            y, rnorm = conv3d_ws(xs, _ws_pack(wf, wkey + ('wsf',)), bpk, desc, name=_conv_name(kind, nd, k, 'fwd'))
         else:
             if _tc_ok(desc):
                 wf_arg = _tc_pack(wf, wkey + ('f',))
@@ -648,6 +682,10 @@ class _EqConv(torch.autograd.Function):
                       kernels=1 if bkind == KIND_EXPAND else _tc_passes(bdesc),
                       nbytes=4 * (du.numel() + 2 * gx.numel()), flops=bflops)
                 rec_in.pre_applied = True
+            elif ctx.needs_input_grad[0] and kind == KIND_CONV and nd == 3 and k == 3 and _ws_ok(bdesc):
+                # wide layer: bwd-data = the weight-streaming kernel on the flipped / transposed weights
+                gx, _ = conv3d_ws(split_pack(du), _ws_pack(wb, ctx.wkey + ('wsb',)), None, bdesc,
+                                  name=_conv_name(kind, nd, k, 'bwd_data'))
             elif ctx.needs_input_grad[0]:
                 gx = torch.empty_like(x)
                 # bwd-data = the same implicit GEMM with flipped/transposed weights, no epilogue

@@ -186,3 +186,37 @@ def test_conv2d_weight_gradient_on_tensor_cores_vs_fp64(shape):
     assert err < (2e-5 if prec == 1 else 1e-2), f'relative L2 {err:.3g}'
     bref = du.double().sum(dim=(0, 2, 3))
     assert float((gbp.double().reshape(-1) - bref).abs().max() / bref.abs().max()) < (1e-4 if prec == 1 else 1e-2)
+
+
+@pytest.mark.parametrize('shape', [(2, 64, 128, 6, 16, 16), (1, 128, 64, 5, 16, 16), (1, 256, 256, 3, 16, 16), (2, 64, 64, 4, 12, 10),
+                                   (1, 96, 192, 3, 16, 16)])
+@pytest.mark.parametrize('precision', [1, 2])
+def test_wide_conv_weight_streaming_vs_fp64(dev, shape, precision):
+    """Released network widths (reference tools/train/train.sh:37-46: 64/128/256-channel 3-D blocks on a 16^3 latent):
+    eq_conv routes them to the weight-streaming tcgen05 kernel (csrc/conv3d_ws.cu), forward (scale, bias, LeakyReLU,
+    PixelNorm over all channel chunks) and bwd-data; checked against fp64 autograd of the reference op."""
+    from latentfusion_b200 import ops
+    n, cin, cout, d, h, w = shape
+    torch.manual_seed(sum(shape))
+    x = torch.randn(n, cin, d, h, w, device=dev, requires_grad=True)
+    wt = torch.randn(cout, cin, 3, 3, 3, device=dev)
+    b = torch.randn(cout, device=dev) * 0.1
+    g = torch.randn(n, cout, d, h, w, device=dev)
+    ops.KernelTrace.reset(True)
+    try:
+        y = ops.eq_conv(x, wt, b, act=True, norm=True, precision=precision)
+        y.backward(g)
+        names = [r[0] for r in ops.KernelTrace.records]
+    finally:
+        ops.KernelTrace.reset(False)
+    assert 'lf_conv_bwd_weight' not in names and names.count('lf_conv_fwd[conv3d_k3]') == 1, names
+    x64 = x.detach().double().requires_grad_(True)
+    he = math.sqrt(2.0 / (cin * 27))
+    u = F.conv3d(x64, wt.double(), None, padding=1) * he + b.double().view(1, -1, 1, 1, 1)
+    u = F.leaky_relu(u, 0.2)
+    ref = u / torch.sqrt((u * u).mean(dim=1, keepdim=True) + 1e-8)
+    ref.backward(g.double())
+    tol = dict(atol=2e-4, rtol=2e-3) if precision == 1 else dict(atol=4e-2, rtol=4e-2)
+    torch.testing.assert_close(y.double(), ref, **tol)
+    gerr = float((x.grad.double() - x64.grad).norm() / x64.grad.norm())
+    assert gerr < (1e-4 if precision == 1 else 5e-2), f'd/dx relative L2 {gerr:.3g}'     # (plain bf16 operands, K up to 27*256)
