@@ -257,10 +257,13 @@ int lf_pose_loss_bwd(const lf_loss_desc* desc, const float* depth_logits, const 
  * staged by bulk TMA, weight tiles of one (dz, group, tap) stream through a 4-slot ring, accumulators of all M-tiles of
  * the (small) plane live in TMEM across the whole K loop.  x_split: split-planar input (Cin padded to 16 must be a
  * multiple of 32); y32 fp32 channels-last; PixelNorm (desc->norm) runs as a second small kernel over `scratch`
- * (lf_conv3d_ws_scratch floats) and writes rnorm.  Planes up to (tiles x chunk <= 512 TMEM columns), e.g. 16x16 at 128. */
+ * (lf_conv3d_ws_scratch floats) and writes rnorm.  Also takes 2-D 3x3 layers (ndim 2, d = 1: one plane per image, the
+ * U-Nets' 128..512-channel maps); a plane larger than TMEM / shared memory hold at once is cut into tile groups that
+ * stream the weights again (row pitch up to ~130 positions). */
 int lf_conv3d_ws_supported(const lf_conv_desc* desc);
-int64_t lf_conv3d_ws_weight_bytes(int cin, int cout);
-int lf_conv3d_ws_pack_weights(const float* w_packed27 /* [27][Cin][Cout] */, void* out, int cin, int cout, void* stream);
+int64_t lf_conv3d_ws_weight_bytes(int taps /* 27 | 9 */, int cin, int cout);
+int lf_conv3d_ws_pack_weights(const float* w_packed /* [27 | 9][Cin][Cout] */, void* out, int taps, int cin, int cout,
+                              void* stream);
 int64_t lf_conv3d_ws_scratch(const lf_conv_desc* desc);
 int lf_conv3d_ws(const lf_conv_desc* desc, const void* x_split, const void* w_packed, const float* bias, float* y32,
                  float* rnorm, float* scratch, void* stream);

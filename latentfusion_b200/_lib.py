@@ -60,8 +60,8 @@ _SIGNATURES = {
     'lf_softmax_blend_bwd': (c_int, [c_f32p] * 6 + [c_int, c_int, c_i64, c_int, c_vp]),
     'lf_depth_sum_fwd': (c_int, [c_f32p, c_f32p, c_int, c_int, c_i64, c_int, c_vp]),
     'lf_conv3d_ws_supported': (c_int, [ctypes.POINTER(ConvDesc)]),
-    'lf_conv3d_ws_weight_bytes': (c_i64, [c_int, c_int]),
-    'lf_conv3d_ws_pack_weights': (c_int, [c_f32p, c_vp, c_int, c_int, c_vp]),
+    'lf_conv3d_ws_weight_bytes': (c_i64, [c_int, c_int, c_int]),
+    'lf_conv3d_ws_pack_weights': (c_int, [c_f32p, c_vp, c_int, c_int, c_int, c_vp]),
     'lf_conv3d_ws_scratch': (c_i64, [ctypes.POINTER(ConvDesc)]),
     'lf_conv3d_ws': (c_int, [ctypes.POINTER(ConvDesc), c_vp, c_vp, c_f32p, c_f32p, c_f32p, c_f32p, c_vp]),
     'lf_set_option': (c_int, [ctypes.c_char_p, c_int]),

@@ -41,6 +41,7 @@ struct Params {
     float* ss;                     // [positions][nchunks] partial sums of squares (nullable)
     int64_t x_part;
     int n, d, h, w, Wp, PP, KCin, G, cout, NCH, nchunks, T, L_alloc, items, nprod;
+    int ndz, Tg, ngroups;          // 3 (3-D) | 1 (2-D: one plane per image); M-tiles per item and tile groups per plane
     uint32_t slab_bytes, btile_bytes;
     float scale, slope;
     int act;
@@ -85,17 +86,20 @@ conv3d_ws_kernel(const __grid_constant__ Params p) {
 
     const uint32_t region = (uint32_t)p.L_alloc * 16u;              // one 8-channel chunk of a slab
     const int nparts = p.nprod == 3 ? 2 : 1;
-    const uint32_t copy_bytes = (uint32_t)min(p.L_alloc, p.PP) * 16u;
 
     if (warp == 0) {
         // =========================== TMA PRODUCER ===========================
         // lanes 0..7: the 8 regions (part, k-chunk) of the activation slab; lane 8: the weight tile of each tap
         uint32_t sa = 0, sb = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-            const int c = item % p.nchunks;
-            const int dpl = (item / p.nchunks) % p.d, n = item / (p.nchunks * p.d);
-            for (int dz = 0; dz < 3; ++dz) {
-                const int e = dpl + dz - 1;
+            int r_ = item;
+            const int c = r_ % p.nchunks; r_ /= p.nchunks;
+            const int tg = r_ % p.ngroups; r_ /= p.ngroups;
+            const int dpl = r_ % p.d, n = r_ / p.d;
+            const int start = tg * p.Tg * 128;                               // first slab position of this tile group
+            const uint32_t copy_bytes = (uint32_t)min(p.L_alloc, p.PP - start) * 16u;
+            for (int dz = 0; dz < p.ndz; ++dz) {
+                const int e = dpl + (p.ndz == 3 ? dz - 1 : 0);
                 if (e < 0 || e >= p.d) continue;
                 for (int g = 0; g < p.G; ++g, ++sa) {
                     const uint32_t st = sa % kAStages;
@@ -106,10 +110,11 @@ conv3d_ws_kernel(const __grid_constant__ Params p) {
                     __syncwarp();
                     if (lane < 4 * nparts) {
                         const int part = lane >> 2, kc = lane & 3;
-                        const uint16_t* src = p.x + part * p.x_part + (((int64_t)n * p.d + e) * p.KCin + g * 4 + kc) * p.PP * 8;
+                        const uint16_t* src = p.x + part * p.x_part +
+                                              ((((int64_t)n * p.d + e) * p.KCin + g * 4 + kc) * p.PP + start) * 8;
                         bulk_g2s(as0 + st * p.slab_bytes + (uint32_t)lane * region, src, copy_bytes, bar_af + 8 * st);
                     }
-                    const uint16_t* wt = p.wpk + ((((int64_t)c * 3 + dz) * p.G + g) * 9) * (p.btile_bytes / 2);
+                    const uint16_t* wt = p.wpk + ((((int64_t)c * p.ndz + dz) * p.G + g) * 9) * (p.btile_bytes / 2);
                     for (int tap = 0; tap < 9; ++tap, ++sb) {
                         const uint32_t sl = sb % kBRing;
                         if (lane == 8) {
@@ -133,12 +138,14 @@ conv3d_ws_kernel(const __grid_constant__ Params p) {
         const uint32_t b_ks = (2u * (uint32_t)p.NCH * 16u) >> 4, a_ks = 2u * (region >> 4);   // +16 input channels
         uint32_t sa = 0, sb = 0, it = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-            const int dpl = (item / p.nchunks) % p.d;
+            const int tg = (item / p.nchunks) % p.ngroups;
+            const int dpl = (item / (p.nchunks * p.ngroups)) % p.d;
+            const int Tcur = min(p.Tg, p.T - tg * p.Tg);
             mbar_wait(bar_acce, (it & 1) ^ 1, 23);                           // the previous item's rows have been drained
             tc_fence_after();
             uint32_t fresh = 1;                                              // first MMA of the item overwrites
-            for (int dz = 0; dz < 3; ++dz) {
-                const int e = dpl + dz - 1;
+            for (int dz = 0; dz < p.ndz; ++dz) {
+                const int e = dpl + (p.ndz == 3 ? dz - 1 : 0);
                 if (e < 0 || e >= p.d) continue;
                 for (int g = 0; g < p.G; ++g, ++sa) {
                     const uint32_t st = sa % kAStages;
@@ -150,7 +157,7 @@ conv3d_ws_kernel(const __grid_constant__ Params p) {
                         tc_fence_after();
                         const int dy = tap / 3, dx = tap - dy * 3;
                         const uint32_t b0 = b_lbo | ((bs0 + sl * p.btile_bytes) >> 4);
-                        for (int t = iz; t < p.T; t += 3) {
+                        for (int t = iz; t < Tcur; t += 3) {
                             const uint32_t dcol = tmem_base + (uint32_t)(t * p.NCH);
                             const uint32_t at = a0 + (uint32_t)(t * 128 + dy * p.Wp + dx);
                             for (int ks = 0; ks < 2; ++ks) {
@@ -182,8 +189,11 @@ conv3d_ws_kernel(const __grid_constant__ Params p) {
         const int first = p.Wp + 1;
         uint32_t it = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-            const int c = item % p.nchunks;
-            const int dpl = (item / p.nchunks) % p.d, n = item / (p.nchunks * p.d);
+            int r_ = item;
+            const int c = r_ % p.nchunks; r_ /= p.nchunks;
+            const int tg = r_ % p.ngroups; r_ /= p.ngroups;
+            const int dpl = r_ % p.d, n = r_ / p.d;
+            const int Tcur = min(p.Tg, p.T - tg * p.Tg);
             for (int i = threadIdx.x - 128; i < p.NCH; i += 128) {
                 const int ch = c * p.NCH + i;
                 bias_s[i] = (p.bias != nullptr && ch < p.cout) ? p.bias[ch] : 0.f;
@@ -191,8 +201,8 @@ conv3d_ws_kernel(const __grid_constant__ Params p) {
             asm volatile("bar.sync 1, 128;" ::: "memory");
             mbar_wait(bar_accf, it & 1, 26);
             tc_fence_after();
-            for (int t = 0; t < p.T; ++t) {
-                const int q = first + t * 128 + wq * 32 + lane;
+            for (int t = 0; t < Tcur; ++t) {
+                const int q = first + (tg * p.Tg + t) * 128 + wq * 32 + lane;
                 const int yp = fast_div(q, p.magic_Wp), xp = q - yp * p.Wp;
                 const bool valid = (yp >= 1) && (yp <= p.h) && (xp >= 1) && (xp <= p.w);
                 const int64_t pos = (((int64_t)n * p.d + dpl) * p.h + (yp - 1)) * p.w + (xp - 1);
@@ -254,9 +264,9 @@ ws_finish_kernel(float* __restrict__ y, const float* __restrict__ ss, float* __r
 
 // [27][cin][cout] fp32 -> [chunk][dz][g][tap9][part][kc4][NCH][8] bf16 (hi | lo)
 __global__ void pack_weights_ws_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int cin, int cout, int G,
-                                       int NCH, int nchunks) {
+                                       int NCH, int nchunks, int ndz) {
     const int64_t per_tile = (int64_t)4 * NCH * 8;                 // elements of one part
-    const int64_t total = (int64_t)nchunks * 3 * G * 9 * per_tile;
+    const int64_t total = (int64_t)nchunks * ndz * G * 9 * per_tile;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = e;
         const int j = (int)(r % 8); r /= 8;
@@ -264,14 +274,14 @@ __global__ void pack_weights_ws_kernel(const float* __restrict__ w, uint16_t* __
         const int kc = (int)(r % 4); r /= 4;
         const int tap = (int)(r % 9); r /= 9;
         const int g = (int)(r % G); r /= G;
-        const int dz = (int)(r % 3);
-        const int c = (int)(r / 3);
+        const int dz = (int)(r % ndz);
+        const int c = (int)(r / ndz);
         const int ci = g * kGroup + kc * 8 + j, co = c * NCH + row;
         float v = 0.f;
         if (ci < cin && co < cout) v = w[((int64_t)(dz * 9 + tap) * cin + ci) * cout + co];
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-        const int64_t tile = ((((int64_t)c * 3 + dz) * G + g) * 9 + tap) * (2 * per_tile);
+        const int64_t tile = ((((int64_t)c * ndz + dz) * G + g) * 9 + tap) * (2 * per_tile);
         const int64_t o = tile + ((int64_t)kc * NCH + row) * 8 + j;
         out[o] = __bfloat16_as_ushort(hi);
         out[o + per_tile] = __bfloat16_as_ushort(lo);
@@ -279,12 +289,13 @@ __global__ void pack_weights_ws_kernel(const float* __restrict__ w, uint16_t* __
 }
 
 struct Plan {
-    int cin_pad, cout_pad, G, NCH, nchunks, Wp, PP, T, L_alloc;
+    int cin_pad, cout_pad, G, NCH, nchunks, Wp, PP, T, L_alloc, ndz, Tg, ngroups;
     uint32_t slab_bytes, btile_bytes, smem_bytes;
 };
 
 static bool make_plan(const lf_conv_desc* d, Plan& pl) {
-    if (d->ndim != 3 || d->k != 3) return false;
+    if (d->k != 3 || !(d->ndim == 3 || (d->ndim == 2 && d->d == 1))) return false;
+    pl.ndz = d->ndim == 3 ? 3 : 1;
     if (d->precision != 1 && d->precision != 2) return false;
     if (d->n < 1 || d->d < 1 || d->h < 1 || d->w < 1 || d->cin < 1 || d->cout < 4 || (d->cout & 3)) return false;
     pl.cin_pad = (d->cin + kGroup - 1) / kGroup * kGroup;
@@ -298,14 +309,23 @@ static bool make_plan(const lf_conv_desc* d, Plan& pl) {
     if (pl.Wp >= 4096 || pl.PP >= (1 << 20)) return false;
     const int span = (d->h - 1) * pl.Wp + d->w;
     pl.T = (span + 127) / 128;
-    if (pl.T * pl.NCH > 512) return false;                          // all M-tiles of the plane live in TMEM
-    pl.L_alloc = (pl.T * 128 + 2 * pl.Wp + 2 + 7) / 8 * 8;
-    if ((uint32_t)pl.L_alloc * 16u >= (1u << 18)) return false;     // descriptor LBO field
-    pl.slab_bytes = 8u * pl.L_alloc * 16u;
     pl.btile_bytes = 2u * 4u * pl.NCH * 16u;
-    pl.smem_bytes = kAStages * pl.slab_bytes + kBRing * pl.btile_bytes + 8 * (2 * kAStages + 2 * kBRing + 2) + 16 + 4 * 128 + 64;
-    if (pl.smem_bytes > 227u * 1024u) return false;
-    if (((kAStages * pl.slab_bytes + kBRing * pl.btile_bytes) >> 4) >= (1u << 14)) return false;    // 14-bit start address
+    // M-tiles per item: as many as TMEM (512 columns) and shared memory (two slabs of Tg*128 + 2 rows of halo) allow;
+    // a larger plane is cut into tile groups, each of which streams the weights again
+    const uint32_t fixed = kBRing * pl.btile_bytes + 8 * (2 * kAStages + 2 * kBRing + 2) + 16 + 4 * 128 + 64;
+    pl.Tg = 0;
+    for (int tg = (512 / pl.NCH < pl.T ? 512 / pl.NCH : pl.T); tg >= 1; --tg) {
+        const int L = (tg * 128 + 2 * pl.Wp + 2 + 7) / 8 * 8;
+        if ((uint32_t)L * 16u >= (1u << 18)) continue;              // descriptor LBO field
+        const uint32_t slab = 8u * L * 16u;
+        if (kAStages * slab + fixed > 227u * 1024u) continue;
+        if (((kAStages * slab + kBRing * pl.btile_bytes) >> 4) >= (1u << 14)) continue;    // 14-bit start address
+        pl.Tg = tg; pl.L_alloc = L; pl.slab_bytes = slab; pl.smem_bytes = kAStages * slab + fixed;
+        break;
+    }
+    if (pl.Tg == 0) return false;
+    pl.ngroups = (pl.T + pl.Tg - 1) / pl.Tg;
+    if ((int64_t)d->n * d->d * pl.ngroups * pl.nchunks >= (1ll << 30)) return false;
     return true;
 }
 
@@ -320,19 +340,20 @@ extern "C" int lf_conv3d_ws_supported(const lf_conv_desc* desc) {
     return (desc != nullptr && ws::make_plan(desc, pl)) ? 1 : 0;
 }
 
-extern "C" int64_t lf_conv3d_ws_weight_bytes(int cin, int cout) {
-    if (cin <= 0 || cout <= 0) return 0;
+extern "C" int64_t lf_conv3d_ws_weight_bytes(int taps, int cin, int cout) {
+    if (cin <= 0 || cout <= 0 || (taps != 27 && taps != 9)) return 0;
     const int64_t cin_pad = (cin + 31) / 32 * 32, cout_pad = (cout + 63) / 64 * 64;
-    return 27 * cin_pad * cout_pad * 2 * 2;
+    return taps * cin_pad * cout_pad * 2 * 2;
 }
 
-extern "C" int lf_conv3d_ws_pack_weights(const float* w27, void* out, int cin, int cout, void* stream) {
-    LF_CHECK_ARG(w27 && out && cin > 0 && cout > 0, "conv3d_ws_pack_weights: bad arguments");
+// w: [27 | 9][Cin][Cout] fp32 (the packed-tap layout of lf_conv_fwd) -> the streamed tile order, bf16 hi | lo
+extern "C" int lf_conv3d_ws_pack_weights(const float* w, void* out, int taps, int cin, int cout, void* stream) {
+    LF_CHECK_ARG(w && out && cin > 0 && cout > 0 && (taps == 27 || taps == 9), "conv3d_ws_pack_weights: bad arguments");
     const int cin_pad = (cin + 31) / 32 * 32, cout_pad = (cout + 63) / 64 * 64;
     const int NCH = (cout_pad % 128 == 0) ? 128 : 64;
-    const int64_t total = 27ll * cin_pad * cout_pad;
+    const int64_t total = (int64_t)taps * cin_pad * cout_pad;
     ws::pack_weights_ws_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        w27, reinterpret_cast<uint16_t*>(out), cin, cout, cin_pad / 32, NCH, cout_pad / NCH);
+        w, reinterpret_cast<uint16_t*>(out), cin, cout, cin_pad / 32, NCH, cout_pad / NCH, taps / 9);
     LF_RETURN_LAUNCH();
 }
 
@@ -347,7 +368,7 @@ extern "C" int lf_conv3d_ws(const lf_conv_desc* desc, const void* x_split, const
                             float* y32, float* rnorm, float* scratch, void* stream) {
     ws::Plan pl;
     if (desc == nullptr || !ws::make_plan(desc, pl)) {
-        set_error("conv3d_ws: unsupported shape/precision (3-D k=3, plane tiles x channel chunk <= 512 TMEM columns)");
+        set_error("conv3d_ws: unsupported shape/precision (k=3, Cin padding to a multiple of 32, plane pitch that fits a slab)");
         return LF_EUNSUPPORTED;
     }
     LF_CHECK_ARG(x_split && w_packed && y32, "conv3d_ws: null pointer");
@@ -361,7 +382,8 @@ extern "C" int lf_conv3d_ws(const lf_conv_desc* desc, const void* x_split, const
     p.x_part = (int64_t)desc->n * desc->d * xin_pad * pl.PP;
     p.n = desc->n; p.d = desc->d; p.h = desc->h; p.w = desc->w; p.Wp = pl.Wp; p.PP = pl.PP;
     p.KCin = xin_pad / 8; p.G = pl.G; p.cout = desc->cout; p.NCH = pl.NCH; p.nchunks = pl.nchunks; p.T = pl.T;
-    p.L_alloc = pl.L_alloc; p.items = desc->n * desc->d * pl.nchunks; p.nprod = desc->precision == 1 ? 3 : 1;
+    p.L_alloc = pl.L_alloc; p.items = desc->n * desc->d * pl.ngroups * pl.nchunks; p.nprod = desc->precision == 1 ? 3 : 1;
+    p.ndz = pl.ndz; p.Tg = pl.Tg; p.ngroups = pl.ngroups;
     p.slab_bytes = pl.slab_bytes; p.btile_bytes = pl.btile_bytes;
     p.scale = desc->scale; p.slope = desc->slope; p.act = desc->act;
     p.magic_Wp = tcx::make_magic(pl.Wp);

@@ -378,8 +378,8 @@ def _ws_pack(wf, key):
     if hit is not None and hit[0]() is key[0]:
         return hit[1]
     taps, cin, cout = wf.shape
-    out = torch.empty(L.lib().lf_conv3d_ws_weight_bytes(cin, cout) // 2, device=wf.device, dtype=torch.int16)
-    _call('lf_conv3d_ws_pack_weights', L.lib().lf_conv3d_ws_pack_weights, (_p(wf), _p(out), cin, cout, _stream()))
+    out = torch.empty(L.lib().lf_conv3d_ws_weight_bytes(taps, cin, cout) // 2, device=wf.device, dtype=torch.int16)
+    _call('lf_conv3d_ws_pack_weights', L.lib().lf_conv3d_ws_pack_weights, (_p(wf), _p(out), taps, cin, cout, _stream()))
     _cache_put(_TC_PACK_CACHE, key[1:], (weakref.ref(key[0]), out), 256)
     return out
 
@@ -389,7 +389,8 @@ def _ws_ok(desc):
 
 
 def conv3d_ws(xs, wpk, bias, desc, name='lf_conv3d_ws'):
-    """wide 3x3x3 layer with streamed weights: SplitVol -> (dense fp32 channels-last, rnorm | None)"""
+    """wide 3x3x3 (or, with a one-plane volume and desc.ndim == 2, 3x3) layer with streamed weights:
+    SplitVol -> (dense fp32 channels-last [N,Cout,D,H,W], rnorm | None)"""
     lib = L.lib()
     dev = xs.buf.device
     y = empty_cl((xs.n, desc.cout, xs.d, xs.h, xs.w), dev)
@@ -398,7 +399,8 @@ def conv3d_ws(xs, wpk, bias, desc, name='lf_conv3d_ws'):
     scratch = torch.empty(lib.lf_conv3d_ws_scratch(ctypes.byref(desc)), device=dev, dtype=torch.float32) if desc.norm else None
     _call(name, lib.lf_conv3d_ws,
           (ctypes.byref(desc), _p(xs.buf), _p(wpk), _p(bias), _p(y), _p(rnorm), _p(scratch), _stream()),
-          kernels=2 if desc.norm else 1, nbytes=xs.buf.numel() * 2 + 4 * y.numel(), flops=2 * positions * 27 * xs.c * desc.cout)
+          kernels=2 if desc.norm else 1, nbytes=xs.buf.numel() * 2 + 4 * y.numel(),
+          flops=2 * positions * (27 if desc.ndim == 3 else 9) * xs.c * desc.cout)
     return y, rnorm
 
 
@@ -544,7 +546,8 @@ class _EqConv(torch.autograd.Function):
         desc = _desc(kind, nd, n, d, h, w, gcin, gcout, k, scale, act, slope, norm,
                      PRECISION_BF16X3 if precision == PRECISION_MIXED else precision)
         use_dz = kind == KIND_CONV and nd == 3 and k == 3 and _dz_ok(desc)
-        use_ws = (not use_dz) and kind == KIND_CONV and nd == 3 and k == 3 and _ws_ok(desc)      # wide layers
+        # wide layers: 3-D ones the depth-batched kernel cannot hold, 2-D ones the per-tap kernel cannot hold
+        use_ws = ((not use_dz) and kind == KIND_CONV and k == 3 and (nd == 3 or not _tc_ok(desc)) and _ws_ok(desc))
         y = None if (use_dz or use_ws) else empty_cl(out_shape, dev)
         rnorm = torch.empty(positions, device=dev, dtype=torch.float32) if (norm and not (use_dz or use_ws)) else None
         taps = wf.shape[0]
@@ -560,8 +563,10 @@ class _EqConv(torch.autograd.Function):
                                      want_dense=True, want_split=emit_split, name=_conv_name(kind, nd, k, 'fwd'))
             _EqConv.last_split = ys
         elif use_ws:
-            xs = x_split if x_split is not None else split_pack(x)
+            xs = x_split if x_split is not None else split_pack(x if nd == 3 else x.unsqueeze(2))
             y, rnorm = conv3d_ws(xs, _ws_pack(wf, wkey + ('wsf',)), bpk, desc, name=_conv_name(kind, nd, k, 'fwd'))
+            if nd == 2:
+                y = y.squeeze(2)
         else:
             if _tc_ok(desc):
                 wf_arg = _tc_pack(wf, wkey + ('f',))
@@ -682,10 +687,13 @@ class _EqConv(torch.autograd.Function):
                       kernels=1 if bkind == KIND_EXPAND else _tc_passes(bdesc),
                       nbytes=4 * (du.numel() + 2 * gx.numel()), flops=bflops)
                 rec_in.pre_applied = True
-            elif ctx.needs_input_grad[0] and kind == KIND_CONV and nd == 3 and k == 3 and _ws_ok(bdesc):
+            elif (ctx.needs_input_grad[0] and kind == KIND_CONV and k == 3 and (nd == 3 or not _tc_ok(bdesc))
+                  and _ws_ok(bdesc)):
                 # wide layer: bwd-data = the weight-streaming kernel on the flipped / transposed weights
-                gx, _ = conv3d_ws(split_pack(du), _ws_pack(wb, ctx.wkey + ('wsb',)), None, bdesc,
-                                  name=_conv_name(kind, nd, k, 'bwd_data'))
+                gx, _ = conv3d_ws(split_pack(du if nd == 3 else du.unsqueeze(2)), _ws_pack(wb, ctx.wkey + ('wsb',)), None,
+                                  bdesc, name=_conv_name(kind, nd, k, 'bwd_data'))
+                if nd == 2:
+                    gx = gx.squeeze(2)
             elif ctx.needs_input_grad[0]:
                 gx = torch.empty_like(x)
                 # bwd-data = the same implicit GEMM with flipped/transposed weights, no epilogue

@@ -220,3 +220,38 @@ def test_wide_conv_weight_streaming_vs_fp64(dev, shape, precision):
     torch.testing.assert_close(y.double(), ref, **tol)
     gerr = float((x.grad.double() - x64.grad).norm() / x64.grad.norm())
     assert gerr < (1e-4 if precision == 1 else 5e-2), f'd/dx relative L2 {gerr:.3g}'     # (plain bf16 operands, K up to 27*256)
+
+
+@pytest.mark.parametrize('shape', [(2, 512, 512, 8, 8), (1, 256, 512, 16, 16), (2, 128, 196, 64, 64), (1, 196, 128, 128, 128),
+                                   (3, 64, 128, 33, 17)])
+def test_wide_conv2d_weight_streaming_vs_fp64(dev, shape):
+    """the U-Nets' wide 3x3 layers (released widths: 128..512 channels on 4^2..128^2 maps) on the same kernel: one plane
+    per image, maps larger than one TMEM / shared-memory slab cut into tile groups.  The gradient is checked tightly
+    without the LeakyReLU (a pre-activation within fp32 rounding of zero takes the other branch than in fp64, and with
+    hundreds of channels per PixelNorm row one flip perturbs the whole row) and loosely with it."""
+    from latentfusion_b200 import ops
+    n, cin, cout, h, w = shape
+    torch.manual_seed(sum(shape))
+    wt = torch.randn(cout, cin, 3, 3, device=dev)
+    b = torch.randn(cout, device=dev) * 0.1
+    g = torch.randn(n, cout, h, w, device=dev)
+    he = math.sqrt(2.0 / (cin * 9))
+    for act, gtol in ((False, 1e-4), (True, 2e-2)):
+        x = torch.randn(n, cin, h, w, device=dev, requires_grad=True)
+        ops.KernelTrace.reset(True)
+        try:
+            y = ops.eq_conv(x, wt, b, act=act, norm=True, precision=1)
+            y.backward(g)
+            launched = {r[0] for r in ops.KernelTrace.records}
+        finally:
+            ops.KernelTrace.reset(False)
+        x64 = x.detach().double().requires_grad_(True)
+        u = F.conv2d(x64, wt.double(), None, padding=1) * he + b.double().view(1, -1, 1, 1)
+        if act:
+            u = F.leaky_relu(u, 0.2)
+        ref = u / torch.sqrt((u * u).mean(dim=1, keepdim=True) + 1e-8)
+        ref.backward(g.double())
+        torch.testing.assert_close(y.double(), ref, atol=2e-4, rtol=2e-3)
+        gerr = float((x.grad.double() - x64.grad).norm() / x64.grad.norm())
+        assert gerr < gtol, f'd/dx relative L2 {gerr:.3g} (act={act})'
+        assert 'lf_conv_fwd[conv2d_k3]' in launched and 'lf_conv_bwd_data[conv2d_k3]' in launched
