@@ -490,6 +490,7 @@ def mark_single_consumer(t):
 # row of y (32 lines per load instruction) and the epilogue becomes the critical stage.  Opt-in (LFB200_FUSE_EPI=1)
 # until the row is staged through shared memory.
 _FUSE_EPI = _os.environ.get('LFB200_FUSE_EPI', '0') == '1'
+_WS_2D = _os.environ.get('LFB200_WS_2D', '0') == '1'       # A/B: 2-D 3x3 layers on the weight-streaming kernel even when the per-tap one fits
 _DW_FFMA = _os.environ.get('LFB200_DW_FFMA', '0') == '1'     # A/B: weight gradients on the exact FFMA kernel
 
 
@@ -547,7 +548,7 @@ class _EqConv(torch.autograd.Function):
                      PRECISION_BF16X3 if precision == PRECISION_MIXED else precision)
         use_dz = kind == KIND_CONV and nd == 3 and k == 3 and _dz_ok(desc)
         # wide layers: 3-D ones the depth-batched kernel cannot hold, 2-D ones the per-tap kernel cannot hold
-        use_ws = ((not use_dz) and kind == KIND_CONV and k == 3 and (nd == 3 or not _tc_ok(desc)) and _ws_ok(desc))
+        use_ws = ((not use_dz) and kind == KIND_CONV and k == 3 and (nd == 3 or _WS_2D or not _tc_ok(desc)) and _ws_ok(desc))
         y = None if (use_dz or use_ws) else empty_cl(out_shape, dev)
         rnorm = torch.empty(positions, device=dev, dtype=torch.float32) if (norm and not (use_dz or use_ws)) else None
         taps = wf.shape[0]
@@ -687,7 +688,7 @@ class _EqConv(torch.autograd.Function):
                       kernels=1 if bkind == KIND_EXPAND else _tc_passes(bdesc),
                       nbytes=4 * (du.numel() + 2 * gx.numel()), flops=bflops)
                 rec_in.pre_applied = True
-            elif (ctx.needs_input_grad[0] and kind == KIND_CONV and k == 3 and (nd == 3 or not _tc_ok(bdesc))
+            elif (ctx.needs_input_grad[0] and kind == KIND_CONV and k == 3 and (nd == 3 or _WS_2D or not _tc_ok(bdesc))
                   and _ws_ok(bdesc)):
                 # wide layer: bwd-data = the weight-streaming kernel on the flipped / transposed weights
                 gx, _ = conv3d_ws(split_pack(du if nd == 3 else du.unsqueeze(2)), _ws_pack(wb, ctx.wkey + ('wsb',)), None,
