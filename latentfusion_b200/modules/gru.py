@@ -85,20 +85,46 @@ class ConvGRUCell(nn.Module):
 
     def _gate3(self, gate, x, h, term):
         """conv over [x | extra | h] with the extra part precomputed: x and h both have hidden-size channel groups"""
+        fan_in = int(math.prod(gate.module.weight.shape[1:]))
+        wx, wh = self._split_weights(gate, x.shape[1], h.shape[1])
+        return (ops.eq_conv(x, wx, gate.bias, precision=gate.precision, fan_in=fan_in)
+                + ops.eq_conv(h, wh, None, precision=gate.precision, fan_in=fan_in) + term)
+
+    def _split_weights(self, gate, cx, ch):
+        """(W[:, :cx], W[:, -ch:]) contiguous; cached while the weights are frozen (keeps their packed-weight entries)"""
         w = gate.module.weight
-        cx, ch = x.shape[1], h.shape[1]
-        fan_in = int(math.prod(w.shape[1:]))
         track = torch.is_grad_enabled() and w.requires_grad
         key, hit = (w._version, w.data_ptr(), cx, ch), self._parts_cache.get(('3', id(gate)))
         if not track and hit is not None and hit[0] == key:
-            wx, wh = hit[1], hit[2]
-        else:
-            wx, wh = w[:, :cx].contiguous(), w[:, w.shape[1] - ch:].contiguous()
-            if not track:       # frozen weights: keep the slices (and with them their packed-weight cache entries)
-                wx, wh = wx.detach(), wh.detach()
-                self._parts_cache[('3', id(gate))] = (key, wx, wh)
-        return (ops.eq_conv(x, wx, gate.bias, precision=gate.precision, fan_in=fan_in)
-                + ops.eq_conv(h, wh, None, precision=gate.precision, fan_in=fan_in) + term)
+            return hit[1], hit[2]
+        wx, wh = w[:, :cx].contiguous(), w[:, w.shape[1] - ch:].contiguous()
+        if not track:
+            wx, wh = wx.detach(), wh.detach()
+            self._parts_cache[('3', id(gate))] = (key, wx, wh)
+        return wx, wh
+
+    def input_terms(self, x_all, extra_terms, views):
+        """The input half of every step's gate pre-activations in ONE convolution per gate: the steps' inputs do not
+        depend on the recurrence, so conv(x_i, W[:, :C]) + bias + (constant extra term) is evaluated for all views at
+        once (a [B*views]-image batch fills the machine; the per-step convolutions see only the hidden state).
+        x_all [B, views, C, ...] -> three tensors [B, views, hidden, ...] (update, reset, out)."""
+        b, cx = x_all.shape[0], x_all.shape[2]
+        flat = x_all.reshape(b * views, *x_all.shape[2:])
+        out = []
+        for gate, term in zip((self.update_gate, self.reset_gate, self.out_gate), extra_terms):
+            wx, _ = self._split_weights(gate, cx, self.hidden_dim)
+            fan_in = int(math.prod(gate.module.weight.shape[1:]))
+            pre = ops.eq_conv(flat, wx, gate.bias, precision=gate.precision, fan_in=fan_in)
+            out.append(pre.view(b, views, *pre.shape[1:]) + term.unsqueeze(1))
+        return tuple(out)
+
+    def step_hidden(self, h_cur, pre_u, pre_r, pre_o, main_channels):
+        """one recurrence step given the input halves of the three gates: only conv(h, W[:, -hidden:]) remains"""
+        def hconv(gate, h):
+            _, wh = self._split_weights(gate, main_channels, self.hidden_dim)
+            return ops.eq_conv(h, wh, None, precision=gate.precision, fan_in=int(math.prod(gate.module.weight.shape[1:])))
+        update, h_reset = ops.gru_gates1(pre_u + hconv(self.update_gate, h_cur), pre_r + hconv(self.reset_gate, h_cur), h_cur)
+        return ops.gru_gates2(h_cur, update, pre_o + hconv(self.out_gate, h_reset))
 
     def forward(self, x, h_cur, extra=None):
         if extra is not None:           # (x: the main channels only; extra = extra_terms(...) of the remaining inputs)

@@ -127,10 +127,15 @@ class GRUFuser(_ParamFuser):
         coords = (utils.get_normalized_pixel_coords if self._planar else utils.get_normalized_voxel_coords)(seed)
         if not self._planar and self.in_channels % 4 == 0 and self.gru.splits_inputs(seed):
             # the coordinate channels are the same constant field at every step: convolve them once per gate
-            terms = self.gru.extra_terms(coords, self.in_channels)
+            views = z_obj.shape[1] - 1
+            if views == 0:
+                return seed.unsqueeze(1), {}
+            # ... and the view inputs do not depend on the recurrence: their half of every gate is one batched
+            # convolution per gate; the per-step convolutions only see the hidden state
+            pre_u, pre_r, pre_o = self.gru.input_terms(z_obj[:, 1:], self.gru.extra_terms(coords, self.in_channels), views)
             state = seed
-            for i in range(1, z_obj.shape[1]):
-                state = self.gru(z_obj[:, i], state, extra=terms)
+            for i in range(views):
+                state = self.gru.step_hidden(state, pre_u[:, i], pre_r[:, i], pre_o[:, i], self.in_channels)
             return state.unsqueeze(1), {}
         return _scan_views(z_obj, coords, self.gru, seed).unsqueeze(1), {}
 
