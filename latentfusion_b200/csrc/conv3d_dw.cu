@@ -18,10 +18,12 @@
 // and N with [du_hi(co) | du_lo(co)]: ONE M=128 MMA yields all four hi/lo products of up to four dx taps (the row
 // and column halves are added in the reduction; hi*hi + hi*lo + lo*hi + lo*lo is the exact product of the bf16x2
 // splits, fp32 accumulation in TMEM).  A CTA owns one dy tap (dyt = blockIdx % 3: the x run is offset by
-// (dyt-1) rows), all three dz (x plane e pairs with du planes e+1, e, e-1: a 4-slot ring of du planes) and a
-// strided set of (sample, 128-position chunk) columns that it marches through in depth; its 3*NM accumulators
-// (<= 384 TMEM columns) live across all its items and are written once, as per-CTA partials that a second kernel
-// sums in a fixed order (deterministic, no atomics).
+// (dyt-1) rows), all three dz (x plane e pairs with du planes e+1, e, e-1: a ring of du planes, 3 x stages) and a
+// strided set of (sample, 128-position chunk, depth segment) columns that it marches through in depth; its 3*NM
+// accumulators (<= 384 TMEM columns) live across all its items and are written once, as per-CTA partials that a second
+// kernel sums in a fixed order (deterministic, no atomics).  One MMA-issuer warp per dz (a warp sustains one tcgen05.mma
+// per ~120 cycles), one bulk copy per producer lane.  The same kernel takes 2-D 3x3 layers (one plane per image, the
+// centre dz only, up to 64 channels: the accumulator budget is then NM * N <= 512 columns).
 #include "tc_common.cuh"
 
 #include <cuda_bf16.h>
@@ -48,6 +50,7 @@ struct Params {
     int span, nchunks, items, G;   // interior positions per plane, 128-position chunks, (sample, chunk, depth segment) items, CTAs per dy tap
     int nseg, dseg;                // depth segments per column and planes per segment
     int two_d, dring;              // 2-D convolution (one plane per image, dz = 1 only); du ring slots in use
+    int x_kcs, x_kc0, dy_kcs, dy_kc0;   // 8-channel chunks per plane of the whole buffers, first chunk of this call's channel group
     int Lx;                        // positions per x region (allocated)
     uint32_t x_stage_bytes, dy_slot_bytes;
 };
@@ -120,15 +123,15 @@ conv3d_dw_kernel(const __grid_constant__ Params p) {
             if (x_lane) {
                 const int cp = lane / xg, g = lane - cp * xg;
                 const int part = g / p.KCi, kc = g - part * p.KCi;
-                x_off = part * p.x_part + ((((int64_t)n * p.d) * p.KCi + kc) * p.PP + q0 + (dyt - 1) * p.Wp - 1 + cp) * 8;
+                x_off = part * p.x_part + ((((int64_t)n * p.d) * p.x_kcs + p.x_kc0 + kc) * p.PP + q0 + (dyt - 1) * p.Wp - 1 + cp) * 8;
             }
             int64_t d_off = 0;
             if (d_lane) {
                 const int g = lane - 16;
                 const int part = g / p.KCo, kc = g - part * p.KCo;
-                d_off = part * p.dy_part + ((((int64_t)n * p.d) * p.KCo + kc) * p.PP + q0) * 8;
+                d_off = part * p.dy_part + ((((int64_t)n * p.d) * p.dy_kcs + p.dy_kc0 + kc) * p.PP + q0) * 8;
             }
-            const int64_t x_plane = (int64_t)p.KCi * p.PP * 8, d_plane = (int64_t)p.KCo * p.PP * 8;
+            const int64_t x_plane = (int64_t)p.x_kcs * p.PP * 8, d_plane = (int64_t)p.dy_kcs * p.PP * 8;
             auto load_dy = [&](int dpl) {
                 const uint32_t r = pc + (uint32_t)(dpl - dlo), sl = r % DR;
                 const uint16_t* dsrc = p.dy + d_off + dpl * d_plane;
@@ -258,7 +261,8 @@ conv3d_dw_kernel(const __grid_constant__ Params p) {
 
 // partials [G*3 ctas][3*NM][128][N] -> grad_w [27][cin][cout]: fixed summation order (CTA slot, then x part, then du part)
 __global__ void dw_reduce_kernel(const float* __restrict__ ws, float* __restrict__ gw, int G, int NM, int NCOPY, int R, int N,
-                                 int cin, int cout, int cin_pad, int cout_pad, int nparts, float scale, int two_d) {
+                                 int cin, int cout, int cin_pad, int cout_pad, int nparts, float scale, int two_d,
+                                 int cin_total, int cout_total, int ci_off, int co_off) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (two_d ? 9 : 27) * cin * cout) return;
     const int co = idx % cout, ci = (idx / cout) % cin, tap = idx / (cout * cin);
@@ -272,7 +276,8 @@ __global__ void dw_reduce_kernel(const float* __restrict__ ws, float* __restrict
             for (int py = 0; py < nparts; ++py)
                 s += base[(int64_t)(cp * R + px * cin_pad + ci) * N + py * cout_pad + co];
     }
-    gw[idx] = s * scale;        // du is the gradient of conv(x, W * he): d/dW carries the He constant
+    // du is the gradient of conv(x, W * he): d/dW carries the He constant
+    gw[((int64_t)tap * cin_total + ci_off + ci) * cout_total + co_off + co] = s * scale;
 }
 
 // bias gradient: per-channel sum of a split-planar volume (hi + lo), two fixed-order stages
@@ -370,35 +375,55 @@ static bool make_plan(const lf_conv_desc* d, Plan& pl) {
 
 using namespace lf;
 
+// Layers wider than one call's operand shapes are evaluated as channel-group pairs (32 input x 32 output channels per
+// call, each reading its chunks of the same split-planar buffers); `sub` is the descriptor of one pair.
+static bool plan_for(const lf_conv_desc* desc, dw::Plan& pl, lf_conv_desc& sub, int& gin, int& gout) {
+    if (desc == nullptr) return false;
+    sub = *desc; gin = gout = 1;
+    if (dw::make_plan(desc, pl)) return true;
+    if (desc->precision != 1 && desc->precision != 2) return false;
+    const int cin_pad = (desc->cin + 15) / 16 * 16, cout_pad = (desc->cout + 15) / 16 * 16;
+    // (a 16-channel tail group reads two chunks past its plane: finite data of the next plane, or the zero-filled stage
+    //  behind a copy clamped at the end of the buffer; those rows / columns of the accumulators are never read)
+    sub.cin = 32; sub.cout = 32;
+    if (!dw::make_plan(&sub, pl)) return false;
+    gin = (cin_pad + 31) / 32; gout = (cout_pad + 31) / 32;
+    return true;
+}
+
 extern "C" int lf_conv3d_dw_supported(const lf_conv_desc* desc) {
-    dw::Plan pl;
-    return (desc != nullptr && dw::make_plan(desc, pl)) ? 1 : 0;
+    dw::Plan pl; lf_conv_desc sub; int gi, go;
+    return plan_for(desc, pl, sub, gi, go) ? 1 : 0;
 }
 
 // workspace (floats): per-CTA partial accumulators + the bias column-sum partials
 extern "C" int64_t lf_conv3d_dw_ws(const lf_conv_desc* desc) {
-    dw::Plan pl;
-    if (desc == nullptr || !dw::make_plan(desc, pl)) return 0;
-    return (int64_t)pl.G * 3 * pl.nacc * 128 * pl.N + (int64_t)desc->n * desc->d * pl.cout_pad;
+    dw::Plan pl; lf_conv_desc sub; int gi, go;
+    if (!plan_for(desc, pl, sub, gi, go)) return 0;
+    const int cout_pad = (desc->cout + 15) / 16 * 16;
+    return (int64_t)pl.G * 3 * pl.nacc * 128 * pl.N + (int64_t)desc->n * desc->d * cout_pad;
 }
 
-// grad_w_packed [27][Cin][Cout] (overwritten) = desc->scale * sum x (.) du over all positions; grad_bias [Cout] (nullable) = sum du.
-// x_split / du_split: split-planar volumes of the forward input and of d(loss)/d(pre-activation output)
-// (precision 1: hi and lo parts; 2: hi parts only).  Reference: autograd of modules/equalized.py:57-64.
+// grad_w_packed [27 | 9][Cin][Cout] (overwritten) = desc->scale * sum x (.) du over all positions; grad_bias [Cout]
+// (nullable) = sum du.  x_split / du_split: split-planar volumes of the forward input and of
+// d(loss)/d(pre-activation output) (precision 1: hi and lo parts; 2: hi parts only).
+// Reference: autograd of modules/equalized.py:57-64.
 extern "C" int lf_conv3d_dw(const lf_conv_desc* desc, const void* x_split, const void* du_split, float* ws,
                             float* grad_w_packed, float* grad_bias, void* stream) {
-    dw::Plan pl;
-    if (desc == nullptr || !dw::make_plan(desc, pl)) {
-        set_error("conv3d_dw: unsupported shape/precision (k=3; 3-D: parts*Cin_pad in {32, 64}, parts*Cout_pad <= 64; 2-D: <= 128)");
+    dw::Plan pl; lf_conv_desc sub; int gin, gout;
+    if (!plan_for(desc, pl, sub, gin, gout)) {
+        set_error("conv3d_dw: unsupported shape/precision (k=3; one call: parts*Cin_pad in {32, 64[, 128 in 2-D]}; wider "
+                  "layers: 32x32 channel-group pairs)");
         return LF_EUNSUPPORTED;
     }
     LF_CHECK_ARG(x_split && du_split && ws && grad_w_packed, "conv3d_dw: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    const int cin_pad = (desc->cin + 15) / 16 * 16, cout_pad = (desc->cout + 15) / 16 * 16;
     dw::Params p;
     p.x = reinterpret_cast<const uint16_t*>(x_split);
     p.dy = reinterpret_cast<const uint16_t*>(du_split);
-    p.x_part = (int64_t)desc->n * desc->d * pl.cin_pad * pl.PP;
-    p.dy_part = (int64_t)desc->n * desc->d * pl.cout_pad * pl.PP;
+    p.x_part = (int64_t)desc->n * desc->d * cin_pad * pl.PP;
+    p.dy_part = (int64_t)desc->n * desc->d * cout_pad * pl.PP;
     p.x_end = p.x + 2 * p.x_part;            // the buffers always hold both parts (lf_split_bytes)
     p.dy_end = p.dy + 2 * p.dy_part;
     p.ws = ws;
@@ -406,18 +431,30 @@ extern "C" int lf_conv3d_dw(const lf_conv_desc* desc, const void* x_split, const
     p.NCOPY = pl.NCOPY; p.NM = pl.NM; p.R = pl.R; p.N = pl.N;
     p.span = pl.span; p.nchunks = pl.nchunks; p.items = pl.items; p.G = pl.G; p.Lx = pl.Lx;
     p.nseg = pl.nseg; p.dseg = pl.dseg; p.two_d = pl.two_d; p.dring = pl.dring;
+    p.x_kcs = cin_pad / 8; p.dy_kcs = cout_pad / 8;
     p.x_stage_bytes = pl.x_stage_bytes; p.dy_slot_bytes = pl.dy_slot_bytes;
     cudaError_t e = cudaFuncSetAttribute(dw::conv3d_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) { set_error("conv3d_dw: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return (int)e; }
-    dw::conv3d_dw_kernel<<<pl.G * 3, dw::kThreads, pl.smem_bytes, st>>>(p);
-    const int total = (pl.two_d ? 9 : 27) * desc->cin * desc->cout;
-    dw::dw_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(ws, grad_w_packed, pl.G, pl.NM, pl.NCOPY, pl.R, pl.N, desc->cin,
-                                                              desc->cout, pl.cin_pad, pl.cout_pad, pl.nparts, desc->scale, pl.two_d);
+    for (int gi = 0; gi < gin; ++gi)
+        for (int go = 0; go < gout; ++go) {
+            const int ci_off = gi * 32, co_off = go * 32;
+            const int cin_g = gin == 1 ? desc->cin : (desc->cin - ci_off < 32 ? desc->cin - ci_off : 32);
+            const int cout_g = gout == 1 ? desc->cout : (desc->cout - co_off < 32 ? desc->cout - co_off : 32);
+            if (cin_g <= 0 || cout_g <= 0) continue;
+            p.x_kc0 = gin == 1 ? 0 : gi * 4;
+            p.dy_kc0 = gout == 1 ? 0 : go * 4;
+            dw::conv3d_dw_kernel<<<pl.G * 3, dw::kThreads, pl.smem_bytes, st>>>(p);
+            const int total = (pl.two_d ? 9 : 27) * cin_g * cout_g;
+            dw::dw_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(ws, grad_w_packed, pl.G, pl.NM, pl.NCOPY, pl.R, pl.N, cin_g,
+                                                                      cout_g, pl.cin_pad, pl.cout_pad, pl.nparts, desc->scale,
+                                                                      pl.two_d, desc->cin, desc->cout, gin == 1 ? 0 : ci_off,
+                                                                      gout == 1 ? 0 : co_off);
+        }
     if (grad_bias != nullptr) {
         float* partial = ws + (int64_t)pl.G * 3 * pl.nacc * 128 * pl.N;
         const int planes = desc->n * desc->d;
-        dw::split_colsum_kernel<<<planes, 256, 0, st>>>(p.dy, p.dy_part, pl.nparts, pl.KCo, pl.PP, partial);
-        dw::colsum_finish_kernel<<<(desc->cout + 63) / 64, 64, 0, st>>>(partial, planes, pl.cout_pad, desc->cout, grad_bias);
+        dw::split_colsum_kernel<<<planes, 256, 0, st>>>(p.dy, p.dy_part, pl.nparts, cout_pad / 8, pl.PP, partial);
+        dw::colsum_finish_kernel<<<(desc->cout + 63) / 64, 64, 0, st>>>(partial, planes, cout_pad, desc->cout, grad_bias);
     }
     LF_RETURN_LAUNCH();
 }

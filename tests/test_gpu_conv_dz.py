@@ -141,7 +141,8 @@ def test_block_forward_backward_through_dz_path(dev, c, size, train):
 @pytest.mark.gpu
 @pytest.mark.parametrize('shape', [(2, 32, 32, 16, 16, 16, 1), (1, 8, 8, 10, 12, 14, 1), (3, 32, 16, 5, 20, 9, 1),
                                    (2, 32, 32, 12, 16, 16, 2), (1, 16, 32, 1, 24, 24, 1), (2, 12, 20, 7, 33, 17, 1),
-                                   (1, 16, 16, 6, 7, 8, 1)])      # (narrow plane: the rounded-up run ends past the buffer)
+                                   (1, 16, 16, 6, 7, 8, 1),      # (narrow plane: the rounded-up run ends past the buffer)
+                                   (1, 64, 96, 4, 16, 16, 1), (1, 128, 60, 3, 12, 14, 1)])   # wide: 32x32 channel-group pairs
 def test_conv3d_weight_gradient_on_tensor_cores_vs_fp64(shape):
     """lf_conv3d_dw (MN-major tcgen05 over the split-planar twins) against autograd of F.conv3d in fp64: weight gradient
     [27][Cin][Cout] and bias gradient; precision 1 = all four bf16x2 split products (fp32-grade), 2 = bf16 operands."""
@@ -168,7 +169,7 @@ def test_conv3d_weight_gradient_on_tensor_cores_vs_fp64(shape):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize('shape', [(3, 32, 64, 24, 20, 1), (2, 64, 64, 16, 16, 1), (4, 4, 32, 33, 17, 1), (2, 64, 32, 12, 12, 1),
-                                   (2, 32, 32, 16, 16, 2)])
+                                   (2, 32, 32, 16, 16, 2), (2, 256, 128, 16, 16, 1), (1, 128, 196, 24, 20, 1)])
 def test_conv2d_weight_gradient_on_tensor_cores_vs_fp64(shape):
     """the same kernel on 2-D maps (the U-Nets' 3x3 convolutions): one plane per image, centre dz only, up to 64 channels"""
     import torch.nn.functional as F
@@ -199,7 +200,7 @@ def test_wide_conv_weight_streaming_vs_fp64(dev, shape, precision):
     n, cin, cout, d, h, w = shape
     torch.manual_seed(sum(shape))
     x = torch.randn(n, cin, d, h, w, device=dev, requires_grad=True)
-    wt = torch.randn(cout, cin, 3, 3, 3, device=dev)
+    wt = torch.randn(cout, cin, 3, 3, 3, device=dev, requires_grad=True)
     b = torch.randn(cout, device=dev) * 0.1
     g = torch.randn(n, cout, d, h, w, device=dev)
     ops.KernelTrace.reset(True)
@@ -209,10 +210,12 @@ def test_wide_conv_weight_streaming_vs_fp64(dev, shape, precision):
         names = [r[0] for r in ops.KernelTrace.records]
     finally:
         ops.KernelTrace.reset(False)
-    assert 'lf_conv_bwd_weight' not in names and names.count('lf_conv_fwd[conv3d_k3]') == 1, names
+    # forward, bwd-data and (channel-group pairs of) the weight gradient all on the tensor cores
+    assert 'lf_conv_bwd_weight' not in names and 'lf_conv3d_dw' in names and names.count('lf_conv_fwd[conv3d_k3]') == 1, names
     x64 = x.detach().double().requires_grad_(True)
+    w64 = wt.detach().double().requires_grad_(True)
     he = math.sqrt(2.0 / (cin * 27))
-    u = F.conv3d(x64, wt.double(), None, padding=1) * he + b.double().view(1, -1, 1, 1, 1)
+    u = F.conv3d(x64, w64, None, padding=1) * he + b.double().view(1, -1, 1, 1, 1)
     u = F.leaky_relu(u, 0.2)
     ref = u / torch.sqrt((u * u).mean(dim=1, keepdim=True) + 1e-8)
     ref.backward(g.double())
@@ -220,6 +223,8 @@ def test_wide_conv_weight_streaming_vs_fp64(dev, shape, precision):
     torch.testing.assert_close(y.double(), ref, **tol)
     gerr = float((x.grad.double() - x64.grad).norm() / x64.grad.norm())
     assert gerr < (1e-4 if precision == 1 else 5e-2), f'd/dx relative L2 {gerr:.3g}'     # (plain bf16 operands, K up to 27*256)
+    werr = float((wt.grad.double() - w64.grad).norm() / w64.grad.norm())
+    assert werr < (1e-4 if precision == 1 else 5e-2), f'd/dW relative L2 {werr:.3g}'
 
 
 @pytest.mark.parametrize('shape', [(2, 512, 512, 8, 8), (1, 256, 512, 16, 16), (2, 128, 196, 64, 64), (1, 196, 128, 128, 128),
