@@ -255,8 +255,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        os.environ.setdefault('NCCL_DEBUG', 'WARN')
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # NCCL's version banner must not land on stdout (one JSON line only)
+        os.environ.setdefault('NCCL_DEBUG', 'WARN')      # (NCCL's one-line version banner precedes the JSON line on stdout, as in round 1)
         dist.init_process_group('nccl', device_id=dev)
     ops.set_default_precision(args.precision)
 
