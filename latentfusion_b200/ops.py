@@ -499,6 +499,7 @@ class _EqConv(torch.autograd.Function):
     Reference: modules/equalized.py:57-64 + blocks.py:152-158 + modules/__init__.py:14-15."""
     last_rec = None        # _ActRec of the most recent forward, picked up by eq_conv() to tag the returned tensor
     last_split = None      # split-planar twin of the most recent forward's output (when asked for), tagged likewise
+    last_in_split = None   # split-planar twin of the most recent forward's INPUT when it had to be packed here
 
     @staticmethod
     def forward(ctx, x, weight, bias, kind, depth, act, slope, norm, precision, fan_in=None, rec_in=None,
@@ -559,6 +560,7 @@ class _EqConv(torch.autograd.Function):
             # depth-batched tcgen05 kernel on split-planar activations (one launch for bf16x3); the producer may have
             # left the split-planar form of x next to it (x_split), otherwise it is packed here
             xs = x_split if x_split is not None else split_pack(x)
+            _EqConv.last_in_split = xs if x_split is None else None
             ctx.xs = xs if rec_in is not None else None      # the producer layer's output, for the fused backward epilogue
             y, ys, rnorm = conv3d_dz(xs, _dz_pack(wf, wkey + ('dzf',)), bpk, gcout, scale, act, slope, norm, desc.precision,
                                      want_dense=True, want_split=emit_split, name=_conv_name(kind, nd, k, 'fwd'))
@@ -739,8 +741,18 @@ def eq_conv(x, weight, bias, act=False, slope=0.2, norm=False, kind=KIND_CONV, d
     rec_in = None
     if getattr(x, '_lf_single_use', False) and torch.is_grad_enabled() and (_FUSE_EPI or _dz_shape(x, weight, kind, precision)):
         rec_in = getattr(x, '_lf_actnorm', None)
+    x_split = getattr(x, '_lf_split', None)
+    if x_split is None:
+        # inference: a tensor that was packed for one convolution keeps its twin for the next convolution that reads it
+        # (the GRU's hidden state feeds two gates); dropped as soon as the tensor is written to
+        cached = getattr(x, '_lf_split_cache', None)
+        if cached is not None and cached[0] == x._version:
+            x_split = cached[1]
     y = _EqConv.apply(x, weight, bias, kind, depth, bool(act), float(slope), bool(norm), int(precision), fan_in, rec_in,
-                      getattr(x, '_lf_split', None), bool(emit_split))
+                      x_split, bool(emit_split))
+    if _EqConv.last_in_split is not None and not torch.is_grad_enabled():
+        x._lf_split_cache = (x._version, _EqConv.last_in_split)
+    _EqConv.last_in_split = None
     if y.requires_grad and _EqConv.last_rec is not None:
         y._lf_actnorm = _EqConv.last_rec        # lets a single downstream lfb200 conv fuse this layer's backward
     if _EqConv.last_split is not None:
