@@ -268,6 +268,19 @@ int64_t lf_conv3d_ws_scratch(const lf_conv_desc* desc);
 int lf_conv3d_ws(const lf_conv_desc* desc, const void* x_split, const void* w_packed, const float* bias, float* y32,
                  float* rnorm, float* scratch, void* stream);
 
+/* ---- backward of the depth collapse fused with the producer's activation backward (csrc/expand_tc.cu) ----
+ * Replaces, in the pose loop, the autograd of FactorProjection3d2d (modules/geometry.py:704-749) w.r.t. its input volume
+ * followed by the PixelNorm/LeakyReLU backward of the camera block that produced it (blocks.py:152-164):
+ *   du_prev = actnorm_bwd(he * du x W^T, y_prev, rnorm_prev), written in split-planar form (dense fp32 too if asked).
+ * collapse_desc: the FORWARD collapse descriptor (ndim 1: cin = volume channels <= 32, cout = projected channels <= 64,
+ * d = k = depth), precision 1 | 2.  du_split2d: split-planar twin of the 2-D gradient as a one-plane volume. */
+int lf_expand_tc_supported(const lf_conv_desc* collapse_desc);
+int64_t lf_expand_tc_weight_bytes(int depth, int cin, int cout);
+int lf_expand_tc_pack_weights(const float* w /* [depth][cin][cout] */, void* out, int depth, int cin, int cout, void* stream);
+int lf_expand_tc_bwd_epi(const lf_conv_desc* collapse_desc, const void* du_split2d, const void* w_packed,
+                         const void* y_prev_split, const float* rnorm_prev, int prev_act, float prev_slope, int prev_norm,
+                         void* du_prev_split, float* du_prev32 /* nullable */, void* stream);
+
 /* ---- weight gradient of the 3x3x3 convolution on the tensor cores (csrc/conv3d_dw.cu) ----
  * Replaces the autograd of modules/equalized.py:57-64 w.r.t. the weight inside ReconTrainer.run_iteration
  * (tools/train/train_reconstruct.py:523-534).  x_split / du_split: split-planar volumes (layout above) of the forward

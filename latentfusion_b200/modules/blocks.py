@@ -2,6 +2,7 @@
 ``latentfusion/modules/blocks.py`` (create_blocks :10-75, InputBlock :78-90, OutputBlock :107-119,
 Block :136-164).  A Block here is two fused kernels (+ one for the optional resize) instead of the
 reference's ~14 elementwise passes."""
+import torch
 from torch import nn
 
 from . import Interpolate, PixelNorm, EqualizedConv2d, EqualizedConv3d
@@ -100,7 +101,11 @@ class Block(nn.Module):
         # (3-D: conv1's epilogue also leaves the split-planar form conv2's TMA staging reads)
         x = self.conv1(x, act=True, slope=slope, norm=True, emit_split=isinstance(self.conv1, EqualizedConv3d))
         # conv2 is the only consumer of conv1's output: its bwd-data kernel can apply conv1's activation/norm backward
-        x = self.conv2(ops.mark_single_consumer(x), act=True, slope=slope, norm=True)
+        # (emit_out_split: the consumer of this block — the Photographer's depth collapse — reads conv2's activation
+        #  backward inputs from the split-planar twin in its fused backward kernel)
+        x = self.conv2(ops.mark_single_consumer(x), act=True, slope=slope, norm=True,
+                       emit_split=(getattr(self, 'emit_out_split', False) and self.interpolate is None
+                                   and torch.is_grad_enabled()))
         if self.interpolate is not None:
             x = self.interpolate(x)
         return x

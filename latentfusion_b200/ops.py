@@ -384,6 +384,22 @@ def _ws_pack(wf, key):
     return out
 
 
+def _ex_ok(desc):
+    return desc.precision in (1, 2) and bool(L.lib().lf_expand_tc_supported(ctypes.byref(desc)))
+
+
+def _ex_pack(wf, key):
+    """collapse weights [depth][Cin][Cout] fp32 -> the fused collapse-backward kernel's tile order (cached)"""
+    hit = _TC_PACK_CACHE.get(key[1:])
+    if hit is not None and hit[0]() is key[0]:
+        return hit[1]
+    depth, cin, cout = wf.shape
+    out = torch.empty(L.lib().lf_expand_tc_weight_bytes(depth, cin, cout) // 2, device=wf.device, dtype=torch.int16)
+    _call('lf_expand_tc_pack_weights', L.lib().lf_expand_tc_pack_weights, (_p(wf), _p(out), depth, cin, cout, _stream()))
+    _cache_put(_TC_PACK_CACHE, key[1:], (weakref.ref(key[0]), out), 256)
+    return out
+
+
 def _ws_ok(desc):
     return desc.precision in (1, 2) and bool(L.lib().lf_conv3d_ws_supported(ctypes.byref(desc)))
 
@@ -471,12 +487,13 @@ class _ActRec:
     consumer of that output is another lfb200 convolution (Block: conv1 -> conv2; Photographer: camera block ->
     depth collapse), the consumer's bwd-data kernel applies this layer's activation/norm backward in its epilogue
     (lf_conv_bwd_data_epi) and sets `pre_applied`, and this layer's own backward then skips lf_actnorm_bwd."""
-    __slots__ = ('shape', 'rnorm', 'act', 'slope', 'norm', 'pre_applied')
+    __slots__ = ('shape', 'rnorm', 'act', 'slope', 'norm', 'pre_applied', 'train')
 
     # (holds the norms but NOT the output tensor: the consumer has that tensor saved as its own input, and a
     # reference from here would make an output <-> record cycle that only the garbage collector could free)
     def __init__(self, shape, rnorm, act, slope, norm):
         self.shape, self.rnorm, self.act, self.slope, self.norm, self.pre_applied = shape, rnorm, act, slope, norm, False
+        self.train = False      # the layer's weights take gradients (a consumer that fuses this layer's backward then also writes dense du)
 
 
 def mark_single_consumer(t):
@@ -490,6 +507,7 @@ def mark_single_consumer(t):
 # row of y (32 lines per load instruction) and the epilogue becomes the critical stage.  Opt-in (LFB200_FUSE_EPI=1)
 # until the row is staged through shared memory.
 _FUSE_EPI = _os.environ.get('LFB200_FUSE_EPI', '0') == '1'
+_EX_OFF = _os.environ.get('LFB200_EX_OFF', '0') == '1'      # A/B: depth-collapse backward on the FFMA expand kernel + lf_actnorm_bwd_split
 _WS_2D = _os.environ.get('LFB200_WS_2D', '0') == '1'       # A/B: 2-D 3x3 layers on the weight-streaming kernel even when the per-tap one fits
 _DW_FFMA = _os.environ.get('LFB200_DW_FFMA', '0') == '1'     # A/B: weight gradients on the exact FFMA kernel
 
@@ -556,6 +574,8 @@ class _EqConv(torch.autograd.Function):
         wkey = (weight, id(weight), weight._version, kind)
         _EqConv.last_split = None
         ctx.xs = None
+        if kind == KIND_COLLAPSE and rec_in is not None:
+            ctx.xs = x_split                                  # the producer's output twin, for the fused backward
         if use_dz:
             # depth-batched tcgen05 kernel on split-planar activations (one launch for bf16x3); the producer may have
             # left the split-planar form of x next to it (x_split), otherwise it is packed here
@@ -584,6 +604,8 @@ class _EqConv(torch.autograd.Function):
         ctx.wkey = wkey
         ctx.rec_in = rec_in
         ctx.rec_out = _ActRec(tuple(y.shape), rnorm, act, slope, norm) if ((act or norm) and kind != KIND_EXPAND) else None
+        if ctx.rec_out is not None:
+            ctx.rec_out.train = bool(weight.requires_grad)
         _EqConv.last_rec = ctx.rec_out
         ctx.cfg = (kind, depth, act, slope, norm, precision, nd, n, d, h, w, gcin, gcout, k, scale,
                    tuple(weight.shape), bias is not None)
@@ -680,7 +702,24 @@ class _EqConv(torch.autograd.Function):
                       nbytes=4 * 3 * gy.numel())
             else:
                 du = gy
-            if epi:
+            use_ex = (kind == KIND_COLLAPSE and rec_in is not None and ctx.xs is not None and ctx.needs_input_grad[0]
+                      and rec_in.shape == tuple(x.shape) and not _EX_OFF)
+            if use_ex:
+                fdesc = _desc(KIND_COLLAPSE, 3, n, d, h, w, cin, cout, d, scale, 0, 0.0, 0, 1 if precision == 3 else precision)
+                use_ex = _ex_ok(fdesc)
+            if use_ex:
+                # tensor-core depth expand + the producer layer's PixelNorm/LeakyReLU backward, straight to split-planar du
+                wf_c, _ = _pack_weight_cached(ctx.wkey[0], kind, depth)
+                du2s = split_pack(du.unsqueeze(2))
+                gx = torch.empty_like(x)                      # dense only when the producer's weights train
+                gxs = SplitVol.empty(n, cin, d, h, w, x.device)
+                _call(_conv_name(kind, nd, k, 'bwd_data'), lib.lf_expand_tc_bwd_epi,
+                      (ctypes.byref(fdesc), _p(du2s.buf), _p(_ex_pack(wf_c, ctx.wkey + ('ex',))), _p(ctx.xs.buf), _p(rec_in.rnorm),
+                       int(rec_in.act), float(rec_in.slope), int(rec_in.norm), _p(gxs.buf), _p(gx if rec_in.train else None),
+                       _stream()), nbytes=2 * (ctx.xs.buf.numel() + gxs.buf.numel()), flops=bflops)
+                rec_in.pre_applied = True
+                _put_grad_split(gx, gxs)
+            elif epi:
                 # bwd-data + the producer layer's PixelNorm/LeakyReLU backward in one kernel: returns du of that layer
                 gx = torch.empty_like(x)
                 w_arg = wb if bkind == KIND_EXPAND else _tc_pack(wb, ctx.wkey + ('b',))
@@ -731,6 +770,14 @@ class _EqConv(torch.autograd.Function):
         return gx, gw, gb, None, None, None, None, None, None, None, None, None, None
 
 
+def _ex_shape(x, weight, kind, depth, precision):
+    """would the backward of this depth collapse run on the fused tcgen05 kernel (needs the producer's split-planar twin)?"""
+    if kind != KIND_COLLAPSE or _EX_OFF or x.dim() != 5 or precision not in (1, 2, 3) or getattr(x, '_lf_split', None) is None:
+        return False
+    n, cin, d, h, w = x.shape
+    return _ex_ok(_desc(KIND_COLLAPSE, 3, n, d, h, w, cin, weight.shape[0], d, 1.0, False, 0.0, False, 1 if precision == 3 else precision))
+
+
 def eq_conv(x, weight, bias, act=False, slope=0.2, norm=False, kind=KIND_CONV, depth=0, precision=None, fan_in=None,
             emit_split=False):
     """emit_split: also leave the split-planar twin of the output on the returned tensor (`_lf_split`), for a following
@@ -739,7 +786,8 @@ def eq_conv(x, weight, bias, act=False, slope=0.2, norm=False, kind=KIND_CONV, d
     if precision is None:
         precision = _default_precision
     rec_in = None
-    if getattr(x, '_lf_single_use', False) and torch.is_grad_enabled() and (_FUSE_EPI or _dz_shape(x, weight, kind, precision)):
+    if getattr(x, '_lf_single_use', False) and torch.is_grad_enabled() and (
+            _FUSE_EPI or _dz_shape(x, weight, kind, precision) or _ex_shape(x, weight, kind, depth, precision)):
         rec_in = getattr(x, '_lf_actnorm', None)
     x_split = getattr(x, '_lf_split', None)
     if x_split is None:

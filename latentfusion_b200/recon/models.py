@@ -200,6 +200,8 @@ class Photographer(_Checkpointable, nn.Module):
         self.occlusion_module = unet.UNet3d(object_config[-1] + 1, 1, occlusion_config) if occlusion_config else None
         self.camera_blocks = create_blocks(camera_config, skip_connect_start=True, skip_connection_views=in_views,
                                            **blocks3d)
+        if projection_type == 'factor' and len(self.camera_blocks) and not occlusion_config:
+            self.camera_blocks[-1].emit_out_split = True        # see Block.forward / ops._EqConv (fused collapse backward)
         self.projection_block = (FactorProjection3d2d(camera_config[-1], image_config[0][0],
                                                       out_size=self.camera_out_size)
                                  if projection_type == 'factor' else None)
