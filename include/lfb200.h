@@ -268,6 +268,16 @@ int64_t lf_conv3d_ws_scratch(const lf_conv_desc* desc);
 int lf_conv3d_ws(const lf_conv_desc* desc, const void* x_split, const void* w_packed, const float* bias, float* y32,
                  float* rnorm, float* scratch, void* stream);
 
+/* ---- depth collapse on the tensor cores (csrc/collapse_tc.cu) ----
+ * Same reference op as lf_conv_fwd with ndim = 1 (FactorProjection3d2d + LeakyReLU + PixelNorm), reading the volume from
+ * the split-planar twin its producer left (x_split) instead of the dense fp32 tensor: HBM-bound instead of FFMA-bound.
+ * Cin <= 32, Cout <= 32 (multiple of 4), precision 1 | 2; y fp32 channels-last [N][H][W][Cout], rnorm nullable. */
+int lf_collapse_tc_supported(const lf_conv_desc* desc);
+int64_t lf_collapse_tc_weight_bytes(int depth, int cin, int cout);
+int lf_collapse_tc_pack_weights(const float* w /* [depth][cin][cout] */, void* out, int depth, int cin, int cout, void* stream);
+int lf_collapse_tc(const lf_conv_desc* desc, const void* x_split, const void* w_packed, const float* bias, float* y,
+                   float* rnorm, void* stream);
+
 /* ---- backward of the depth collapse fused with the producer's activation backward (csrc/expand_tc.cu) ----
  * Replaces, in the pose loop, the autograd of FactorProjection3d2d (modules/geometry.py:704-749) w.r.t. its input volume
  * followed by the PixelNorm/LeakyReLU backward of the camera block that produced it (blocks.py:152-164):

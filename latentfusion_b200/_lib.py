@@ -68,6 +68,10 @@ _SIGNATURES = {
     'lf_expand_tc_weight_bytes': (c_i64, [c_int, c_int, c_int]),
     'lf_expand_tc_pack_weights': (c_int, [c_f32p, c_vp, c_int, c_int, c_int, c_vp]),
     'lf_expand_tc_bwd_epi': (c_int, [ctypes.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_f32p, c_int, c_float, c_int, c_vp, c_f32p, c_vp]),
+    'lf_collapse_tc_supported': (c_int, [ctypes.POINTER(ConvDesc)]),
+    'lf_collapse_tc_weight_bytes': (c_i64, [c_int, c_int, c_int]),
+    'lf_collapse_tc_pack_weights': (c_int, [c_f32p, c_vp, c_int, c_int, c_int, c_vp]),
+    'lf_collapse_tc': (c_int, [ctypes.POINTER(ConvDesc), c_vp, c_vp, c_f32p, c_f32p, c_f32p, c_vp]),
     'lf_set_option': (c_int, [ctypes.c_char_p, c_int]),
     'lf_conv3d_dw_supported': (c_int, [ctypes.POINTER(ConvDesc)]),
     'lf_conv3d_dw_ws': (c_i64, [ctypes.POINTER(ConvDesc)]),

@@ -384,6 +384,18 @@ def _ws_pack(wf, key):
     return out
 
 
+def _ct_pack(wf, key):
+    """collapse weights [depth][Cin][Cout] fp32 -> the tensor-core collapse kernel's per-plane tiles (cached)"""
+    hit = _TC_PACK_CACHE.get(key[1:])
+    if hit is not None and hit[0]() is key[0]:
+        return hit[1]
+    depth, cin, cout = wf.shape
+    out = torch.empty(L.lib().lf_collapse_tc_weight_bytes(depth, cin, cout) // 2, device=wf.device, dtype=torch.int16)
+    _call('lf_collapse_tc_pack_weights', L.lib().lf_collapse_tc_pack_weights, (_p(wf), _p(out), depth, cin, cout, _stream()))
+    _cache_put(_TC_PACK_CACHE, key[1:], (weakref.ref(key[0]), out), 256)
+    return out
+
+
 def _ex_ok(desc):
     return desc.precision in (1, 2) and bool(L.lib().lf_expand_tc_supported(ctypes.byref(desc)))
 
@@ -585,6 +597,12 @@ class _EqConv(torch.autograd.Function):
             y, ys, rnorm = conv3d_dz(xs, _dz_pack(wf, wkey + ('dzf',)), bpk, gcout, scale, act, slope, norm, desc.precision,
                                      want_dense=True, want_split=emit_split, name=_conv_name(kind, nd, k, 'fwd'))
             _EqConv.last_split = ys
+        elif (kind == KIND_COLLAPSE and x_split is not None and not _EX_OFF and desc.precision in (1, 2)
+              and L.lib().lf_collapse_tc_supported(ctypes.byref(desc))):
+            # the producer left the split-planar twin of the volume: HBM-bound tensor-core collapse (csrc/collapse_tc.cu)
+            _call(_conv_name(kind, nd, k, 'fwd'), L.lib().lf_collapse_tc,
+                  (ctypes.byref(desc), _p(x_split.buf), _p(_ct_pack(wf, wkey + ('ct',))), _p(bpk), _p(y), _p(rnorm), _stream()),
+                  nbytes=2 * x_split.buf.numel() + 4 * y.numel(), flops=2 * positions * taps * gcin * gcout)
         elif use_ws:
             xs = x_split if x_split is not None else split_pack(x if nd == 3 else x.unsqueeze(2))
             y, rnorm = conv3d_ws(xs, _ws_pack(wf, wkey + ('wsf',)), bpk, desc, name=_conv_name(kind, nd, k, 'fwd'))
