@@ -545,7 +545,7 @@ def search_block(args, dev, rank, world, barrier, max_over_ranks, S4=128, C4=16,
     mask = (torch.rand(1, V, 1, P, P, generator=g) > 0.3).float()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     recon = []
-    for _ in range(2):
+    for _ in range(3):                      # cold, allocator settling, steady
         barrier(); e0.record()
         with torch.no_grad():
             z_obj = lfdist.build_latent_object_sharded(model, ref_cams, color, mask, rank, world)
