@@ -281,7 +281,7 @@ extern "C" int lf_pose_loss_fwd(const lf_loss_desc* desc, const float* depth_log
     cudaMemsetAsync(sums, 0, sizeof(float) * 8 * g.n, st);
     const int HW = g.width * g.height;
     const int bx = min((HW + 255) / 256, 4 * sm_count() / max(1, min(g.n, 8)) + 1);
-    target_sum_kernel<<<min(64, (HW + 255) / 256), 256, 0, st>>>(g, target_depth, target_mask, sums);
+    target_sum_kernel<<<min(2 * sm_count(), (HW + 255) / 256), 256, 0, st>>>(g, target_depth, target_mask, sums);
     pose_loss_sums_kernel<<<dim3(bx, g.n), 256, 0, st>>>(g, depth_logits, mask_logits, viewport, tz, target_depth, target_mask, sums);
     pose_loss_terms_kernel<<<(g.n + 63) / 64, 64, 0, st>>>(g, sums, terms);
     LF_RETURN_LAUNCH();
@@ -301,7 +301,7 @@ extern "C" int lf_pose_loss_search_fwd(const lf_loss_desc* desc, const float* de
     cudaMemsetAsync(sums, 0, sizeof(float) * 8 * g.n, st);
     const int HW = g.width * g.height;
     const int bx = min((HW + 255) / 256, 4 * sm_count() / max(1, min(g.n, 8)) + 1);
-    target_sum_kernel<<<min(64, (HW + 255) / 256), 256, 0, st>>>(g, target_depth, target_mask, sums);
+    target_sum_kernel<<<min(2 * sm_count(), (HW + 255) / 256), 256, 0, st>>>(g, target_depth, target_mask, sums);
     pose_loss_sums_kernel<<<dim3(bx, g.n), 256, 0, st>>>(g, depth_logits, mask_logits, viewport, tz, target_depth, target_mask, sums);
     pose_loss_terms_kernel<<<(g.n + 63) / 64, 64, 0, st>>>(g, sums, terms);
     LF_RETURN_LAUNCH();

@@ -609,6 +609,203 @@ resample_o2c_bwd_cam_kernel(const float* __restrict__ gout, const float* __restr
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// backward w.r.t. the camera block, depth-marching variant (C = 4 << LPVL)
+// ------------------------------------------------------------------------------------------
+// The brick kernel above spends ~84 warp instructions per voxel (ncu, profiles/r01b): every lane of a group
+// repeats the corner index arithmetic, all 8 corners are re-read through L1, and every voxel pays 17 shuffles
+// (state broadcast, 3-value tree over the group's lanes, hand-back to the owning lane).  This variant walks
+// (i, j) columns in depth exactly like resample_march_kernel — parity-addressed register slots for the 8
+// corners (~3.7 loads per step), per-step records prepared by one lane and handed over through shared memory —
+// and removes the per-voxel cross-lane traffic altogether: along one column a = (u-cx)/fx, b = (v-cy)/fy, tu, tv
+// are constants and x = a z, y = b z, so all 17 gradient terms are linear in six per-lane column sums
+//     sum g_ox, sum g_ox z, sum g_oy, sum g_oy z, sum g_oz, sum g_oz z       (g_o* = d/d(ix,iy,iz) * mult / half)
+// of the lane's OWN 4-channel partial dot products.  The lanes of a group never exchange anything until the single
+// block reduction at the end of the chunk.  The three coordinate derivatives come from one hierarchical pass over
+// the 8 per-corner dots d[q] = <g, corner q>: x-differences and x-interpolants first, then y, then z (27
+// operations instead of 36).  grad_out (read once, from HBM) is prefetched D depth steps ahead into a register
+// ring with L1::no_allocate so it does not evict the cube's lines; the corner slots that change at step s+1 are
+// re-loaded right after the dot products of step s, so they are in flight during its remaining arithmetic.
+// Measured at config B (8 cameras, 64^3 x 32 channels; tools/kbench.py --only bwdcam, ncu in profiles/r02c_*):
+// 86 M warp instructions instead of 176 M, 278 -> 133 us (2.27 TB/s of algorithmic bytes, 34 % of the HBM roofline).
+// The kernel is occupancy-bound (long-scoreboard stalls at 16-20 warps per SM): 96 registers and 4-warp CTAs (20
+// warps) beat 128 registers and 8-warp CTAs (16 warps, 151 us); forcing 80 registers spills the corner slots.
+__device__ __forceinline__ float4 ldg_f4_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+// <a, b> with two packed operations and one add
+__device__ __forceinline__ float dot4_x2(const float4& a, const float4& b) {
+    unsigned long long a0, a1, b0, b1, t;
+    a0 = ((unsigned long long)__float_as_uint(a.y) << 32) | __float_as_uint(a.x);
+    a1 = ((unsigned long long)__float_as_uint(a.w) << 32) | __float_as_uint(a.z);
+    b0 = ((unsigned long long)__float_as_uint(b.y) << 32) | __float_as_uint(b.x);
+    b1 = ((unsigned long long)__float_as_uint(b.w) << 32) | __float_as_uint(b.z);
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(a0), "l"(b0));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(t) : "l"(a1), "l"(b1));
+    return __uint_as_float((unsigned)t) + __uint_as_float((unsigned)(t >> 32));
+}
+
+constexpr int kBwdCamMaxChunks = 4;          // depth chunks per column (bounds the workspace, see lf_resample_o2c_bwd_cam_ws)
+
+template <int LPVL, int NW, int MINB, int D>
+__global__ void __launch_bounds__(NW * 32, MINB)
+resample_o2c_bwd_cam_march_kernel(const float* __restrict__ gout, const float* __restrict__ vol,
+                                  const float* __restrict__ cam, float* __restrict__ ws,
+                                  int views_per_obj, int N, int S, int KC) {
+    constexpr int LPV = 1 << LPVL, G = 32 / LPV, C = 4 * LPV;
+    constexpr int TI = 2 * G, TJ = NW / 2;
+    constexpr int SLOTS = G * (LPV + 1);
+    
+    const int nti = (S + TI - 1) / TI, ntj = (S + TJ - 1) / TJ, nkc = (S + KC - 1) / KC;
+    int b = blockIdx.x;
+    const int ti = b % nti; b /= nti;
+    const int tj = b % ntj; b /= ntj;
+    const int kc = b % nkc; const int n = b / nkc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane & (LPV - 1), g = lane >> LPVL;
+    const int i = ti * TI + (warp & 1) * G + g;
+    const int j = tj * TJ + (warp >> 1);
+    const bool col_ok = i < S && j < S;
+    const int ic = min(i, S - 1), jc = min(j, S - 1);
+    const int k0 = kc * KC, k1 = min(S, k0 + KC);
+
+    __shared__ float cm[LF_CAM_STRIDE];
+    // record of one (group, step): offsets 0-3 | offsets 4-7 | WX0 WX1 WY0 WY1 | WZ0 WZ1 z - | mx my mz -
+    __shared__ uint4 rec[NW][5][SLOTS];
+    __shared__ float red[NW][kCamGradTerms];
+    if (threadIdx.x < LF_CAM_STRIDE) cm[threadIdx.x] = cam[(int64_t)n * LF_CAM_STRIDE + threadIdx.x];
+    __syncthreads();
+
+    // per-column part of the chain (same operations, in the same order, as gen_grid<0>)
+    const float tu = linspace_at(0.f, 1.f, S, ic), tv = linspace_at(0.f, 1.f, S, jc);
+    const float ax = (tu * cm[14] + cm[12] - cm[16]) / cm[18];
+    const float by = (tv * cm[15] + cm[13] - cm[17]) / cm[19];
+    const float half = cm[22];
+    const float mh = ((float)S / 2.f) / half;          // border multiplier (S/2 inside, 0 where clamped) over half
+
+    const int64_t S3 = (int64_t)S * S * S;
+    const float4* vb = reinterpret_cast<const float4*>(vol + (int64_t)(n / views_per_obj) * S3 * C) + sub;
+    const float4* gp = reinterpret_cast<const float4*>(gout + ((((int64_t)n * S + k0) * S + jc) * S + ic) * C) + sub;
+    const int64_t ostep = (int64_t)S * S * LPV;        // float4 units per depth step
+    const int slot = g * (LPV + 1) + sub;
+
+    // lane (g, sub) prepares depth step kr + sub of column g.  Steps past the end of the chunk get a valid (clamped)
+    // record with zero multipliers, so the walk below is straight-line code for all LPV steps of a round.
+    auto prepare = [&](int kr) {
+        const int k = min(kr + sub, S - 1);
+        const float z = linspace_at(0.f, 1.f, S, k) * cm[21] + cm[20];
+        const float y = by * z;
+        const float x = ax * z;
+        const float gx = (cm[0] * x + cm[1] * y + cm[2] * z + cm[3]) / half;
+        const float gy = (cm[4] * x + cm[5] * y + cm[6] * z + cm[7]) / half;
+        const float gz = (cm[8] * x + cm[9] * y + cm[10] * z + cm[11]) / half;
+        const Samp sp = make_samp(gx, gy, gz, S);
+        const int x1 = min(sp.x0 + 1, S - 1), y1 = min(sp.y0 + 1, S - 1), z1 = min(sp.z0 + 1, S - 1);
+        const float wx0 = 1.f - sp.wx1, wy0 = 1.f - sp.wy1, wz0 = 1.f - sp.wz1;
+        const bool ox_ = sp.x0 & 1, oy_ = sp.y0 & 1, oz_ = sp.z0 & 1;
+        const int X[2] = {ox_ ? x1 : sp.x0, ox_ ? sp.x0 : x1};
+        const int Y[2] = {oy_ ? y1 : sp.y0, oy_ ? sp.y0 : y1};
+        const int Z[2] = {oz_ ? z1 : sp.z0, oz_ ? sp.z0 : z1};
+        uint32_t off[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) off[q] = (uint32_t)((Z[q >> 2] * S + Y[(q >> 1) & 1]) * S + X[q & 1]) * LPV;
+        rec[warp][0][slot] = make_uint4(off[0], off[1], off[2], off[3]);
+        rec[warp][1][slot] = make_uint4(off[4], off[5], off[6], off[7]);
+        rec[warp][2][slot] = make_uint4(__float_as_uint(ox_ ? sp.wx1 : wx0), __float_as_uint(ox_ ? wx0 : sp.wx1),
+                                        __float_as_uint(oy_ ? sp.wy1 : wy0), __float_as_uint(oy_ ? wy0 : sp.wy1));
+        rec[warp][3][slot] = make_uint4(__float_as_uint(oz_ ? sp.wz1 : wz0), __float_as_uint(oz_ ? wz0 : sp.wz1),
+                                        __float_as_uint(z), 0u);
+        // d(weight of slot 1)/d(ix) = +1 when slot 1 holds the +1 corner (x0 even), -1 otherwise; times the border
+        // multiplier over half (sp.m* is S/2 strictly inside, 0 where clamped)
+        const float live = (kr + sub < k1) ? mh : 0.f;
+        rec[warp][4][slot] = make_uint4(__float_as_uint(sp.mx != 0.f ? (ox_ ? -live : live) : 0.f),
+                                        __float_as_uint(sp.my != 0.f ? (oy_ ? -live : live) : 0.f),
+                                        __float_as_uint(sp.mz != 0.f ? (oz_ ? -live : live) : 0.f), 0u);
+    };
+
+    uint32_t held[8];
+    float4 val[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { held[q] = 0xffffffffu; val[q] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    float4 gring[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) gring[d] = (k0 + d < k1) ? ldg_f4_stream(gp + d * ostep) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* gnext = gp + D * ostep;              // grad_out of step (current + D)
+    float A0 = 0.f, A1 = 0.f, B0 = 0.f, B1 = 0.f, C0 = 0.f, C1 = 0.f;
+
+    const uint4* r0 = &rec[warp][0][g * (LPV + 1)];
+    // the corner slots that change at step s are re-loaded (after the dot products of step s-1 have consumed them)
+    auto fetch = [&](int s) {
+        const uint4 o0 = r0[s], o1 = r0[SLOTS + s];
+        const uint32_t off[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (col_ok && off[q] != held[q]) val[q] = ldg_f4_at(vb, off[q]);
+            held[q] = off[q];
+        }
+    };
+
+    for (int kr = k0; kr < k1; kr += LPV) {
+        prepare(kr);
+        __syncwarp();
+        fetch(0);
+#pragma unroll
+        for (int s = 0; s < LPV; ++s) {
+            float d[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) d[q] = dot4_x2(gring[s % D], val[q]);
+            if (kr + s + D < k1) gring[s % D] = ldg_f4_stream(gnext);
+            gnext += ostep;
+            if (s + 1 < LPV) fetch(s + 1);              // in flight during the arithmetic below
+            const uint4 wa = r0[2 * SLOTS + s], wb = r0[3 * SLOTS + s], wm = r0[4 * SLOTS + s];
+            const float WX0 = __uint_as_float(wa.x), WX1 = __uint_as_float(wa.y);
+            const float WY0 = __uint_as_float(wa.z), WY1 = __uint_as_float(wa.w);
+            const float WZ0 = __uint_as_float(wb.x), WZ1 = __uint_as_float(wb.y), z = __uint_as_float(wb.z);
+            // slot q = pz*4 + py*2 + px: differences and interpolants along x ...
+            const float e0 = d[1] - d[0], e1 = d[3] - d[2], e2 = d[5] - d[4], e3 = d[7] - d[6];
+            const float m0 = WX0 * d[0] + WX1 * d[1], m1 = WX0 * d[2] + WX1 * d[3];
+            const float m2 = WX0 * d[4] + WX1 * d[5], m3 = WX0 * d[6] + WX1 * d[7];
+            // ... then y, then z
+            const float ex = WZ0 * (WY0 * e0 + WY1 * e1) + WZ1 * (WY0 * e2 + WY1 * e3);
+            const float ey = WZ0 * (m1 - m0) + WZ1 * (m3 - m2);
+            const float ez = (WY0 * m2 + WY1 * m3) - (WY0 * m0 + WY1 * m1);
+            const float px = ex * __uint_as_float(wm.x), py = ey * __uint_as_float(wm.y), pz = ez * __uint_as_float(wm.z);
+            A0 += px; A1 += px * z;
+            B0 += py; B1 += py * z;
+            C0 += pz; C1 += pz * z;
+        }
+        __syncwarp();
+    }
+
+    // six column sums -> the 17 terms (x = ax z, y = by z along the column)
+    float acc[kCamGradTerms];
+    acc[0] = ax * A1; acc[1] = by * A1; acc[2] = A1; acc[3] = A0;
+    acc[4] = ax * B1; acc[5] = by * B1; acc[6] = B1; acc[7] = B0;
+    acc[8] = ax * C1; acc[9] = by * C1; acc[10] = C1; acc[11] = C0;
+    const float lx1 = cm[0] * A1 + cm[4] * B1 + cm[8] * C1, lx0 = cm[0] * A0 + cm[4] * B0 + cm[8] * C0;
+    const float ly1 = cm[1] * A1 + cm[5] * B1 + cm[9] * C1, ly0 = cm[1] * A0 + cm[5] * B0 + cm[9] * C0;
+    const float lz0 = cm[2] * A0 + cm[6] * B0 + cm[10] * C0;
+    const float lu = lx1 / cm[18], lv = ly1 / cm[19];
+    acc[12] = lu; acc[14] = lu * tu;
+    acc[13] = lv; acc[15] = lv * tv;
+    acc[16] = lz0 + lx0 * ax + ly0 * by;
+#pragma unroll
+    for (int t = 0; t < kCamGradTerms; ++t) {
+        const float r = warp_sum(acc[t]);
+        if (lane == 0) red[warp][t] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < kCamGradTerms) {
+        float r = 0.f;
+        for (int w = 0; w < NW; ++w) r += red[w][threadIdx.x];
+        ws[(int64_t)blockIdx.x * kCamGradTerms + threadIdx.x] = r;
+    }
+}
+
 // stage 2: one warp per (camera, term); lanes stride over the block partials, fixed-order fp64 tree
 __global__ void resample_o2c_bwd_cam_finish(const float* __restrict__ ws, float* __restrict__ gcam,
                                             int blocks_per_cam) {
@@ -720,7 +917,37 @@ extern "C" int lf_resample_o2c_bwd_vol(const float* gout, const float* cam, floa
 
 extern "C" int64_t lf_resample_o2c_bwd_cam_ws(int N, int S) {
     if (N <= 0 || S <= 0) return 0;
-    return (int64_t)N * brick_grid(S, CBX, CBY, CBZ).per_cam() * kCamGradTerms;
+    // the larger of the brick kernel's and the marching kernel's block counts (narrowest column tile, most depth chunks)
+    const int64_t brick = brick_grid(S, CBX, CBY, CBZ).per_cam();
+    const int64_t march = (int64_t)((S + 3) / 4) * ((S + 1) / 2) * kBwdCamMaxChunks;
+    return (int64_t)N * (brick > march ? brick : march) * kCamGradTerms;
+}
+
+// depth-marching camera gradient: C = 4 << LPVL.  LFB200_BWDCAM: 0 = this kernel (4-warp CTAs, 5 per SM), 2 = 8-warp
+// CTAs at 2 per SM, 1 = the brick kernel (A/B timing and the cross-check test)
+template <int LPVL>
+static int launch_bwd_cam_march(const float* gout, const float* vol, const float* cam, float* gcam, float* ws,
+                                int vpo, int N, int S, cudaStream_t st) {
+    constexpr int LPV = 1 << LPVL, G = 32 / LPV;
+    const int mode = option(OPT_BWDCAM);
+    const int TJ = (mode == 2) ? 4 : 2;                 // CTA = 2 x TJ warps
+    const int64_t cols = (int64_t)((S + 2 * G - 1) / (2 * G)) * ((S + TJ - 1) / TJ);
+    // depth chunks of ~32 steps.  The split depends on S only, never on N or the machine: a camera's gradient is then
+    // bit-identical whatever batch it is processed in (hypotheses sharded over GPUs reproduce the single-GPU numbers).
+    int nkc = S / 32;
+    nkc = nkc < 1 ? 1 : (nkc > kBwdCamMaxChunks ? kBwdCamMaxChunks : nkc);
+    const int KC = ((S + nkc - 1) / nkc + LPV - 1) / LPV * LPV;
+    nkc = (S + KC - 1) / KC;
+    const int64_t bpc = cols * nkc;
+    LF_CHECK_ARG(N * bpc < (1ll << 31), "o2c_bwd_cam: too many columns");
+    const unsigned grid = (unsigned)(N * bpc);
+    constexpr int D2 = LPV < 2 ? LPV : 2, D4 = LPV < 4 ? LPV : 4;
+    // measured at config B (8 cameras, 64^3 x 32): 4 warps x 5 CTAs/SM (96 registers, prefetch distance 2) 133 us;
+    // 8 warps x 2 CTAs/SM (128 registers, distance 4) 151 us; distance 4 at 96 registers spills (142 us)
+    if (mode == 2) resample_o2c_bwd_cam_march_kernel<LPVL, 8, 2, D4><<<grid, 256, 0, st>>>(gout, vol, cam, ws, vpo, N, S, KC);
+    else resample_o2c_bwd_cam_march_kernel<LPVL, 4, 5, D2><<<grid, 128, 0, st>>>(gout, vol, cam, ws, vpo, N, S, KC);
+    resample_o2c_bwd_cam_finish<<<N, 32 * LF_CAMGRAD_STRIDE, 0, st>>>(ws, gcam, (int)bpc);
+    LF_RETURN_LAUNCH();
 }
 
 extern "C" int lf_resample_o2c_bwd_cam(const float* gout, const float* vol, const float* cam, float* gcam,
@@ -730,6 +957,11 @@ extern "C" int lf_resample_o2c_bwd_cam(const float* gout, const float* vol, cons
     LF_CHECK_ARG(B > 0 && N % B == 0, "o2c: N=%d must be a multiple of B=%d", N, B);
     const int bpc = brick_grid(S, CBX, CBY, CBZ).per_cam();
     cudaStream_t st = (cudaStream_t)stream;
+    if (option(OPT_BWDCAM) != 1 && (int64_t)S * S * S * (C / 4) < (1ll << 32)) {
+        if (C == 16) return launch_bwd_cam_march<2>(gout, vol, cam, gcam, ws, N / B, N, S, st);
+        if (C == 32) return launch_bwd_cam_march<3>(gout, vol, cam, gcam, ws, N / B, N, S, st);
+        if (C == 64) return launch_bwd_cam_march<4>(gout, vol, cam, gcam, ws, N / B, N, S, st);
+    }
     if (C % 4 == 0) {
         const int l = lpv_log2_for(C, 4);
         resample_o2c_bwd_cam_kernel<4><<<N * bpc, 256, 0, st>>>(gout, vol, cam, ws, N / B, N, C, S, l, bpc);

@@ -71,6 +71,23 @@ def main():
             o.backward(w)
         med2, best2 = timeit(bwd, a.iters, flush)
         out['o2c_fwd+bwd_cam'] = dict(ms=med2, bwd_only_ms=med2 - med, GBs_bwd=nbytes / (med2 - med) / 1e6)
+    if a.only in ('all', 'resample', 'bwdcam'):
+        # camera gradient alone, straight through the C ABI, per kernel variant (LFB200_BWDCAM)
+        import ctypes
+        from latentfusion_b200 import _lib as L
+        blk = cam.o2c_block(1.0).detach().contiguous()
+        w = ops.to_cl(torch.randn(N, C, S, S, S, device=dev))
+        ws = torch.empty(L.lib().lf_resample_o2c_bwd_cam_ws(N, S), device=dev)
+        gc = torch.empty(N, L.CAMGRAD_STRIDE, device=dev)
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        nbytes = 4 * C * S ** 3 * (1 + N)
+        for opt, name in ((0, 'march_4w5_d2'), (2, 'march_8w2_d4'), (1, 'brick')):
+            L.check(L.lib().lf_set_option(b'LFB200_BWDCAM', opt), 'opt')
+            med, best = timeit(lambda: L.check(L.lib().lf_resample_o2c_bwd_cam(
+                ops._p(w), ops._p(vol), ops._p(blk), ops._p(gc), ops._p(ws), 1, N, C, S, st), 'bwd_cam'), a.iters, flush)
+            out[f'o2c_bwd_cam[{name}]'] = dict(ms=med, best_ms=best, GBs=nbytes / med / 1e6,
+                                              frac=nbytes / med / 1e6 / peaks['hbm_gbs'])
+        L.lib().lf_set_option(b'LFB200_BWDCAM', 0)
     if a.only in ('all', 'conv'):
         x = ops.to_cl(torch.randn(N, C, S, S, S, device=dev))
         wgt = torch.randn(C, C, 3, 3, 3, device=dev)
