@@ -67,6 +67,11 @@ int64_t lf_resample_o2c_bwd_cam_ws(int N, int S);
 int lf_resample_o2c_bwd_cam(const float* grad_out, const float* vol, const float* cam,
                             float* grad_cam, float* workspace,
                             int B, int N, int C, int S, void* stream);
+/* the same gradient laid out as a camera block [N][LF_CAM_STRIDE] (terms 0..15 in place, d/d(znear) at [20], zeros
+ * elsewhere): what lf_camera_o2c_bwd consumes, without a re-layout pass in between */
+int lf_resample_o2c_bwd_cam_block(const float* grad_out, const float* vol, const float* cam,
+                                  float* grad_block, float* workspace,
+                                  int B, int N, int C, int S, void* stream);
 /* backward w.r.t. the volume (training). grad_vol [B][S^3][C] must be zeroed by the caller. */
 int lf_resample_o2c_bwd_vol(const float* grad_out, const float* cam, float* grad_vol,
                             int B, int N, int C, int S, void* stream);
@@ -225,6 +230,16 @@ int lf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
                  float beta1, float beta2, float eps, void* stream);
 int lf_plateau_step(const float* rank_loss /*[n]*/, float* lr, float* best, float* num_bad, int n,
                     float threshold, float patience, float factor, void* stream);
+/* Loss combination + bookkeeping of one refinement iteration (pose/estimation.py:611-660; replaces ~35 elementwise
+ * launches of the autograd graph of sum(w*term).mean() and of the history snapshots): rank[i] = sum_k w_rank[k]*terms[i][k]
+ * and the same with w_opt (left to right), grad_terms[i][k] = w_opt[k] / n (the gradient optim.mean().backward() hands
+ * lf_pose_loss_bwd), and the snapshot of (rank, optim, terms, log_quaternion, translation) into the chunk history
+ * h_rank/h_optim [chunk][n], h_terms [chunk][k][n], h_lq/h_tr [chunk][n][3] at *slot, which then advances modulo chunk;
+ * *step_count += 1 when given (the batched Adam's step counter). */
+int lf_refine_record(const float* terms /*[n][k]*/, int n, int k, const float* w_rank /*[k]*/, const float* w_opt /*[k]*/,
+                     const float* log_quaternion /*[n][3]*/, const float* translation /*[n][3]*/, float* rank /*[n]*/,
+                     float* grad_terms /*[n][k]*/, float* h_rank, float* h_optim, float* h_terms, float* h_lq, float* h_tr,
+                     long long* slot /*[1]*/, int chunk, float* step_count /*[1], nullable*/, void* stream);
 
 /* ---- fused pose-loss head (recon/models.py:455-484 interpret_logits; modules/geometry.py:261-285 uncrop,
  *      :555-558 denormalize_depth; pose/estimation.py:70-118 default_pose_loss; pose/utils.py:81-117) ----
@@ -235,6 +250,12 @@ typedef struct {
     int n, p;              /* hypotheses, crop side */
     int width, height;     /* full frame */
     float z_span, eps;     /* Camera.z_span; denormalize_depth eps (0.01) */
+    /* layout of the logit maps and of tz, in floats; 0 = dense ([N][P][P] maps, tz[N]).  The decoder's fused heads write
+     * channels-last logits [N][P][P][H]: depth_logits = base, mask_logits = base + 1, pix_stride = H, hyp_stride = P*P*H;
+     * tz = translation + 2 with tz_stride = 3.  The gradients use the layout of their inputs; with a non-dense layout
+     * lf_pose_loss_bwd does not zero-fill them (grad_depth_logits / grad_mask_logits when pix/hyp strides are given,
+     * grad_tz when tz_stride > 1): the caller passes zero-filled tensors. */
+    int pix_stride, hyp_stride, tz_stride;
 } lf_loss_desc;
 int lf_pose_loss_fwd(const lf_loss_desc* desc, const float* depth_logits, const float* mask_logits,
                      const float* viewport, const float* tz, const float* target_depth, const float* target_mask,

@@ -28,7 +28,8 @@ class ConvDesc(ctypes.Structure):
 class LossDesc(ctypes.Structure):
     """lf_loss_desc (include/lfb200.h)."""
     _fields_ = [('n', c_int), ('p', c_int), ('width', c_int), ('height', c_int),
-                ('z_span', c_float), ('eps', c_float)]
+                ('z_span', c_float), ('eps', c_float),
+                ('pix_stride', c_int), ('hyp_stride', c_int), ('tz_stride', c_int)]
 
 
 _SIGNATURES = {
@@ -38,6 +39,7 @@ _SIGNATURES = {
     'lf_resample_o2c_fwd': (c_int, [c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_vp]),
     'lf_resample_o2c_bwd_cam_ws': (c_i64, [c_int, c_int]),
     'lf_resample_o2c_bwd_cam': (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_vp]),
+    'lf_resample_o2c_bwd_cam_block': (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_vp]),
     'lf_resample_o2c_bwd_vol': (c_int, [c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_vp]),
     'lf_resample_c2o_fwd': (c_int, [c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_vp]),
     'lf_resample_c2o_bwd_vol': (c_int, [c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_vp]),
@@ -93,6 +95,7 @@ _SIGNATURES = {
     'lf_camera_o2c_fwd': (c_int, [c_f32p] * 5 + [c_int, c_float, c_float, c_vp]),
     'lf_camera_o2c_bwd': (c_int, [c_f32p] * 6 + [c_int, c_vp]),
     'lf_adam_step': (c_int, [c_f32p] * 4 + [c_int, c_int, c_f32p, c_f32p, c_float, c_float, c_float, c_vp]),
+    'lf_refine_record': (c_int, [c_f32p, c_int, c_int] + [c_f32p] * 11 + [c_vp, c_int, c_f32p, c_vp]),
     'lf_plateau_step': (c_int, [c_f32p] * 4 + [c_int, c_float, c_float, c_float, c_vp]),
     'lf_pose_loss_fwd': (c_int, [ctypes.POINTER(LossDesc)] + [c_f32p] * 8 + [c_vp]),
     'lf_pose_loss_search_fwd': (c_int, [ctypes.POINTER(LossDesc)] + [c_f32p] * 8 + [c_vp]),

@@ -142,9 +142,57 @@ __global__ void plateau_kernel(const float* __restrict__ rank_loss, float* __res
     num_bad[i] = nb;
 }
 
+// One refinement iteration's loss combination and bookkeeping (reference pose/estimation.py:611-660): the ranking and
+// optimisation losses as the weighted sums of the terms (left to right, like Python's sum() over the loss dict), the
+// gradient of mean_n(optim) w.r.t. the terms (what optim.mean().backward() hands the loss head: w_opt[k] / N), and the
+// snapshot of this iteration into the chunk history at `slot`, which then advances.  One CTA.
+__global__ void refine_record_kernel(const float* __restrict__ terms, int n, int k, const float* __restrict__ w_rank,
+                                     const float* __restrict__ w_opt, const float* __restrict__ lq,
+                                     const float* __restrict__ tr, float* __restrict__ rank, float* __restrict__ gterms,
+                                     float* __restrict__ h_rank, float* __restrict__ h_optim, float* __restrict__ h_terms,
+                                     float* __restrict__ h_lq, float* __restrict__ h_tr, long long* __restrict__ slot,
+                                     int chunk, float* __restrict__ step_count) {
+    const long long sl = *slot;
+    const float inv_n = 1.f / (float)n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float r = 0.f, o = 0.f;
+        for (int j = 0; j < k; ++j) {
+            const float t = terms[i * k + j];
+            r = __fadd_rn(r, __fmul_rn(w_rank[j], t));
+            o = __fadd_rn(o, __fmul_rn(w_opt[j], t));
+            gterms[i * k + j] = __fmul_rn(inv_n, w_opt[j]);
+            h_terms[(sl * k + j) * n + i] = t;
+        }
+        rank[i] = r;
+        h_rank[sl * n + i] = r;
+        h_optim[sl * n + i] = o;
+        for (int c = 0; c < 3; ++c) {
+            h_lq[(sl * n + i) * 3 + c] = lq[i * 3 + c];
+            h_tr[(sl * n + i) * 3 + c] = tr[i * 3 + c];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *slot = (sl + 1) % chunk;
+        if (step_count) *step_count += 1.f;
+    }
+}
+
 }  // namespace lf
 
 using namespace lf;
+
+extern "C" int lf_refine_record(const float* terms, int n, int k, const float* w_rank, const float* w_opt,
+                                const float* log_quaternion, const float* translation, float* rank, float* grad_terms,
+                                float* h_rank, float* h_optim, float* h_terms, float* h_lq, float* h_tr,
+                                long long* slot, int chunk, float* step_count, void* stream) {
+    LF_CHECK_ARG(terms && w_rank && w_opt && log_quaternion && translation && rank && grad_terms && h_rank && h_optim &&
+                 h_terms && h_lq && h_tr && slot && n > 0 && k > 0 && chunk > 0, "refine_record: bad arguments");
+    refine_record_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(terms, n, k, w_rank, w_opt, log_quaternion, translation, rank,
+                                                              grad_terms, h_rank, h_optim, h_terms, h_lq, h_tr, slot, chunk,
+                                                              step_count);
+    LF_RETURN_LAUNCH();
+}
 
 extern "C" int lf_camera_o2c_fwd(const float* log_quaternion, const float* translation, const float* viewport,
                                  const float* intrinsic, float* block, int n, float z_span, float cube_size,

@@ -20,6 +20,7 @@ constexpr int kSums = 6;   // A=sum dl1, B=sum dl1*pm*tm, C=sum pm*tm, D=sum pm,
 struct LossGeom {
     int n, p, width, height;
     float range, base_off;    // z = (tanh(dl)+1)/2 * gate * range + (tz + base_off)
+    int ps, hs, tzs;          // strides in floats: between crop pixels of a logit map, between hypotheses, between tz entries
     int premask;              // coarse search (PoseEstimator._render_observation, estimation.py:187-197): the crop's metric
                               // depth is multiplied by the crop's own sigmoid(mask) before it is pasted into the frame
 };
@@ -44,7 +45,7 @@ __device__ __forceinline__ float clip_coord(float g, int P, float& mult) {
     return ix;
 }
 
-__device__ __forceinline__ PixelSample make_sample(float X, float Y, const float* vp, int P) {
+__device__ __forceinline__ PixelSample make_sample(float X, float Y, const float* vp, int P, int ps) {
     PixelSample s;
     const float vw = vp[2] - vp[0], vh = vp[3] - vp[1];
     const float gx = (X - vp[0]) / vw * 2.f - 1.f;       // geometry.py:281-282
@@ -54,13 +55,13 @@ __device__ __forceinline__ PixelSample make_sample(float X, float Y, const float
     if (!isfinite(ix)) { ix = 0.f; s.mx = 0.f; }
     if (!isfinite(iy)) { iy = 0.f; s.my = 0.f; }
     const int xn = (int)nearbyintf(ix), yn = (int)nearbyintf(iy);
-    s.near_idx = yn * P + xn;
+    s.near_idx = (yn * P + xn) * ps;
     const float fx0 = floorf(ix), fy0 = floorf(iy);
     const int x0 = (int)fx0, y0 = (int)fy0;
     s.fx = ix - fx0; s.fy = iy - fy0;
     s.x0in = (x0 + 1 < P); s.y0in = (y0 + 1 < P);
     const int x1 = s.x0in ? x0 + 1 : x0, y1 = s.y0in ? y0 + 1 : y0;
-    s.i00 = y0 * P + x0; s.i01 = y0 * P + x1; s.i10 = y1 * P + x0; s.i11 = y1 * P + x1;
+    s.i00 = (y0 * P + x0) * ps; s.i01 = (y0 * P + x1) * ps; s.i10 = (y1 * P + x0) * ps; s.i11 = (y1 * P + x1) * ps;
     const float wx1 = s.x0in ? s.fx : 0.f, wy1 = s.y0in ? s.fy : 0.f;
     const float wx0 = 1.f - s.fx, wy0 = 1.f - s.fy;
     s.w00 = wx0 * wy0; s.w01 = wx1 * wy0; s.w10 = wx0 * wy1; s.w11 = wx1 * wy1;
@@ -95,13 +96,13 @@ pose_loss_sums_kernel(const LossGeom g, const float* __restrict__ dlog, const fl
                       const float* __restrict__ tdepth, const float* __restrict__ tmask, float* __restrict__ sums) {
     const int n = blockIdx.y;
     const int HW = g.width * g.height;
-    const float* dl = dlog + (size_t)n * g.p * g.p;
-    const float* ml = mlog + (size_t)n * g.p * g.p;
-    const float base = tz[n] + g.base_off;
+    const float* dl = dlog + (size_t)n * g.hs;
+    const float* ml = mlog + (size_t)n * g.hs;
+    const float base = tz[n * g.tzs] + g.base_off;
     float acc[kSums] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int px = blockIdx.x * blockDim.x + threadIdx.x; px < HW; px += gridDim.x * blockDim.x) {
         const int Y = px / g.width, X = px - Y * g.width;
-        const PixelSample s = make_sample((float)X, (float)Y, vp + 4 * n, g.p);
+        const PixelSample s = make_sample((float)X, (float)Y, vp + 4 * n, g.p, g.ps);
         const PixelTerms t = eval_pixel(s, dl, ml, tdepth[px], tmask[px], g.range, base, g.premask);
         acc[0] += t.dl1;
         acc[1] += t.dl1 * t.pm * t.tm;
@@ -169,7 +170,7 @@ __device__ __forceinline__ void warp_atomic_add(float* base, int idx, float v) {
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 pose_loss_bwd_kernel(const LossGeom g, const float* __restrict__ dlog, const float* __restrict__ mlog,
                      const float* __restrict__ vp, const float* __restrict__ tz,
                      const float* __restrict__ tdepth, const float* __restrict__ tmask,
@@ -177,11 +178,11 @@ pose_loss_bwd_kernel(const LossGeom g, const float* __restrict__ dlog, const flo
                      float* __restrict__ g_dl, float* __restrict__ g_ml, float* __restrict__ g_vp, float* __restrict__ g_tz) {
     const int n = blockIdx.y;
     const int HW = g.width * g.height;
-    const float* dl = dlog + (size_t)n * g.p * g.p;
-    const float* ml = mlog + (size_t)n * g.p * g.p;
-    float* gdl = g_dl + (size_t)n * g.p * g.p;
-    float* gml = g_ml + (size_t)n * g.p * g.p;
-    const float base = tz[n] + g.base_off;
+    const float* dl = dlog + (size_t)n * g.hs;
+    const float* ml = mlog + (size_t)n * g.hs;
+    float* gdl = g_dl + (size_t)n * g.hs;
+    float* gml = g_ml + (size_t)n * g.hs;
+    const float base = tz[n * g.tzs] + g.base_off;
     const float* s = sums + n * 8;
     const float fHW = (float)HW;
     // d(total)/d(sums) from d(total)/d(terms)
@@ -196,6 +197,8 @@ pose_loss_bwd_kernel(const LossGeom g, const float* __restrict__ dlog, const flo
     const float dE = ((s[4] > 1e-4f) ? -g_iou / s[4] : 0.f) - dU;
     const float dF = g_msk / fHW;
     const float vx0 = vp[4 * n], vy0 = vp[4 * n + 1], vw = vp[4 * n + 2] - vx0, vh = vp[4 * n + 3] - vy0;
+    const float inv_vw = 1.f / vw, inv_vh = 1.f / vh, two_inv_vw = 2.f * inv_vw, two_inv_vh = 2.f * inv_vh;
+    const float half_p = (float)g.p * 0.5f;            // d ix / d gx
 
     float a_tz = 0.f, a_vp[4] = {0.f, 0.f, 0.f, 0.f};
     // full warps only: the aggregation helper uses warp-wide votes
@@ -204,7 +207,7 @@ pose_loss_bwd_kernel(const LossGeom g, const float* __restrict__ dlog, const flo
         const bool live = px < HW;
         const int pc = live ? px : HW - 1;
         const int Y = pc / g.width, X = pc - Y * g.width;
-        const PixelSample smp = make_sample((float)X, (float)Y, vp + 4 * n, g.p);
+        const PixelSample smp = make_sample((float)X, (float)Y, vp + 4 * n, g.p, g.ps);
         const PixelTerms t = eval_pixel(smp, dl, ml, tdepth[pc], tmask[pc], g.range, base);
         float d_dl1 = dA + dB * t.pm * t.tm;
         float d_pm = dB * t.dl1 * t.tm + dC * t.tm + dD + dE * t.tm * t.valid;
@@ -230,14 +233,15 @@ pose_loss_bwd_kernel(const LossGeom g, const float* __restrict__ dlog, const flo
         const float wx0 = 1.f - smp.fx, wx1 = smp.x0in ? smp.fx : 0.f;
         const float dml_dix = (smp.x0in ? (m01 - m00) : -m00) * wy0 + ((smp.x0in ? m11 : 0.f) - m10) * wy1;
         const float dml_diy = (smp.y0in ? (m10 - m00) : -m00) * wx0 + ((smp.y0in ? m11 : 0.f) - m01) * wx1;
-        const float gix = d_ml * dml_dix * smp.mx * ((float)g.p * 0.5f);   // d ix / d gx = P/2
-        const float giy = d_ml * dml_diy * smp.my * ((float)g.p * 0.5f);
-        // gx = (X - vx0)/vw*2 - 1
-        const float rx = ((float)X - vx0) / vw, ry = ((float)Y - vy0) / vh;
-        a_vp[0] += gix * 2.f * (rx - 1.f) / vw;      // d gx / d vx0 = 2*(-1/vw + (X-vx0)/vw^2)
-        a_vp[2] += gix * 2.f * (-rx) / vw;           // d gx / d vx1
-        a_vp[1] += giy * 2.f * (ry - 1.f) / vh;
-        a_vp[3] += giy * 2.f * (-ry) / vh;
+        const float gix = d_ml * dml_dix * smp.mx * half_p;
+        const float giy = d_ml * dml_diy * smp.my * half_p;
+        // gx = (X - vx0)/vw*2 - 1:  d gx / d vx0 = 2*(rx - 1)/vw,  d gx / d vx1 = -2*rx/vw  with rx = (X - vx0)/vw
+        const float rx = ((float)X - vx0) * inv_vw, ry = ((float)Y - vy0) * inv_vh;
+        const float tx = gix * two_inv_vw, ty = giy * two_inv_vh;
+        a_vp[0] += tx * (rx - 1.f);
+        a_vp[2] -= tx * rx;
+        a_vp[1] += ty * (ry - 1.f);
+        a_vp[3] -= ty * ry;
     }
     __shared__ float red[8][5];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -252,8 +256,23 @@ pose_loss_bwd_kernel(const LossGeom g, const float* __restrict__ dlog, const flo
         float r = 0.f;
         for (int w = 0; w < 8; ++w) r += red[w][threadIdx.x];
         if (threadIdx.x < 4) atomicAdd(g_vp + 4 * n + threadIdx.x, r);
-        else atomicAdd(g_tz + n, r);
+        else atomicAdd(g_tz + n * g.tzs, r);
     }
+}
+
+// blocks along x for a (bx, n) grid of grid-stride CTAs: as many as are co-resident (occupancy x SMs), so that the
+// launch is ONE balanced wave (600 CTAs on 444 slots ran as two waves, the second one nearly empty)
+template <typename K>
+static int blocks_x(K kernel, int n, int HW) {
+    static int per_sm = 0;                      // per kernel instantiation (K is a distinct function type per kernel)
+    if (per_sm == 0) {
+        int v = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, 256, 0) != cudaSuccess || v < 1) v = 2;
+        per_sm = v;
+    }
+    int bx = per_sm * sm_count() / max(1, n);
+    bx = max(1, min(bx, (HW + 255) / 256));
+    return bx;
 }
 
 static int loss_geom(const lf_loss_desc* d, LossGeom& g) {
@@ -263,6 +282,11 @@ static int loss_geom(const lf_loss_desc* d, LossGeom& g) {
     g.range = 2.f * d->z_span + 2.f * d->eps;          // (zfar + eps) - (znear - eps)
     g.base_off = -d->z_span - d->eps;                  // znear - eps = tz - z_span - eps
     g.premask = 0;
+    LF_CHECK_ARG(d->pix_stride >= 0 && d->hyp_stride >= 0 && d->tz_stride >= 0, "pose_loss: negative stride");
+    g.ps = d->pix_stride > 0 ? d->pix_stride : 1;
+    g.hs = d->hyp_stride > 0 ? d->hyp_stride : d->p * d->p * g.ps;
+    g.tzs = d->tz_stride > 0 ? d->tz_stride : 1;
+    LF_CHECK_ARG((int64_t)g.hs >= (int64_t)(d->p * d->p - 1) * g.ps + 1, "pose_loss: hypothesis stride smaller than one logit map");
     return LF_OK;
 }
 
@@ -280,7 +304,7 @@ extern "C" int lf_pose_loss_fwd(const lf_loss_desc* desc, const float* depth_log
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(sums, 0, sizeof(float) * 8 * g.n, st);
     const int HW = g.width * g.height;
-    const int bx = min((HW + 255) / 256, 4 * sm_count() / max(1, min(g.n, 8)) + 1);
+    const int bx = blocks_x(pose_loss_sums_kernel, g.n, HW);
     target_sum_kernel<<<min(2 * sm_count(), (HW + 255) / 256), 256, 0, st>>>(g, target_depth, target_mask, sums);
     pose_loss_sums_kernel<<<dim3(bx, g.n), 256, 0, st>>>(g, depth_logits, mask_logits, viewport, tz, target_depth, target_mask, sums);
     pose_loss_terms_kernel<<<(g.n + 63) / 64, 64, 0, st>>>(g, sums, terms);
@@ -300,7 +324,7 @@ extern "C" int lf_pose_loss_search_fwd(const lf_loss_desc* desc, const float* de
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(sums, 0, sizeof(float) * 8 * g.n, st);
     const int HW = g.width * g.height;
-    const int bx = min((HW + 255) / 256, 4 * sm_count() / max(1, min(g.n, 8)) + 1);
+    const int bx = blocks_x(pose_loss_sums_kernel, g.n, HW);
     target_sum_kernel<<<min(2 * sm_count(), (HW + 255) / 256), 256, 0, st>>>(g, target_depth, target_mask, sums);
     pose_loss_sums_kernel<<<dim3(bx, g.n), 256, 0, st>>>(g, depth_logits, mask_logits, viewport, tz, target_depth, target_mask, sums);
     pose_loss_terms_kernel<<<(g.n + 63) / 64, 64, 0, st>>>(g, sums, terms);
@@ -317,13 +341,17 @@ extern "C" int lf_pose_loss_bwd(const lf_loss_desc* desc, const float* depth_log
     LF_CHECK_ARG(depth_logits && mask_logits && viewport && tz && target_depth && target_mask && sums && grad_terms &&
                  grad_depth_logits && grad_mask_logits && grad_viewport && grad_tz, "pose_loss_bwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t crop = sizeof(float) * (size_t)g.n * g.p * g.p;
-    cudaMemsetAsync(grad_depth_logits, 0, crop, st);
-    cudaMemsetAsync(grad_mask_logits, 0, crop, st);
+    // dense layout: the gradients are zero-filled here; strided layout (maps interleaved in one tensor, tz a column of
+    // the translation): the caller passes zero-filled tensors of the inputs' layout
+    if (g.ps == 1 && g.hs == g.p * g.p) {
+        const size_t crop = sizeof(float) * (size_t)g.n * g.p * g.p;
+        cudaMemsetAsync(grad_depth_logits, 0, crop, st);
+        cudaMemsetAsync(grad_mask_logits, 0, crop, st);
+    }
     cudaMemsetAsync(grad_viewport, 0, sizeof(float) * 4 * g.n, st);
-    cudaMemsetAsync(grad_tz, 0, sizeof(float) * g.n, st);
+    if (g.tzs == 1) cudaMemsetAsync(grad_tz, 0, sizeof(float) * g.n, st);
     const int HW = g.width * g.height;
-    const int bx = min((HW + 255) / 256, 4 * sm_count() / max(1, min(g.n, 8)) + 1);
+    const int bx = blocks_x(pose_loss_bwd_kernel, g.n, HW);
     pose_loss_bwd_kernel<<<dim3(bx, g.n), 256, 0, st>>>(g, depth_logits, mask_logits, viewport, tz, target_depth,
                                                       target_mask, sums, grad_terms, grad_depth_logits,
                                                       grad_mask_logits, grad_viewport, grad_tz);

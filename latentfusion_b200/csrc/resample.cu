@@ -806,18 +806,31 @@ resample_o2c_bwd_cam_march_kernel(const float* __restrict__ gout, const float* _
     }
 }
 
-// stage 2: one warp per (camera, term); lanes stride over the block partials, fixed-order fp64 tree
+// stage 2: one warp per (camera, term); lanes stride over the block partials, fixed-order fp64 tree.
+// out_stride = LF_CAMGRAD_STRIDE: the 17 terms in order (+ zero padding); out_stride = LF_CAM_STRIDE: a gradient of the
+// camera block itself, terms 0..15 in place, d/d(znear) at [20], zeros elsewhere (what lf_camera_o2c_bwd consumes).
 __global__ void resample_o2c_bwd_cam_finish(const float* __restrict__ ws, float* __restrict__ gcam,
-                                            int blocks_per_cam) {
+                                            int blocks_per_cam, int out_stride) {
     const int n = blockIdx.x;
     const int t = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* row = gcam + (int64_t)n * out_stride;
+    if (out_stride == LF_CAM_STRIDE) {
+        const int c = threadIdx.x;                         // zero the columns no term lands in
+        if (c < LF_CAM_STRIDE && c >= 16 && c != 20) row[c] = 0.f;
+    }
     if (t >= LF_CAMGRAD_STRIDE) return;
     double a = 0.0;
     if (t < kCamGradTerms)
         for (int b = lane; b < blocks_per_cam; b += 32) a += (double)ws[((int64_t)n * blocks_per_cam + b) * kCamGradTerms + t];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) gcam[(int64_t)n * LF_CAMGRAD_STRIDE + t] = (float)a;
+    if (lane != 0) return;
+    if (out_stride == LF_CAM_STRIDE) {
+        if (t < 16) row[t] = (float)a;
+        else if (t == 16) row[20] = (float)a;
+    } else {
+        row[t] = (float)a;
+    }
 }
 
 static int lpv_log2_for(int C, int vec) {
@@ -927,7 +940,7 @@ extern "C" int64_t lf_resample_o2c_bwd_cam_ws(int N, int S) {
 // CTAs at 2 per SM, 1 = the brick kernel (A/B timing and the cross-check test)
 template <int LPVL>
 static int launch_bwd_cam_march(const float* gout, const float* vol, const float* cam, float* gcam, float* ws,
-                                int vpo, int N, int S, cudaStream_t st) {
+                                int vpo, int N, int S, int out_stride, cudaStream_t st) {
     constexpr int LPV = 1 << LPVL, G = 32 / LPV;
     const int mode = option(OPT_BWDCAM);
     const int TJ = (mode == 2) ? 4 : 2;                 // CTA = 2 x TJ warps
@@ -946,21 +959,21 @@ static int launch_bwd_cam_march(const float* gout, const float* vol, const float
     // 8 warps x 2 CTAs/SM (128 registers, distance 4) 151 us; distance 4 at 96 registers spills (142 us)
     if (mode == 2) resample_o2c_bwd_cam_march_kernel<LPVL, 8, 2, D4><<<grid, 256, 0, st>>>(gout, vol, cam, ws, vpo, N, S, KC);
     else resample_o2c_bwd_cam_march_kernel<LPVL, 4, 5, D2><<<grid, 128, 0, st>>>(gout, vol, cam, ws, vpo, N, S, KC);
-    resample_o2c_bwd_cam_finish<<<N, 32 * LF_CAMGRAD_STRIDE, 0, st>>>(ws, gcam, (int)bpc);
+    resample_o2c_bwd_cam_finish<<<N, 32 * LF_CAMGRAD_STRIDE, 0, st>>>(ws, gcam, (int)bpc, out_stride);
     LF_RETURN_LAUNCH();
 }
 
-extern "C" int lf_resample_o2c_bwd_cam(const float* gout, const float* vol, const float* cam, float* gcam,
-                                       float* ws, int B, int N, int C, int S, void* stream) {
+static int bwd_cam_impl(const float* gout, const float* vol, const float* cam, float* gcam, float* ws, int B, int N,
+                        int C, int S, int out_stride, void* stream) {
     if (int e = check_common(gout, vol, cam, N, C, S)) return e;
     LF_CHECK_ARG(gcam && ws, "o2c_bwd_cam: null output/workspace");
     LF_CHECK_ARG(B > 0 && N % B == 0, "o2c: N=%d must be a multiple of B=%d", N, B);
     const int bpc = brick_grid(S, CBX, CBY, CBZ).per_cam();
     cudaStream_t st = (cudaStream_t)stream;
     if (option(OPT_BWDCAM) != 1 && (int64_t)S * S * S * (C / 4) < (1ll << 32)) {
-        if (C == 16) return launch_bwd_cam_march<2>(gout, vol, cam, gcam, ws, N / B, N, S, st);
-        if (C == 32) return launch_bwd_cam_march<3>(gout, vol, cam, gcam, ws, N / B, N, S, st);
-        if (C == 64) return launch_bwd_cam_march<4>(gout, vol, cam, gcam, ws, N / B, N, S, st);
+        if (C == 16) return launch_bwd_cam_march<2>(gout, vol, cam, gcam, ws, N / B, N, S, out_stride, st);
+        if (C == 32) return launch_bwd_cam_march<3>(gout, vol, cam, gcam, ws, N / B, N, S, out_stride, st);
+        if (C == 64) return launch_bwd_cam_march<4>(gout, vol, cam, gcam, ws, N / B, N, S, out_stride, st);
     }
     if (C % 4 == 0) {
         const int l = lpv_log2_for(C, 4);
@@ -969,8 +982,18 @@ extern "C" int lf_resample_o2c_bwd_cam(const float* gout, const float* vol, cons
         const int l = lpv_log2_for(C, 1);
         resample_o2c_bwd_cam_kernel<1><<<N * bpc, 256, 0, st>>>(gout, vol, cam, ws, N / B, N, C, S, l, bpc);
     }
-    resample_o2c_bwd_cam_finish<<<N, 32 * LF_CAMGRAD_STRIDE, 0, st>>>(ws, gcam, bpc);
+    resample_o2c_bwd_cam_finish<<<N, 32 * LF_CAMGRAD_STRIDE, 0, st>>>(ws, gcam, bpc, out_stride);
     LF_RETURN_LAUNCH();
+}
+
+extern "C" int lf_resample_o2c_bwd_cam(const float* gout, const float* vol, const float* cam, float* gcam,
+                                       float* ws, int B, int N, int C, int S, void* stream) {
+    return bwd_cam_impl(gout, vol, cam, gcam, ws, B, N, C, S, LF_CAMGRAD_STRIDE, stream);
+}
+
+extern "C" int lf_resample_o2c_bwd_cam_block(const float* gout, const float* vol, const float* cam, float* gblock,
+                                             float* ws, int B, int N, int C, int S, void* stream) {
+    return bwd_cam_impl(gout, vol, cam, gblock, ws, B, N, C, S, LF_CAM_STRIDE, stream);
 }
 
 extern "C" int lf_resample_c2o_fwd(const float* vol, const float* cam, float* out, int V, int C, int S, void* stream) {

@@ -158,13 +158,11 @@ class _ResampleO2C(torch.autograd.Function):
                   (_p(gout), _p(cam), _p(gvol), B, N, C, S, _stream()), nbytes=4 * C * S ** 3 * (B + N))
         if ctx.needs_input_grad[1]:
             ws = torch.empty(L.lib().lf_resample_o2c_bwd_cam_ws(N, S), device=vol.device, dtype=torch.float32)
-            g = torch.empty(N, L.CAMGRAD_STRIDE, device=vol.device, dtype=torch.float32)
-            _call('lf_resample_o2c_bwd_cam', L.lib().lf_resample_o2c_bwd_cam,
-                  (_p(gout), _p(vol), _p(cam), _p(g), _p(ws), B, N, C, S, _stream()), kernels=2,
+            # the finishing kernel writes the gradient in the camera block's own layout (zeros where no term lands)
+            gcam = torch.empty(N, L.CAM_STRIDE, device=vol.device, dtype=torch.float32)
+            _call('lf_resample_o2c_bwd_cam', L.lib().lf_resample_o2c_bwd_cam_block,
+                  (_p(gout), _p(vol), _p(cam), _p(gcam), _p(ws), B, N, C, S, _stream()), kernels=2,
                   nbytes=4 * C * S ** 3 * (B + N))
-            gcam = torch.zeros(N, L.CAM_STRIDE, device=vol.device, dtype=torch.float32)
-            gcam[:, :16] = g[:, :16]
-            gcam[:, 20] = g[:, 16]
         return gvol, gcam
 
 
@@ -1108,6 +1106,68 @@ class _PoseLoss(torch.autograd.Function):
               (ctypes.byref(desc), _p(dl), _p(ml), _p(vp), _p(tzc), _p(td), _p(tm), _p(sums), _p(gt),
                _p(g_dl), _p(g_ml), _p(g_vp), _p(g_tz), _stream()))
         return g_dl.view(dshape), g_ml.view(mshape), g_vp, g_tz, None, None, None, None, None, None
+
+
+class _PoseLossPacked(torch.autograd.Function):
+    """_PoseLoss on the decoder's own tensors: the channels-last logits [N,2,P,P] of the fused heads (depth = channel 0,
+    mask = channel 1) and the translation [N,3], addressed through lf_loss_desc's strides — no de-interleaving copies
+    forward, no select/add/copy chain backward."""
+
+    @staticmethod
+    def forward(ctx, logits, viewport, translation, target_depth, target_mask, z_span, eps, width, height):
+        _need_cuda(logits, viewport, translation, target_depth, target_mask)
+        n, hh, p = logits.shape[0], logits.shape[1], logits.shape[-1]
+        lg = logits.detach()
+        vp = viewport.detach().float().contiguous()
+        tr = translation.detach().float().contiguous()
+        td = target_depth.detach().float().contiguous().view(height, width)
+        tm = target_mask.detach().float().contiguous().view(height, width)
+        desc = L.LossDesc(n, p, width, height, float(z_span), float(eps), hh, p * p * hh, 3)
+        sums = torch.empty(n, 8, device=lg.device)
+        terms = torch.empty(n, 4, device=lg.device)
+        base = lg.data_ptr()
+        _call('lf_pose_loss_fwd', L.lib().lf_pose_loss_fwd,
+              (ctypes.byref(desc), base, base + 4, _p(vp), tr.data_ptr() + 8, _p(td), _p(tm), _p(sums), _p(terms), _stream()),
+              kernels=3)
+        ctx.save_for_backward(lg, vp, tr, td, tm, sums)
+        ctx.cfg = (n, hh, p, width, height, float(z_span), float(eps))
+        return terms
+
+    @staticmethod
+    def backward(ctx, gterms):
+        lg, vp, tr, td, tm, sums = ctx.saved_tensors
+        _need_cuda(gterms, lg)
+        n, hh, p, width, height, z_span, eps = ctx.cfg
+        desc = L.LossDesc(n, p, width, height, z_span, eps, hh, p * p * hh, 3)
+        g_lg = torch.zeros_like(lg)                       # (same channels-last strides)
+        g_tr = torch.zeros_like(tr)
+        g_vp = torch.empty_like(vp)
+        gt = gterms.float().contiguous()
+        base, gbase = lg.data_ptr(), g_lg.data_ptr()
+        _call('lf_pose_loss_bwd', L.lib().lf_pose_loss_bwd,
+              (ctypes.byref(desc), base, base + 4, _p(vp), tr.data_ptr() + 8, _p(td), _p(tm), _p(sums), _p(gt),
+               gbase, gbase + 4, _p(g_vp), g_tr.data_ptr() + 8, _stream()))
+        return g_lg, g_vp, g_tr, None, None, None, None, None, None
+
+
+def pose_loss_terms_packed(logits, viewport, translation, target_depth, target_mask, z_span, eps=0.01, width=640, height=480):
+    """terms [N,4] straight from the decoder's logits [N,2,P,P] (depth, mask heads) and the translation [N,3]; falls back
+    to the de-interleaved form when the logits are not the fused heads' channels-last fp32 tensor."""
+    n, hh, p = logits.shape[0], logits.shape[1], logits.shape[-1]
+    if (logits.dim() == 4 and hh == 2 and logits.dtype == torch.float32 and logits.shape[2] == p
+            and logits.stride() == (p * p * hh, 1, p * hh, hh) and translation.dtype == torch.float32):
+        return _PoseLossPacked.apply(logits, viewport, translation, target_depth, target_mask, z_span, eps, width, height)
+    return _PoseLoss.apply(logits[:, 0], logits[:, 1], viewport, translation[:, 2], target_depth, target_mask, z_span, eps,
+                           width, height)
+
+
+def refine_record_(terms, w_rank, w_opt, lq, tr, rank, gterms, h_rank, h_optim, h_terms, h_lq, h_tr, slot, chunk, step_count):
+    """lf_refine_record: ranking / optimisation losses, d mean(optim)/d terms and the chunk-history snapshot in one launch."""
+    _need_cuda(terms, w_rank, w_opt, lq, tr, rank, gterms, h_rank, slot)
+    n, k = terms.shape
+    _call('lf_refine_record', L.lib().lf_refine_record,
+          (_p(terms), n, k, _p(w_rank), _p(w_opt), _p(lq), _p(tr), _p(rank), _p(gterms), _p(h_rank), _p(h_optim), _p(h_terms),
+           _p(h_lq), _p(h_tr), slot.data_ptr(), int(chunk), _p(step_count) if step_count is not None else None, _stream()))
 
 
 @torch.no_grad()

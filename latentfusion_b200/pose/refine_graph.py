@@ -40,9 +40,11 @@ class _BatchedAdamPlateau:
         self.patience, self.threshold, self.factor = float(patience), float(threshold), float(factor)
 
     @torch.no_grad()
-    def step(self, rank_loss):
+    def step(self, rank_loss, counted=False):
+        """counted: the step counter was already advanced on the device (ops.refine_record_)"""
         if self.params[0].is_cuda:
-            self.step_count += 1
+            if not counted:
+                self.step_count += 1
             for p, m, v in zip(self.params, self.m, self.v):
                 ops.adam_step_(p, p.grad, m, v, self.step_count, self.lr, self.b1, self.b2, self.eps)
             ops.plateau_step_(rank_loss, self.lr, self.best, self.num_bad, self.threshold, self.patience, self.factor)
@@ -98,7 +100,19 @@ class GraphedRefiner:
         if self.use_latent:
             self.TERMS = GraphedRefiner.TERMS + ('latent',)
             self._set_target_inputs(target_obs, n)
-        self.sched_w = {k: torch.tensor(float(self.weights.get(k, 0.0)), device=dev) for k in estimator.loss_schedules}
+        # the four fused-head terms with static / scheduled weights: combined, differentiated and recorded by one kernel
+        # (ops.refine_record_).  Scheduled weights are 0-dim views into w_opt, refilled from the host before a replay.
+        ph = self.model.photographer
+        self.fast = bool(estimator.fused_loss and ph.predict_depth and ph.predict_mask and not ph.predict_color
+                         and not self.use_latent and z_obj.is_cuda)
+        self.w_rank = torch.tensor([float(self.weights.get(k, 0.0)) for k in self.TERMS[:4]], device=dev)
+        self.w_opt = self.w_rank.clone()
+        self.rank_buf = torch.zeros(n, device=dev)
+        self.gterms = torch.zeros(n, 4, device=dev)
+        if self.fast:
+            self.sched_w = {k: self.w_opt[self.TERMS.index(k)] for k in estimator.loss_schedules if k in self.TERMS[:4]}
+        else:
+            self.sched_w = {k: torch.tensor(float(self.weights.get(k, 0.0)), device=dev) for k in estimator.loss_schedules}
         # device history (one chunk)
         self.h_rank = torch.zeros(chunk, n, device=dev)
         self.h_optim = torch.zeros(chunk, n, device=dev)
@@ -138,6 +152,19 @@ class GraphedRefiner:
             p.grad = None
         cam = self._camera()
         ph = self.model.photographer
+        if self.fast:
+            logits, _, _ = ph.decode(self.z_obj, cam, interpret_logits=False, return_latent=False)
+            terms = ops.pose_loss_terms_packed(logits, cam.viewport, cam.translation, self.target.depth, self.target.mask,
+                                               cam.z_span, 0.01, cam.width, cam.height)
+            with torch.no_grad():
+                # rank / optim, d mean(optim)/d terms, the history snapshot (BEFORE the update: the reference ranks the
+                # cameras that produced this loss) and the optimiser's step counter
+                ops.refine_record_(terms, self.w_rank, self.w_opt, self.lq, self.tr, self.rank_buf, self.gterms,
+                                   self.h_rank, self.h_optim, self.h_terms, self.h_lq, self.h_tr, self.slot, self.chunk,
+                                   self.opt.step_count)
+            terms.backward(self.gterms)
+            self.opt.step(self.rank_buf, counted=True)
+            return
         if est.fused_loss and ph.predict_depth and ph.predict_mask and not ph.predict_color:
             # raw head outputs -> fused loss head (csrc/pose_loss.cu): no full-frame intermediates
             logits, latent, _ = ph.decode(self.z_obj, cam, interpret_logits=False, return_latent=self.use_latent)
@@ -170,7 +197,8 @@ class GraphedRefiner:
 
     def set_schedule_weights(self, step):
         for k, sched in self.est.loss_schedules.items():
-            self.sched_w[k].fill_(float(sched.get(step)))
+            if k in self.sched_w:
+                self.sched_w[k].fill_(float(sched.get(step)))
 
     @staticmethod
     def make_signature(est, z_obj, target_obs, cameras, chunk):

@@ -657,3 +657,68 @@ def test_latent_loss_refinement_graphed_equals_eager(g, dev):
     for (_, ca), (_, cb) in zip(a[2], b[2]):
         torch.testing.assert_close(ca.translation, cb.translation, atol=3e-4, rtol=1e-3)
         torch.testing.assert_close(ca.log_quaternion, cb.log_quaternion, atol=3e-4, rtol=1e-3)
+
+
+def test_packed_loss_head_record_kernel_and_block_gradient_match_the_unfused_forms(dev):
+    """the graph path's glue-free forms: (a) the loss head on the decoder's channels-last logits / translation through
+    lf_loss_desc strides == the de-interleaved call, values and all four gradient paths; (b) lf_refine_record == the
+    torch expressions it replaces; (c) lf_resample_o2c_bwd_cam_block == the 17-term gradient re-laid out."""
+    from latentfusion_b200 import _lib as L, ops
+    torch.manual_seed(3)
+    N, P, H, W = 5, 32, 48, 64
+    logits = torch.randn(N, 2, P, P, device=dev).contiguous(memory_format=torch.channels_last)
+    vp = torch.tensor([[10., 8., 50., 40.]], device=dev).repeat(N, 1) + torch.rand(N, 4, device=dev)
+    tr = torch.randn(N, 3, device=dev) * 0.1 + torch.tensor([0., 0., 1.5], device=dev)
+    td = (torch.rand(H, W, device=dev) > 0.3).float() * (1.4 + 0.2 * torch.rand(H, W, device=dev))
+    tm = (torch.rand(H, W, device=dev) > 0.5).float()
+    gt = torch.randn(N, 4, device=dev)
+    outs = []
+    for packed in (True, False):
+        lg, v, t = (x.clone().requires_grad_(True) for x in (logits, vp, tr))
+        if packed:
+            assert lg.stride() == (2 * P * P, 1, 2 * P, 2)
+            terms = ops.pose_loss_terms_packed(lg, v, t, td, tm, 0.5, 0.01, W, H)
+        else:
+            terms = ops.pose_loss_terms(lg[:, 0], lg[:, 1], v, t[:, 2], td, tm, 0.5, 0.01, W, H)
+        terms.backward(gt)
+        outs.append((terms.detach(), lg.grad, v.grad, t.grad))
+    for a, b in zip(*outs):
+        # same kernels, same per-pixel arithmetic; only the float atomics' arrival order differs
+        torch.testing.assert_close(a, b, atol=1e-5, rtol=1e-4)
+    # (b)
+    chunk, K = 4, 4
+    terms = torch.rand(N, K, device=dev)
+    w_rank = torch.tensor([1.0, 0.5, 0.25, 2.0], device=dev)
+    w_opt = torch.tensor([1.0, 0.0, 0.25, 3.0], device=dev)
+    lq, trn = torch.randn(N, 3, device=dev), torch.randn(N, 3, device=dev)
+    rank, gterms = torch.zeros(N, device=dev), torch.zeros(N, K, device=dev)
+    h_rank, h_opt = torch.zeros(chunk, N, device=dev), torch.zeros(chunk, N, device=dev)
+    h_terms = torch.zeros(chunk, K, N, device=dev)
+    h_lq, h_tr = torch.zeros(chunk, N, 3, device=dev), torch.zeros(chunk, N, 3, device=dev)
+    slot = torch.full((1,), 3, dtype=torch.long, device=dev)
+    steps = torch.zeros(1, device=dev)
+    ops.refine_record_(terms, w_rank, w_opt, lq, trn, rank, gterms, h_rank, h_opt, h_terms, h_lq, h_tr, slot, chunk, steps)
+    t_req = terms.clone().requires_grad_(True)
+    r_ref = sum(float(w_rank[k]) * t_req[:, k] for k in range(K))
+    o_ref = sum(float(w_opt[k]) * t_req[:, k] for k in range(K))
+    o_ref.mean().backward()
+    assert torch.equal(rank, r_ref.detach()) and torch.equal(h_rank[3], r_ref.detach()) and torch.equal(h_opt[3], o_ref.detach())
+    assert torch.equal(gterms, t_req.grad)
+    assert torch.equal(h_terms[3], terms.t()) and torch.equal(h_lq[3], lq) and torch.equal(h_tr[3], trn)
+    assert int(slot) == 0 and float(steps) == 1.0 and float(h_rank[:3].abs().sum()) == 0.0
+    # (c)
+    S, C, Nc = 16, 16, 3
+    cams, _ = ph.synthetic_cameras(Nc, S, seed=4)
+    blk = cams.to(dev).o2c_block(1.0).detach().contiguous()
+    vol = ops.to_cl(torch.randn(1, C, S, S, S, device=dev))
+    g = ops.to_cl(torch.randn(Nc, C, S, S, S, device=dev))
+    ws = torch.empty(L.lib().lf_resample_o2c_bwd_cam_ws(Nc, S), device=dev)
+    g17 = torch.empty(Nc, L.CAMGRAD_STRIDE, device=dev)
+    gblk = torch.full((Nc, L.CAM_STRIDE), float('nan'), device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    L.check(L.lib().lf_resample_o2c_bwd_cam(ops._p(g), ops._p(vol), ops._p(blk), ops._p(g17), ops._p(ws), 1, Nc, C, S, st), 'bwd_cam')
+    L.check(L.lib().lf_resample_o2c_bwd_cam_block(ops._p(g), ops._p(vol), ops._p(blk), ops._p(gblk), ops._p(ws), 1, Nc, C, S, st), 'bwd_cam_block')
+    ref = torch.zeros(Nc, L.CAM_STRIDE, device=dev)
+    ref[:, :16] = g17[:, :16]
+    ref[:, 20] = g17[:, 16]
+    assert torch.equal(gblk, ref)
