@@ -60,6 +60,12 @@ int lf_set_option(const char* name, int value);
  * out  [N][S][S][S][C] */
 int lf_resample_o2c_fwd(const float* vol, const float* cam, float* out,
                         int B, int N, int C, int S, void* stream);
+/* The same resample written straight into the split-planar activation layout of lf_split_pack (out_split:
+ * lf_split_bytes(N, S, S, S, C) bytes, zero halo included) for a following lf_conv3d_dz: no dense fp32 copy of the
+ * [N][S^3][C] volumes and no packing pass.  C in {16, 32, 64} (lf_resample_o2c_fwd_split_supported). */
+int lf_resample_o2c_fwd_split_supported(int C, int S);
+int lf_resample_o2c_fwd_split(const float* vol, const float* cam, void* out_split,
+                              int B, int N, int C, int S, void* stream);
 /* backward w.r.t. the camera block (the pose loop's gradient; replaces grid_sampler_3d_backward's
  * grad_grid + the autograd of geometry.py:469-531,:669-685).
  * grad_cam [N][LF_CAMGRAD_STRIDE]; workspace: lf_resample_o2c_bwd_cam_ws(N,S) floats. */

@@ -37,6 +37,8 @@ _SIGNATURES = {
     'lf_last_error': (ctypes.c_char_p, []),
     'lf_sm_count': (c_int, []),
     'lf_resample_o2c_fwd': (c_int, [c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_vp]),
+    'lf_resample_o2c_fwd_split_supported': (c_int, [c_int, c_int]),
+    'lf_resample_o2c_fwd_split': (c_int, [c_f32p, c_f32p, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     'lf_resample_o2c_bwd_cam_ws': (c_i64, [c_int, c_int]),
     'lf_resample_o2c_bwd_cam': (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_vp]),
     'lf_resample_o2c_bwd_cam_block': (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_vp]),

@@ -13,6 +13,7 @@
 //
 // HBM traffic (algorithmic): fwd 4*C*S^3*(B + N) bytes; bwd_cam 4*C*S^3*(N + B); bwd_vol same.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace lf {
 
@@ -304,7 +305,15 @@ __device__ __forceinline__ void stcs_f8(float4* p, const float4& a, const float4
 }
 
 // W = float4s per lane (1: 128-bit accesses, C = 4*LPV; 2: 256-bit accesses, C = 8*LPV)
-template <int MODE, int LPVL, int MINB, int W>
+// SPLIT (object->camera, W = 1): `out` is the library's split-planar activation layout ([hi|lo][N*S planes][C/8][S+2][S+2][8]
+// bf16, what the depth-batched convolution stages with bulk TMA) instead of dense fp32: the first camera-block
+// convolution then needs no packing pass (268 MB read + 285 MB written per pose-loop iteration at config B).  Same bytes
+// written as fp32; each lane stores its 4 channels as 8 bytes of the hi part and 8 bytes of the lo part; the zero halo is
+// laid down by split_halo_zero_kernel.  Measured at config B: 182 us (with the halo kernel) against 100 us for the dense
+// form + 100 us for lf_split_pack — the 8-byte pieces land in 8 planes per warp step, twice the store wavefronts of one
+// 512-byte run, on a kernel whose L1 data pipe is already a co-limiter — so the Photographer only uses it on request
+// (LFB200_O2C_SPLIT=1); it halves the HBM traffic of the pair but not its time.
+template <int MODE, int LPVL, int MINB, int W, bool SPLIT = false>
 __global__ void __launch_bounds__(256, MINB)
 resample_march_kernel(const float* __restrict__ vol, const float* __restrict__ cam, float* __restrict__ out,
                       int views_per_obj, int N, int S, int KC) {
@@ -347,6 +356,18 @@ resample_march_kernel(const float* __restrict__ vol, const float* __restrict__ c
     float4* op = reinterpret_cast<float4*>(out + ((((int64_t)n * S + k0) * S + jc) * S + ic) * C) + sub * W;
     const int64_t ostep = (int64_t)S * S * LPV * W;        // float4 units per depth step
     const int slot = g * (LPV + 1) + sub;
+    // split-planar output: channel chunk sub/2 of plane (n, k), padded position (jc+1, ic+1), half (sub&1) of its 16 bytes
+    uint16_t* sp = nullptr;
+    int64_t sp_step = 0, sp_part = 0;
+    if (SPLIT) {
+        constexpr int KCH = C / 8;
+        const int Wp = S + 2;
+        const int64_t PP = (int64_t)(S + 2) * Wp;
+        sp_part = (int64_t)N * S * C * PP;
+        sp_step = (int64_t)KCH * PP * 8;
+        sp = reinterpret_cast<uint16_t*>(out) + ((((int64_t)n * S + k0) * KCH + (sub >> 1)) * PP + (int64_t)(jc + 1) * Wp + (ic + 1)) * 8
+             + (sub & 1) * 4;
+    }
 
     // ---- phase 1: lane (g, sub) prepares depth step kr + sub of column g
     auto prepare = [&](int kr) {
@@ -428,10 +449,17 @@ resample_march_kernel(const float* __restrict__ vol, const float* __restrict__ c
                 for (int h = 0; h < W; ++h) Vec<4>::fma(acc[h], w[q], val[q][h]);
             }
             if (col_ok) {
-                if (W == 1) __stcs(op, acc[0]);
+                if (SPLIT) {
+                    uint32_t h0, l0, h1, l1;
+                    tcx::split_bf16x2(acc[0].x, acc[0].y, h0, l0);
+                    tcx::split_bf16x2(acc[0].z, acc[0].w, h1, l1);
+                    *reinterpret_cast<uint2*>(sp) = make_uint2(h0, h1);
+                    *reinterpret_cast<uint2*>(sp + sp_part) = make_uint2(l0, l1);
+                } else if (W == 1) __stcs(op, acc[0]);
                 else stcs_f8(op, acc[0], acc[W - 1]);
             }
             op += ostep;
+            if (SPLIT) sp += sp_step;
         }
         __syncwarp();
     }
@@ -864,6 +892,42 @@ static int launch_march(const float* vol, const float* cam, float* out, int vpo,
     LF_RETURN_LAUNCH();
 }
 
+// zero halo of a split-planar volume: per (plane, channel chunk, part) the rows yp = 0 / h+1 and the columns xp = 0 / w+1
+__global__ void split_halo_zero_kernel(uint16_t* __restrict__ out, int64_t part_elems, int64_t planes_kc, int h, int w) {
+    const int Wp = w + 2, HN = 2 * Wp + 2 * h;
+    const int64_t PP = (int64_t)(h + 2) * Wp;
+    const int64_t total = planes_kc * 2 * HN;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int e = (int)(idx % HN);
+        const int64_t r = idx / HN;
+        const int part = (int)(r & 1);
+        const int64_t pk = r >> 1;
+        int q;
+        if (e < Wp) q = e;                                            // top row
+        else if (e < 2 * Wp) q = (h + 1) * Wp + (e - Wp);             // bottom row
+        else if (e < 2 * Wp + h) q = (e - 2 * Wp + 1) * Wp;           // left column
+        else q = (e - 2 * Wp - h + 1) * Wp + (w + 1);                 // right column
+        *reinterpret_cast<uint4*>(out + part * part_elems + (pk * PP + q) * 8) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+template <int LPVL>
+static int launch_march_split(const float* vol, const float* cam, void* out, int vpo, int N, int S, cudaStream_t st) {
+    constexpr int LPV = 1 << LPVL, G = 32 / LPV, C = 4 * LPV;
+    const int64_t cols = (int64_t)N * ((S + 2 * G - 1) / (2 * G)) * ((S + 3) / 4);
+    int KC = (S + LPV - 1) / LPV * LPV;
+    while (KC > LPV && KC > 16 && cols * ((S + KC - 1) / KC) < 12ll * sm_count()) KC = ((KC / 2) + LPV - 1) / LPV * LPV;
+    const int64_t blocks = cols * ((S + KC - 1) / KC);
+    LF_CHECK_ARG(blocks < (1ll << 31), "resample: too many columns");
+    const int64_t PP = (int64_t)(S + 2) * (S + 2);
+    const int64_t planes_kc = (int64_t)N * S * (C / 8);
+    const int64_t halo = planes_kc * 2 * (2 * (S + 2) + 2 * S);
+    split_halo_zero_kernel<<<(unsigned)((halo + 255) / 256 > 4096 ? 4096 : (halo + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<uint16_t*>(out), (int64_t)N * S * C * PP, planes_kc, S, S);
+    resample_march_kernel<0, LPVL, 3, 1, true><<<(unsigned)blocks, 256, 0, st>>>(vol, cam, reinterpret_cast<float*>(out), vpo, N, S, KC);
+    LF_RETURN_LAUNCH();
+}
+
 // LFB200_RESAMPLE_BRICK=1 selects the brick kernel for every shape (A/B timing and the cross-check test)
 static bool use_march() { return option(OPT_RESAMPLE_BRICK) != 1; }
 
@@ -920,6 +984,25 @@ extern "C" int lf_resample_o2c_fwd(const float* vol, const float* cam, float* ou
     if (int e = check_common(vol, cam, out, N, C, S)) return e;
     LF_CHECK_ARG(B > 0 && N % B == 0, "o2c: N=%d must be a multiple of B=%d", N, B);
     return launch_fwd<0>(vol, cam, out, N / B, N, C, S, (cudaStream_t)stream);
+}
+
+extern "C" int lf_resample_o2c_fwd_split_supported(int C, int S) {
+    return (C == 16 || C == 32 || C == 64) && S > 1 && (int64_t)S * S * S * (C / 4) < (1ll << 32) &&
+           (int64_t)(S + 2) * (S + 2) < (1 << 20);
+}
+
+extern "C" int lf_resample_o2c_fwd_split(const float* vol, const float* cam, void* out_split, int B, int N, int C, int S,
+                                         void* stream) {
+    if (int e = check_common(vol, cam, out_split, N, C, S)) return e;
+    LF_CHECK_ARG(B > 0 && N % B == 0, "o2c: N=%d must be a multiple of B=%d", N, B);
+    if (!lf_resample_o2c_fwd_split_supported(C, S)) {
+        set_error("o2c_fwd_split: needs C in {16, 32, 64} (got C=%d S=%d)", C, S);
+        return LF_EUNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 16) return launch_march_split<2>(vol, cam, out_split, N / B, N, S, st);
+    if (C == 32) return launch_march_split<3>(vol, cam, out_split, N / B, N, S, st);
+    return launch_march_split<4>(vol, cam, out_split, N / B, N, S, st);
 }
 
 extern "C" int lf_resample_o2c_bwd_vol(const float* gout, const float* cam, float* gvol, int B, int N, int C, int S, void* stream) {

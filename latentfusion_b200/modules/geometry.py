@@ -471,11 +471,12 @@ class ObjectToCameraTransform(BaseTransformBlock):
             raise ValueError("only padding_mode='border' is implemented (all the path uses)")
         self.padding_mode = padding_mode
 
-    def forward(self, obj_volume, camera: Camera):
+    def forward(self, obj_volume, camera: Camera, split_only=False):
+        """split_only (internal, see ops.resample_o2c): the caller's single reader stages the split-planar form."""
         if camera.length % obj_volume.shape[0] != 0:
             raise ValueError(f"number of cameras ({camera.length}) must be a multiple of the number of "
                              f"object volumes ({obj_volume.shape[0]})")
-        return ops.resample_o2c(obj_volume, camera.o2c_block(self.cube_size))
+        return ops.resample_o2c(obj_volume, camera.o2c_block(self.cube_size), split_only=split_only)
 
 
 class _Projection(nn.Module):

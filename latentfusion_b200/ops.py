@@ -127,8 +127,10 @@ def empty_cl(shape, device):
 class _ResampleO2C(torch.autograd.Function):
     """ObjectToCameraTransform (reference modules/geometry.py:669-690)."""
 
+    last_split = None     # split_only: the SplitVol that holds the result (the returned dense tensor is NOT written)
+
     @staticmethod
-    def forward(ctx, vol, cam):
+    def forward(ctx, vol, cam, split_only=False):
         _need_cuda(vol, cam)
         vol = to_cl(vol)
         cam = cam.detach().float().contiguous()
@@ -139,8 +141,17 @@ class _ResampleO2C(torch.autograd.Function):
         if cam.shape[1] != L.CAM_STRIDE:
             raise ValueError("camera block must be [N, LF_CAM_STRIDE]")
         out = empty_cl((N, C, S, S, S), vol.device)
-        _call('lf_resample_o2c_fwd', L.lib().lf_resample_o2c_fwd, (_p(vol), _p(cam), _p(out), B, N, C, S, _stream()),
-              nbytes=4 * C * S ** 3 * (B + N))
+        _ResampleO2C.last_split = None
+        if split_only:
+            # the volumes go straight into the split-planar layout the consumer's TMA staging reads; `out` only carries
+            # the shape and the autograd edge (the caller guarantees its single reader is that convolution)
+            sv = SplitVol.empty(N, C, S, S, S, vol.device)
+            _call('lf_resample_o2c_fwd', L.lib().lf_resample_o2c_fwd_split,
+                  (_p(vol), _p(cam), _p(sv.buf), B, N, C, S, _stream()), kernels=2, nbytes=4 * C * S ** 3 * (B + N))
+            _ResampleO2C.last_split = sv
+        else:
+            _call('lf_resample_o2c_fwd', L.lib().lf_resample_o2c_fwd, (_p(vol), _p(cam), _p(out), B, N, C, S, _stream()),
+                  nbytes=4 * C * S ** 3 * (B + N))
         ctx.save_for_backward(vol, cam)
         return out
 
@@ -163,7 +174,7 @@ class _ResampleO2C(torch.autograd.Function):
             _call('lf_resample_o2c_bwd_cam', L.lib().lf_resample_o2c_bwd_cam_block,
                   (_p(gout), _p(vol), _p(cam), _p(gcam), _p(ws), B, N, C, S, _stream()), kernels=2,
                   nbytes=4 * C * S ** 3 * (B + N))
-        return gvol, gcam
+        return gvol, gcam, None
 
 
 class _ResampleC2O(torch.autograd.Function):
@@ -202,8 +213,34 @@ class _ResampleC2O(torch.autograd.Function):
         return gvol, None
 
 
-def resample_o2c(vol, cam_block):
-    return _ResampleO2C.apply(vol, cam_block)
+def resample_o2c(vol, cam_block, split_only=False):
+    """split_only: the result is written ONLY in split-planar form (attached as `_lf_split`, which eq_conv's depth-batched
+    path stages from); the dense tensor returned is uninitialised.  For callers that know the single reader is such a
+    convolution (o2c_split_ok) — the Photographer's first camera block in the pose loop."""
+    out = _ResampleO2C.apply(vol, cam_block, bool(split_only))
+    if _ResampleO2C.last_split is not None:
+        out._lf_split = _ResampleO2C.last_split
+        _ResampleO2C.last_split = None
+    return out
+
+
+def o2c_split_ok(channels, size, n_cams, conv):
+    """may the object->camera volumes feeding `conv` (an EqualizedConv3d) exist in split-planar form only?  Yes when that
+    convolution runs on the depth-batched tcgen05 kernel (which stages the split form and never reads the dense tensor)
+    and its weights are frozen (a weight gradient would want the dense input)."""
+    if _O2C_SPLIT_OFF or getattr(conv, 'ndim', 0) != 3:
+        return False
+    w = conv.module.weight
+    if w.dim() != 5 or w.shape[-1] != 3 or w.shape[1] != channels:
+        return False
+    if torch.is_grad_enabled() and (w.requires_grad or (conv.bias is not None and conv.bias.requires_grad)):
+        return False
+    precision = conv.precision if conv.precision is not None else _default_precision
+    if precision not in (1, 2, 3):
+        return False
+    desc = _desc(KIND_CONV, 3, n_cams, size, size, size, channels, w.shape[0], 3, 1.0, False, 0.0, False,
+                 1 if precision == 3 else precision)
+    return _dz_ok(desc) and bool(L.lib().lf_resample_o2c_fwd_split_supported(channels, size))
 
 
 def resample_c2o(vol, cam_block):
@@ -278,6 +315,10 @@ def _unpack_weight_grad(gw, weight_shape, kind, depth):
 
 _bwd_precision_override = None     # dev/experiments: force the precision of every bwd-data convolution
 _FUSE_BWD = _os.environ.get('LFB200_FUSE_BWD', '0') == '1'
+# K1 writing the split-planar layout itself (lf_resample_o2c_fwd_split) instead of dense fp32 + lf_split_pack: measured
+# at config B 182 us against 100 + 100 us (the 8-byte pieces of 8 planes double the kernel's store wavefronts, and its L1
+# data pipe was already the co-limiter) -> 352.5 vs 352.8 iters/s, no gain, so it stays opt-in (LFB200_O2C_SPLIT=1)
+_O2C_SPLIT_OFF = _os.environ.get('LFB200_O2C_SPLIT', '0') != '1'
 _TC_PACK_CACHE = {}
 
 

@@ -18,7 +18,7 @@ from torch.nn import functional as F
 
 from .. import ops
 from ..modules import unet, EqualizedConv3d
-from ..modules.blocks import create_blocks, OutputBlock3d, OutputBlock2d
+from ..modules.blocks import create_blocks, Block, OutputBlock3d, OutputBlock2d
 from ..modules.geometry import (TileProjection2d3d, FactorProjection2d3d, CameraToObjectTransform, Camera,
                                 ObjectToCameraTransform, FactorProjection3d2d)
 from ..three import b2bv, bv2b
@@ -240,7 +240,13 @@ class Photographer(_Checkpointable, nn.Module):
             if self.skip_connections and depth > 0:
                 z = torch.cat((z, z_obj_mid[-depth - 1]), dim=1)
             z = block(z)
-        z = self.transform_block(z, camera)                 # the single cube is read through L2 by every camera
+        # the single cube is read through L2 by every camera.  In the pose loop (frozen weights, no skip tensors to
+        # concatenate) the frustum volumes' only reader is the first camera block's depth-batched convolution, which stages
+        # the split-planar layout: K1 then writes that layout directly and the dense fp32 copy never exists.
+        first = self.camera_blocks[0] if len(self.camera_blocks) else None
+        split_only = bool(z.is_cuda and not self.skip_connections and isinstance(first, Block)
+                          and ops.o2c_split_ok(z.shape[1], z.shape[-1], len(camera), first.conv1))
+        z = self.transform_block(z, camera, split_only=split_only)
         for depth, block in enumerate(self.camera_blocks):
             if self.skip_connections:
                 z = torch.cat((z, z_cam_mid[-depth - 1]), dim=1)

@@ -722,3 +722,26 @@ def test_packed_loss_head_record_kernel_and_block_gradient_match_the_unfused_for
     ref[:, :16] = g17[:, :16]
     ref[:, 20] = g17[:, 16]
     assert torch.equal(gblk, ref)
+
+
+@pytest.mark.parametrize('C,S,N', [(32, 24, 3), (16, 17, 2), (64, 8, 2)])
+def test_o2c_resample_straight_into_split_planar_layout(dev, C, S, N):
+    """K1 writing the consumer's split-planar layout (hi | lo bf16 planes with a zero halo) == lf_split_pack of its dense
+    fp32 output, bit for bit (same fp32 values, same rounding split), into a buffer that starts as garbage."""
+    from latentfusion_b200 import _lib as L, ops
+    cams, _ = ph.synthetic_cameras(N, S, seed=C + S)
+    blk = cams.to(dev).o2c_block(1.0).detach().contiguous()
+    torch.manual_seed(S)
+    vol = ops.to_cl(torch.randn(1, C, S, S, S, device=dev))
+    dense = ops.resample_o2c(vol, blk)
+    want = ops.split_pack(dense)
+    assert L.lib().lf_resample_o2c_fwd_split_supported(C, S)
+    got = ops.SplitVol.empty(N, C, S, S, S, dev)
+    got.buf.fill_(0x7fc1)                                        # NaN bit patterns: every element must be overwritten
+    L.check(L.lib().lf_resample_o2c_fwd_split(ops._p(vol), ops._p(blk), ops._p(got.buf), 1, N, C, S,
+                                              torch.cuda.current_stream().cuda_stream), 'o2c_fwd_split')
+    assert torch.equal(got.buf, want.buf)
+    # and through the public op: the twin rides on the returned tensor
+    out = ops.resample_o2c(vol, blk, split_only=True)
+    assert torch.equal(out._lf_split.buf, want.buf)
+    torch.testing.assert_close(out._lf_split.to_dense(), dense, atol=0, rtol=2 ** -15)
