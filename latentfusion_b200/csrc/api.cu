@@ -28,7 +28,7 @@ int sm_count() {
 }
 
 static const char* kOptName[OPT_COUNT] = {"LFB200_TC_DC", "LFB200_TC_DEBUG", "LFB200_TC_NO_DUAL", "LFB200_RESAMPLE_KC",
-                                           "LFB200_RESAMPLE_W", "LFB200_RESAMPLE_BRICK", "LFB200_BWDCAM"};
+                                           "LFB200_RESAMPLE_W", "LFB200_RESAMPLE_BRICK", "LFB200_BWDCAM", "LFB200_TC_NO_TRI"};
 static int g_opt[OPT_COUNT];
 static bool g_opt_loaded = false;
 

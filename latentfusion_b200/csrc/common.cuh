@@ -31,7 +31,7 @@ void set_error(const char* fmt, ...);
 
 int sm_count();
 // Tuning / A-B switches: read from the environment ONCE (first use), overridable through lf_set_option (tests, tools).
-enum Option { OPT_TC_DC, OPT_TC_DEBUG, OPT_TC_NO_DUAL, OPT_RESAMPLE_KC, OPT_RESAMPLE_W, OPT_RESAMPLE_BRICK, OPT_BWDCAM, OPT_COUNT };
+enum Option { OPT_TC_DC, OPT_TC_DEBUG, OPT_TC_NO_DUAL, OPT_RESAMPLE_KC, OPT_RESAMPLE_W, OPT_RESAMPLE_BRICK, OPT_BWDCAM, OPT_TC_NO_TRI, OPT_COUNT };
 int option(Option o);
 
 // torch.linspace(a, b, n)[i] exactly as ATen evaluates it (symmetric two-sided formula).

@@ -59,6 +59,11 @@ struct Params {
     int pass_mode;
     int nprod, nmma;           // producer / MMA-issuer warp counts (nprod + nmma + 4 == 16)
     int dual, ncols;           // dual: B = [W_hi | W_lo] (N = 2*cout_pad): one pass yields x_hi*W_hi + x_hi*W_lo; ncols = MMA N
+    // tri (with dual): the whole bf16x3 product in ONE pass.  Every ring slot holds the hi slab followed (slab_half bytes
+    // further) by the lo slab of the same plane; per tap and k-step the issuer adds x_lo * W_hi (an N = cout_pad MMA on
+    // the first cout_pad rows of the dual weight tile, idesc2) to x_hi * [W_hi | W_lo].  The input is read once instead
+    // of twice and the output is written once instead of write + read-modify-write.
+    int tri; uint32_t slab_half, idesc2;
     uint32_t idesc;
     uint32_t slab_bytes, w_bytes;
     int debug;                    // dev only (LFB200_TC_DEBUG): 1 skip MMAs, 2 skip producer work, 4 skip epilogue work
@@ -422,6 +427,14 @@ conv_tc_kernel(const __grid_constant__ Params p) {
 #pragma unroll
                         for (int j = 0; j < kBatch; ++j) {
                             if (udst[j] < 0) continue;
+                            if (p.tri) {
+                                const uint32_t h0 = cvt_bf16x2(v[j].x, v[j].y), h1 = cvt_bf16x2(v[j].z, v[j].w);
+                                const uint32_t l0 = cvt_bf16x2(v[j].x - __uint_as_float(h0 << 16), v[j].y - __uint_as_float(h0 & 0xffff0000u));
+                                const uint32_t l1 = cvt_bf16x2(v[j].z - __uint_as_float(h1 << 16), v[j].w - __uint_as_float(h1 & 0xffff0000u));
+                                *reinterpret_cast<uint2*>(slab + udst[j]) = make_uint2(h0, h1);
+                                *reinterpret_cast<uint2*>(slab + p.slab_half + udst[j]) = make_uint2(l0, l1);
+                                continue;
+                            }
                             const uint32_t lo = pack_bf16x2(v[j].x, v[j].y, p.a_part);
                             const uint32_t hi = pack_bf16x2(v[j].z, v[j].w, p.a_part);
                             *reinterpret_cast<uint2*>(slab + udst[j]) = make_uint2(lo, hi);
@@ -507,6 +520,7 @@ conv_tc_kernel(const __grid_constant__ Params p) {
             // MMA asm would otherwise force a constant reload (LDCU, ~40 cycles) on every loop test
             const int K = p.k, HZ = p.hz, NT = p.NT, RING = p.ring, DEPTH = p.d, DBG = p.debug;
             const uint32_t PP = (uint32_t)p.P, IDESC = p.idesc, COUT_PAD = (uint32_t)p.ncols, SLAB = p.slab_bytes;
+            const uint32_t TRI = (uint32_t)p.tri, IDESC2 = p.idesc2, HALF16 = p.slab_half >> 4;
             for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
                 const int dchunk = item % p.ndchunks;
                 const int d0 = dchunk * p.DC, d1 = min(p.d, d0 + p.DC);
@@ -539,7 +553,10 @@ conv_tc_kernel(const __grid_constant__ Params p) {
                                 for (int dx = 0; dx < K; ++dx) {
                                     uint32_t ak = a_cur, bk = b_cur;
                                     for (int ks = 0; ks < ksteps; ++ks) {
-                                        if (!(DBG & 1) && elect_one()) umma_bf16_lohi(d_tmem, ak, desc_hi, bk, desc_hi, IDESC, acc);
+                                        if (!(DBG & 1) && elect_one()) {
+                                            umma_bf16_lohi(d_tmem, ak, desc_hi, bk, desc_hi, IDESC, acc);
+                                            if (TRI) umma_bf16_lohi(d_tmem, ak + HALF16, desc_hi, bk, desc_hi, IDESC2, 1u);
+                                        }
                                         acc = 1;
                                         ak += a_kstride; bk += b_kstride;
                                     }
@@ -633,10 +650,10 @@ static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 struct Plan {
     int cin_pad, cout_pad, P, R, NT, pos_alloc, ring, DC, nstrips, ndchunks, taps;
-    uint32_t slab_bytes, w_bytes, smem_bytes;
+    uint32_t slab_bytes, w_bytes, smem_bytes, slab_half;
 };
 
-static bool make_plan(const lf_conv_desc* d, Plan& pl, bool dual = false) {
+static bool make_plan(const lf_conv_desc* d, Plan& pl, bool dual = false, bool tri = false) {
     if (!(d->ndim == 2 || d->ndim == 3)) return false;
     if (!(d->k == 1 || d->k == 3)) return false;
     if (d->cin % 4 != 0) return false;
@@ -663,7 +680,7 @@ static bool make_plan(const lf_conv_desc* d, Plan& pl, bool dual = false) {
     for (int R = min(d->h, (nt_max * 128) / pl.P); R >= 1; --R) {
         int pos = (R + 2 * halo) * pl.P + 2 * halo;
         pos = round_up(pos - 4, 8) + 4;                 // pos_alloc == 4 (mod 8): conflict-free producer stores
-        const uint32_t slab = (uint32_t)(pl.cin_pad / 8) * pos * 16;
+        const uint32_t slab = (uint32_t)(pl.cin_pad / 8) * pos * 16 * (tri ? 2u : 1u);
         if ((uint64_t)slab * pl.ring + pl.w_bytes <= budget && ((uint32_t)pos * 16 >> 4) < 16384) { best_R = R; break; }
     }
     if (best_R == 0) return false;
@@ -676,7 +693,8 @@ static bool make_plan(const lf_conv_desc* d, Plan& pl, bool dual = false) {
     pl.NT = (pl.R * pl.P + 127) / 128;
     int pos = (pl.R + 2 * halo) * pl.P + 2 * halo;
     pl.pos_alloc = round_up(pos - 4, 8) + 4;
-    pl.slab_bytes = (uint32_t)(pl.cin_pad / 8) * pl.pos_alloc * 16;
+    pl.slab_half = (uint32_t)(pl.cin_pad / 8) * pl.pos_alloc * 16;
+    pl.slab_bytes = pl.slab_half * (tri ? 2u : 1u);
     pl.smem_bytes = pl.slab_bytes * pl.ring + pl.w_bytes + 256 + 1024;
     // the last tile may read up to (NT*128 + (k-1)*P + k-1 - pos_alloc) positions past a k-chunk: it must stay
     // inside the allocation; chunks are followed by other chunks / the weight buffer, check the very last one
@@ -717,8 +735,10 @@ int conv_tc_launch(const lf_conv_desc* d, const float* x, const float* w, const 
 // one kernel launch: `wpk` points at the packed weight region to use (hi, lo or dual)
 static int conv_tc_launch_pass(const lf_conv_desc* d, const tc::Plan& pl, const float* x, const uint16_t* wpk,
                                const float* bias, float* y, float* rnorm, const TcPrologue* pro, int a_part,
-                               int mode, int dual, cudaStream_t st, const TcEpilogue* epi = nullptr) {
+                               int mode, int dual, cudaStream_t st, const TcEpilogue* epi = nullptr, int tri = 0) {
     tc::Params p;
+    p.tri = tri; p.slab_half = pl.slab_half;
+    p.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(pl.cout_pad >> 3) << 17) | ((128u >> 4) << 24);
     p.epi_y = epi ? epi->y : nullptr; p.epi_r = epi ? epi->rnorm : nullptr;
     p.epi_act = epi ? epi->act : 0; p.epi_norm = epi ? epi->norm : 0; p.epi_slope = epi ? epi->slope : 1.f;
     if (epi) LF_CHECK_ARG((d->cout & 3) == 0 && pl.cout_pad <= 32 && (mode == tc::PASS_ONLY || mode == tc::PASS_LAST),
@@ -773,6 +793,12 @@ int conv_tc_launch_ex(const lf_conv_desc* d, const float* x, const float* w, con
     const size_t part = (size_t)pl.w_bytes / 2;
     if (d->precision == 2) return conv_tc_launch_pass(d, pl, x, wbase, bias, y, rnorm, pro, 0, tc::PASS_ONLY, 0, st, epi);
     const bool no_dual = option(OPT_TC_NO_DUAL) != 0;
+    if (!no_dual && option(OPT_TC_NO_TRI) == 0 && pro == nullptr && d->ndim == 2 && (d->cout & 3) == 0 && pl.cout_pad <= 64) {
+        // 2-D layers: the whole bf16x3 product in one launch (hi and lo slabs staged side by side)
+        tc::Plan pt;
+        if (tc::make_plan(d, pt, true, true))
+            return conv_tc_launch_pass(d, pt, x, wbase + 2 * part, bias, y, rnorm, nullptr, 0, tc::PASS_ONLY, 1, st, epi, 1);
+    }
     if (!no_dual && pro == nullptr && (d->cout & 3) == 0 && pl.cout_pad <= 64) {
         // bf16x3 in TWO passes: x_hi * [W_hi | W_lo] (one N = 2*Cout MMA per tap: the A tile is fetched from shared
         // memory once for both products), then x_lo * W_hi accumulated in the epilogue
@@ -873,6 +899,7 @@ extern "C" int lf_conv_tc_passes(const lf_conv_desc* desc) {
     if (desc->precision == 2) return 1;
     if (option(OPT_TC_NO_DUAL) == 0 && (desc->cout & 3) == 0 && pl.cout_pad <= 64) {
         tc::Plan pd;
+        if (option(OPT_TC_NO_TRI) == 0 && desc->ndim == 2 && tc::make_plan(desc, pd, true, true)) return 1;
         if (tc::make_plan(desc, pd, true)) return 2;
     }
     return 3;
