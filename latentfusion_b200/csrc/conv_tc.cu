@@ -100,6 +100,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
            (int)blockIdx.x, (int)threadIdx.x, bar, parity);
     __trap();
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine (UBLKCP), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -351,25 +359,27 @@ conv_tc_kernel(const __grid_constant__ Params p) {
     float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxRing + 6);     // [cout_pad], zero padded
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxRing);
     const uint32_t bar_accf = smem_u32(bars + 2 * kMaxRing), bar_acce = smem_u32(bars + 2 * kMaxRing + 2);
+    const uint32_t bar_w = smem_u32(bars + 2 * kMaxRing + 5);           // packed weights have landed (bulk TMA)
 
     // warp index broadcast from lane 0 so the compiler knows it is warp-uniform: everything derived from it
     // (tile id, TMEM/descriptor addresses) can then live in uniform registers, which UTCHMMA consumes directly
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
 
-    // ---- one-time setup: weights -> smem, barriers, TMEM
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(p.wpk);
-        uint4* dst = reinterpret_cast<uint4*>(smem + (size_t)p.ring * p.slab_bytes);
-        for (uint32_t i = threadIdx.x; i < p.w_bytes / 16; i += kThreads) dst[i] = __ldg(src + i);
-        fence_proxy_async();
-        for (int i = threadIdx.x; i < p.cout_pad; i += kThreads)
-            bias_s[i] = (p.bias != nullptr && i < p.cout) ? p.bias[i] : 0.f;
-    }
+    // ---- one-time setup: barriers, TMEM, bias; the packed weights come in by bulk TMA while the producers already
+    //      stage the first slab (the issuers wait on bar_w before their first MMA)
+    for (int i = threadIdx.x; i < p.cout_pad; i += kThreads)
+        bias_s[i] = (p.bias != nullptr && i < p.cout) ? p.bias[i] : 0.f;
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.ring; ++i) { mbar_init(bar_full + 8 * i, p.nprod * 32); mbar_init(bar_empty + 8 * i, p.nmma); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8 * i, p.nmma); mbar_init(bar_acce + 8 * i, 32 * kEpiWarps); }
+        mbar_init(bar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_arrive_expect_tx(bar_w, p.w_bytes);
+        for (uint32_t off = 0; off < p.w_bytes; off += 32768u) {
+            const uint32_t nb = p.w_bytes - off < 32768u ? p.w_bytes - off : 32768u;
+            bulk_g2s(wsm + off, reinterpret_cast<const uint8_t*>(p.wpk) + off, nb, bar_w);
+        }
     }
     const int NPROD = p.nprod, NMMA = p.nmma;
     if (warp == NPROD) {
@@ -521,6 +531,7 @@ conv_tc_kernel(const __grid_constant__ Params p) {
             const int K = p.k, HZ = p.hz, NT = p.NT, RING = p.ring, DEPTH = p.d, DBG = p.debug;
             const uint32_t PP = (uint32_t)p.P, IDESC = p.idesc, COUT_PAD = (uint32_t)p.ncols, SLAB = p.slab_bytes;
             const uint32_t TRI = (uint32_t)p.tri, IDESC2 = p.idesc2, HALF16 = p.slab_half >> 4;
+            mbar_wait(bar_w, 0);
             for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
                 const int dchunk = item % p.ndchunks;
                 const int d0 = dchunk * p.DC, d1 = min(p.d, d0 + p.DC);
@@ -685,9 +696,20 @@ static bool make_plan(const lf_conv_desc* d, Plan& pl, bool dual = false, bool t
     }
     if (best_R == 0) return false;
     if (hz == 0) {
-        // 2-D layers have no depth to chunk: shrink the strips until there are enough work items for the machine
+        // 2-D layers have no depth to chunk; the strip height trades halo re-reads and per-item latency against the
+        // number of rounds the persistent CTAs make.  Cost model (in staged positions): rounds x (staged positions of
+        // one item + ~800 for its fixed fill / MMA / drain latency).  E.g. 8 maps of 64^2: R = 2 gave 256 items = two
+        // rounds on 148 SMs with half-empty second M-tiles; R = 4 is 128 items, one round.
         const int sms = sm_count();
-        while (best_R > 2 && (int64_t)d->n * ((d->h + best_R - 1) / best_R) < 2 * sms) best_R = (best_R + 1) / 2;
+        int64_t best_cost = -1;
+        int pick = best_R;
+        for (int R = best_R; R >= (best_R < 2 ? best_R : 2); --R) {
+            const int64_t items = (int64_t)d->n * ((d->h + R - 1) / R);
+            const int64_t rounds = (items + sms - 1) / sms;
+            const int64_t cost = rounds * ((int64_t)(R + 2 * halo) * pl.P + 800);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; pick = R; }
+        }
+        best_R = pick;
     }
     pl.R = best_R;
     pl.NT = (pl.R * pl.P + 127) / 128;
