@@ -45,46 +45,96 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason sampler running during the timed region."""
+    """SM clock / throttle-reason sampler for the timed region.  The region is short (K x ~2.7 ms), so the `nvidia-smi`
+    loop (the recipe's clocks line, 20 ms period) is armed BEFORE the warm-up — its start-up takes longer than the whole
+    region — and only the rows that arrive between start() and stop() count; the same NVML counters are also read
+    in-process every ~2 ms (pynvml) so that the window always holds samples."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+        self.nvml_rows, self.nvml_thread, self.nvml_stop = [], None, threading.Event()
 
-    def start(self):
+    def arm(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml_thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.nvml_thread.start()
+        except Exception:
+            self.nvml_thread = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.time(), [c.strip() for c in line.split(',')]))
+
+    def _poll_nvml(self):
+        n = self.nvml
+        while not self.nvml_stop.is_set():
+            try:
+                self.nvml_rows.append((time.time(), n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM),
+                                       n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)))
+            except Exception:
+                return
+            time.sleep(0.002)
+
+    def start(self):
+        if self.proc is None and self.nvml_thread is None:
+            self.arm()
+        self.t0 = time.time()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        clocks = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        self.t1 = time.time()
+        self.nvml_stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        if self.proc is None and self.nvml_thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        inside = lambda t: self.t0 <= t <= self.t1 + 0.02
+        rows = [r for t, r in self.rows if inside(t) and len(r) >= 7]
+        clocks = [float(r[0]) for r in rows if r[0].replace('.', '').isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 7:
-                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
-                    if v.lower().startswith('active'):
-                        reasons.add(name)
-        smax = next((float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()), None)
+        for r in rows:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        smax = next((float(r[1]) for _, r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()), None)
+        n_smi = len(clocks)
+        nv = [(c, m) for t, c, m in self.nvml_rows if inside(t)]
+        if nv:
+            n = self.nvml
+            clocks += [float(c) for c, _ in nv]
+            bits = (('hw_slowdown', 'nvmlClocksEventReasonHwSlowdown'), ('hw_thermal_slowdown', 'nvmlClocksEventReasonHwThermalSlowdown'),
+                    ('sw_thermal_slowdown', 'nvmlClocksEventReasonSwThermalSlowdown'), ('sw_power_cap', 'nvmlClocksEventReasonSwPowerCap'))
+            for name, attr in bits:
+                bit = getattr(n, attr, None)
+                if bit is not None and any(m & bit for _, m in nv):
+                    reasons.add(name)
+            if smax is None:
+                try:
+                    smax = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
+                except Exception:
+                    pass
         return {"sm_mhz": statistics.median(clocks) if clocks else None, "sm_max_mhz": smax,
-                "reasons": sorted(reasons), "samples": len(clocks)}
+                "reasons": sorted(reasons), "samples": len(clocks), "samples_nvidia_smi": n_smi, "samples_nvml": len(nv),
+                "window_ms": round(1000.0 * (self.t1 - self.t0), 1)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -299,10 +349,12 @@ def run_ours(args):
     # L2 hygiene: the per-step working set (8 cubes x 268 MB activations) is >> 126 MB L2, so every
     # iteration streams from HBM; no explicit flush is needed (stated in config.l2).
     # ---------------- device-resident number ("value") ----------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.arm()                                             # (nvidia-smi needs longer to start than the region lasts)
     est = estimation.load_from_config(cfg, model, num_iters=args.warmup)
     est.estimate(z_obj, target_dev, camera=hyp_full.to(dev))      # W warm-up iterations (captures the loop body once)
     est.num_iters = args.steps
-    sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
