@@ -65,6 +65,8 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            import atexit
+            atexit.register(lambda p=self.proc: p.poll() is None and p.kill())     # never leave the loop running behind us
         except Exception:
             self.proc = None
         try:
