@@ -159,7 +159,8 @@ int64_t lf_conv_tc_weight_bytes(int taps, int cin, int cout);
 int lf_conv_tc_pack_weights(const float* w_packed /* [taps][Cin][Cout] fp32 */, void* out,
                             int taps, int cin, int cout, void* stream);
 int lf_conv_tc_supported(const lf_conv_desc* desc);
-/* kernel launches of lf_conv_fwd on the tcgen05 path for this descriptor: 1 bf16, 2|3 bf16x3; 0 = not covered */
+/* kernel launches of lf_conv_fwd on the tcgen05 path for this descriptor: 1 (bf16, and bf16x3 of 2-D layers whose hi and
+ * lo slabs fit side by side: the one-pass form), 2|3 (bf16x3 otherwise); 0 = not covered */
 int lf_conv_tc_passes(const lf_conv_desc* desc);
 /* Backward-data of a Block conv with the PixelNorm/LeakyReLU backward (lf_actnorm_bwd) fused into the operand
  * staging of the tcgen05 kernel: gx = conv_T(du) * scale with du = LeakyReLU'(y) * PixelNorm^T(gy) never written

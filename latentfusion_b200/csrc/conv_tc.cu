@@ -15,9 +15,13 @@
 //   * Accumulators live in TMEM (double buffered, NT tiles x Cout columns each); one elected thread issues
 //     the MMAs; 4 epilogue warps read TMEM with tcgen05.ld (one output position = one thread = all Cout
 //     channels in registers, so PixelNorm is a thread-local reduction) and write channels-last fp32.
-//   * Precision: operands are bf16, accumulation fp32.  "bf16x3" (precision 1) runs three passes
-//     hi*hi + lo*hi + hi*lo (x = hi + lo, both bf16) accumulating in the fp32 output => ~2^-16 relative
-//     per product, i.e. fp32-parity grade; "bf16" (precision 2) is the single hi*hi pass.
+//   * Precision: operands are bf16, accumulation fp32.  "bf16x3" (precision 1) is hi*hi + lo*hi + hi*lo
+//     (x = hi + lo, both bf16) => ~2^-16 relative per product, i.e. fp32-parity grade; "bf16" (precision 2) is the
+//     single hi*hi product.  2-D layers do all three products in ONE launch (Params::tri: hi and lo slabs side by
+//     side in every ring slot, x_hi * [W_hi | W_lo] as one N = 2*Cout MMA and x_lo * W_hi as an N = Cout MMA on the
+//     same weight tile, both accumulator halves summed in the epilogue); 3-D layers that reach this kernel and
+//     layers too large for that run two passes (dual weights) or three, accumulating in the fp32 output.
+//   * The packed weights arrive by one bulk-TMA copy (cp.async.bulk + mbarrier) while the producers stage the first slab.
 //
 // Pipelines (mbarriers): slab_full/slab_empty[ring] (producers <-> MMA), acc_full/acc_empty[2] (MMA <-> epilogue).
 // Every wait is bounded: a pipeline bug traps instead of hanging the GPU.
